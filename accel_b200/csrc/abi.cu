@@ -1,0 +1,300 @@
+// extern "C" surface declared in include/accel_b200.h.  No C++ exception leaves this file.
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/accel_b200.h"
+#include "graph.h"
+
+using namespace accel;
+
+struct AccelHandle {
+  AccelConfig cfg;
+  Graph* graph;
+  std::string err;
+  const char* stage_names[32];
+  std::vector<std::pair<std::string, float>> stages;
+};
+
+static std::string g_create_err;
+static std::mutex g_mu;
+
+#define ACCEL_TRY try {
+#define ACCEL_CATCH(h)                                                        \
+  }                                                                           \
+  catch (const std::bad_alloc&) { if (h) (h)->err = "out of host memory"; return 2; } \
+  catch (const std::exception& e) { if (h) (h)->err = e.what(); return 3; }  \
+  catch (...) { if (h) (h)->err = "unknown C++ exception"; return 4; }
+
+extern "C" int accel_create(const AccelConfig* config, AccelHandle** out) {
+  AccelHandle* h = nullptr;
+  try {
+    if (!config || !out) { std::lock_guard<std::mutex> l(g_mu); g_create_err = "null argument"; return 1; }
+    h = new AccelHandle();
+    h->cfg = *config;
+    h->graph = new Graph(config->device, config->flags);
+    std::string err;
+    if (!build_accel(*h->graph, config->version, config->height, config->width, config->num_classes, &err)) {
+      std::lock_guard<std::mutex> l(g_mu);
+      g_create_err = err;
+      delete h->graph;
+      delete h;
+      return 1;
+    }
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    std::lock_guard<std::mutex> l(g_mu);
+    g_create_err = e.what();
+  } catch (...) {
+    std::lock_guard<std::mutex> l(g_mu);
+    g_create_err = "unknown C++ exception";
+  }
+  if (h) { delete h->graph; delete h; }
+  return 4;
+}
+
+extern "C" void accel_destroy(AccelHandle* h) {
+  if (!h) return;
+  try {
+    delete h->graph;
+    delete h;
+  } catch (...) {
+  }
+}
+
+extern "C" const char* accel_last_error(const AccelHandle* h) {
+  if (h) return h->err.c_str();
+  std::lock_guard<std::mutex> l(g_mu);
+  static thread_local std::string copy;
+  copy = g_create_err;
+  return copy.c_str();
+}
+
+extern "C" int accel_param_count(const AccelHandle* h) { return h ? (int)h->graph->params().size() : -1; }
+
+extern "C" int accel_param_info(const AccelHandle* h, int index, const char** name, int64_t shape[4], int* ndim) {
+  if (!h || index < 0 || index >= (int)h->graph->params().size()) return 1;
+  const ParamSpec& p = h->graph->params()[index];
+  if (name) *name = p.name.c_str();
+  if (ndim) *ndim = (int)p.shape.size();
+  if (shape)
+    for (size_t i = 0; i < 4; ++i) shape[i] = i < p.shape.size() ? p.shape[i] : 1;
+  return 0;
+}
+
+extern "C" int accel_set_param(AccelHandle* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!name || !data || !shape) { h->err = "null argument"; return 1; }
+  return h->graph->set_param(name, data, shape, ndim, &h->err) ? 0 : 1;
+  ACCEL_CATCH(h)
+}
+
+extern "C" int accel_finalize(AccelHandle* h) {
+  if (!h) return 1;
+  ACCEL_TRY
+  return h->graph->finalize(&h->err) ? 0 : 1;
+  ACCEL_CATCH(h)
+}
+
+static int check_stream_error(AccelHandle* h) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    h->err = std::string("CUDA error: ") + cudaGetErrorString(e);
+    return 5;
+  }
+  return 0;
+}
+
+extern "C" int accel_key_forward(AccelHandle* h, const float* data, float* feat_out, float* score_out,
+                                 uint8_t* label_out, void* stream) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!data) { h->err = "accel_key_forward: data is NULL"; return 1; }
+  void* ext[X_COUNT] = {nullptr};
+  ext[X_DATA] = (void*)data;
+  ext[X_FEAT_OUT] = feat_out;
+  ext[X_SCORE_OUT] = score_out;
+  ext[X_LABEL_OUT] = label_out;
+  if (!h->graph->run("key", ext, (cudaStream_t)stream, &h->err)) return 1;
+  return check_stream_error(h);
+  ACCEL_CATCH(h)
+}
+
+extern "C" int accel_cur_forward(AccelHandle* h, const float* data, const float* data_key, const float* feat_key,
+                                 float* feat_out, float* score_out, uint8_t* label_out, void* stream) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!data || !data_key || !feat_key) { h->err = "accel_cur_forward: data, data_key and feat_key are required"; return 1; }
+  void* ext[X_COUNT] = {nullptr};
+  ext[X_DATA] = (void*)data;
+  ext[X_DATA_KEY] = (void*)data_key;
+  ext[X_FEAT_KEY] = (void*)feat_key;
+  ext[X_FEAT_OUT] = feat_out;
+  ext[X_SCORE_OUT] = score_out;
+  ext[X_LABEL_OUT] = label_out;
+  if (!h->graph->run("cur", ext, (cudaStream_t)stream, &h->err)) return 1;
+  return check_stream_error(h);
+  ACCEL_CATCH(h)
+}
+
+extern "C" int accel_flownet(AccelHandle* h, const float* data, const float* data_key, float* flow_out, void* stream) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!data || !data_key || !flow_out) { h->err = "accel_flownet: null argument"; return 1; }
+  void* ext[X_COUNT] = {nullptr};
+  ext[X_DATA] = (void*)data;
+  ext[X_DATA_KEY] = (void*)data_key;
+  ext[X_FLOW_OUT] = flow_out;
+  if (!h->graph->run("flow", ext, (cudaStream_t)stream, &h->err)) return 1;
+  return check_stream_error(h);
+  ACCEL_CATCH(h)
+}
+
+extern "C" int accel_last_launch_count(const AccelHandle* h) { return h ? h->graph->last_launches() : -1; }
+
+extern "C" int accel_set_profiling(AccelHandle* h, int enabled) {
+  if (!h) return 1;
+  h->graph->set_profiling(enabled != 0);
+  return 0;
+}
+
+extern "C" int accel_stage_times(AccelHandle* h, const char** names, float* ms, int cap) {
+  if (!h) return -1;
+  try {
+    h->stages = h->graph->stage_times();
+    int n = 0;
+    for (auto& kv : h->stages) {
+      if (n >= cap) break;
+      names[n] = kv.first.c_str();
+      ms[n] = kv.second;
+      ++n;
+    }
+    return n;
+  } catch (...) {
+    return -1;
+  }
+}
+
+// ---- operator-level entry points -------------------------------------------------------------------
+
+static int no_device(char* err, int errlen) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    if (err && errlen > 0) snprintf(err, errlen, "no CUDA device: accel_b200 has no CPU fallback");
+    cudaGetLastError();
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" int accel_warp(const float* feat, const float* flow, float* out, int channels, int height, int width,
+                          void* stream) {
+  if (!feat || !flow || !out || channels <= 0 || height <= 0 || width <= 0 || feat == out) return 1;
+  if (no_device(nullptr, 0)) return 6;
+  WarpParams P{};
+  P.feat = feat; P.flow = flow; P.C = channels; P.H = height; P.W = width; P.out_nchw = out;
+  return launch_warp(P, (cudaStream_t)stream) == cudaSuccess ? 0 : 5;
+}
+
+extern "C" int accel_fuse_argmax(const float* score_a, const float* score_b, const float* corr_weight,
+                                 const float* corr_bias, int num_classes, int h, int w, uint8_t* label,
+                                 float* score_full, void* stream) {
+  if (!score_a || !label || num_classes < 1 || num_classes > 32 || h <= 0 || w <= 0) return 1;
+  if (no_device(nullptr, 0)) return 6;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* src = score_a;
+  float* fused = nullptr;
+  if (corr_weight) {
+    if (!score_b) return 1;
+    if (cudaMallocAsync((void**)&fused, (size_t)num_classes * h * w * sizeof(float), st) != cudaSuccess) return 5;
+    FuseParams F{};
+    F.a = score_a; F.b = score_b; F.w = corr_weight; F.out = fused; F.K = num_classes; F.h = h; F.w_ = w;
+    if (launch_fuse_lowres(F, st) != cudaSuccess) return 5;
+    src = fused;
+  }
+  TailParams T{};
+  T.score = src; T.bias = corr_bias; T.K = num_classes; T.h = h; T.w = w; T.factor = 16;
+  T.label = label; T.score_out = score_full;
+  cudaError_t e = launch_tail(T, st);
+  if (fused) cudaFreeAsync(fused, st);
+  return e == cudaSuccess ? 0 : 5;
+}
+
+extern "C" int accel_conv_layer(int kind, const float* in, int cin, int hin, int win, const float* weight, int cout,
+                                int ksize, int stride, int pad, int dilate, int deform_groups, const float* offset,
+                                const float* scale, const float* shift, int act, const float* residual, int engine,
+                                float* out, int device, char* err, int errlen) {
+  auto fail = [&](const std::string& m, int code) {
+    if (err && errlen > 0) snprintf(err, errlen, "%s", m.c_str());
+    return code;
+  };
+  try {
+    if (!in || !weight || !out) return fail("null argument", 1);
+    if (no_device(err, errlen)) return 6;
+    Graph g(device, engine == 1 ? 1 : 0);
+    std::vector<Op>& s = g.seq("layer");
+    const int x = g.new_tensor(cin, hin, win);
+    g.to_split(s, X_DATA, x);
+    EpiSpec e;
+    e.bn = "post";          // scale/shift travel as a BatchNorm with mean 0, var 1-eps
+    e.eps = 0.f;
+    e.act = act;
+    int y;
+    int ho, wo;
+    if (kind == 0) {
+      ho = (hin + 2 * pad - (dilate * (ksize - 1) + 1)) / stride + 1;
+      wo = (win + 2 * pad - (dilate * (ksize - 1) + 1)) / stride + 1;
+    } else if (kind == 1) {
+      ho = 2 * hin; wo = 2 * win;
+    } else {
+      ho = hin; wo = win;
+    }
+    if (residual) {
+      const int r = g.new_tensor(cout, ho, wo);
+      g.to_split(s, X_AUX_IN, r);
+      e.res = r;
+    }
+    if (kind == 0) {
+      y = g.conv(s, "layer", x, "w", cout, ksize, stride, pad, dilate, e);
+    } else if (kind == 1) {
+      y = g.deconv4(s, "layer", x, "w", cout, e);
+    } else {
+      if (!offset || ksize != 3 || stride != 1 || pad != 2 || dilate != 2) return fail("deformable test hook: 3x3, stride 1, pad 2, dilate 2 and an offset tensor are required", 1);
+      const int off = g.new_tensor(deform_groups * 18, hin, win, true);
+      g.copy_f32(s, X_FEAT_KEY, off);
+      y = g.dcn(s, "layer", x, off, "w", cout, deform_groups, e);
+    }
+    if (engine != 0)
+      for (auto& op : s)
+        if (op.type == OP_CONV) op.engine = engine;
+    g.to_nchw(s, y, X_AUX_OUT);
+    std::string msg;
+    std::vector<float> ones(cout, 1.f), zeros(cout, 0.f);
+    const int64_t c1[1] = {cout};
+    int64_t wshape[4] = {cout, cin, ksize, ksize};
+    if (kind == 1) { wshape[0] = cin; wshape[1] = cout; wshape[2] = wshape[3] = 4; }
+    bool ok = g.set_param("w_weight", weight, wshape, 4, &msg) &&
+              g.set_param("post_gamma", scale ? scale : ones.data(), c1, 1, &msg) &&
+              g.set_param("post_beta", shift ? shift : zeros.data(), c1, 1, &msg) &&
+              g.set_param("post_moving_mean", zeros.data(), c1, 1, &msg) &&
+              g.set_param("post_moving_var", ones.data(), c1, 1, &msg);
+    if (!ok) return fail(msg, 1);
+    void* ext[X_COUNT] = {nullptr};
+    ext[X_DATA] = (void*)in;
+    ext[X_AUX_IN] = (void*)residual;
+    ext[X_AUX_OUT] = out;
+    ext[X_FEAT_KEY] = (void*)offset;
+    if (!g.run("layer", ext, 0, &msg)) return fail(msg, 1);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()), 5);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(e.what(), 3);
+  } catch (...) {
+    return fail("unknown C++ exception", 4);
+  }
+}

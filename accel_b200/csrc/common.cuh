@@ -1,0 +1,186 @@
+// Shared device-side types for the Accel hot-path kernels (sm_100a only).
+//
+// Internal activation format ("split fp16"): every activation tensor is NHWC with two fp16 planes,
+// hi = rn16(x) and lo = rn16(x - hi), so hi + lo carries ~22 mantissa bits.  The tensor-core convs
+// consume the planes directly (fp16x3: hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM), the
+// CUDA-core kernels add them back to fp32 on load.  fp32 NCHW only exists at the C-ABI boundary
+// (frames, feat_key / feat_out, score volumes) -- the layouts the reference's Predictor exchanges
+// (dff_deeplab/core/tester.py:32-35, demo.py:184).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace accel {
+
+enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+
+constexpr int kMaxTaps = 25;   // 5x5 is the largest generic kernel (FlowNet conv2/conv3); 7x7 stems are separate
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_LEAKY) return v > 0.f ? v : v * 0.1f;   // LeakyReLU(slope=0.1), ...flownet_deeplab.py:1755
+  return v;
+}
+
+__device__ __forceinline__ void split_f32(float v, __half& hi, __half& lo) {
+  float c = fminf(fmaxf(v, -65504.f), 65504.f);
+  hi = __float2half_rn(c);
+  lo = __float2half_rn(c - __half2float(hi));
+}
+
+struct alignas(16) Half8 {
+  __half2 v[4];
+};
+
+// 8 consecutive channels of one pixel: hi + lo -> fp32
+__device__ __forceinline__ void load8(const __half* hi, const __half* lo, float out[8]) {
+  Half8 a = *reinterpret_cast<const Half8*>(hi);
+  Half8 b = *reinterpret_cast<const Half8*>(lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 fa = __half22float2(a.v[i]);
+    float2 fb = __half22float2(b.v[i]);
+    out[2 * i] = fa.x + fb.x;
+    out[2 * i + 1] = fa.y + fb.y;
+  }
+}
+
+__device__ __forceinline__ void store8(__half* hi, __half* lo, const float v[8]) {
+  Half8 a, b;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half h0, l0, h1, l1;
+    split_f32(v[2 * i], h0, l0);
+    split_f32(v[2 * i + 1], h1, l1);
+    a.v[i] = __halves2half2(h0, h1);
+    b.v[i] = __halves2half2(l0, l1);
+  }
+  *reinterpret_cast<Half8*>(hi) = a;
+  *reinterpret_cast<Half8*>(lo) = b;
+}
+
+struct alignas(8) Half4 {
+  __half2 v[2];
+};
+
+__device__ __forceinline__ void load4(const __half* hi, const __half* lo, float out[4]) {
+  Half4 a = *reinterpret_cast<const Half4*>(hi);
+  Half4 b = *reinterpret_cast<const Half4*>(lo);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float2 fa = __half22float2(a.v[i]);
+    float2 fb = __half22float2(b.v[i]);
+    out[2 * i] = fa.x + fb.x;
+    out[2 * i + 1] = fa.y + fb.y;
+  }
+}
+
+__device__ __forceinline__ void store4(__half* hi, __half* lo, const float v[4]) {
+  Half4 a, b;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    __half h0, l0, h1, l1;
+    split_f32(v[2 * i], h0, l0);
+    split_f32(v[2 * i + 1], h1, l1);
+    a.v[i] = __halves2half2(h0, h1);
+    b.v[i] = __halves2half2(l0, l1);
+  }
+  *reinterpret_cast<Half4*>(hi) = a;
+  *reinterpret_cast<Half4*>(lo) = b;
+}
+
+// What every conv-like kernel does with an accumulator once the contraction is finished:
+//   v = acc * scale[c] + shift[c]  (+ residual)  -> act  -> out (split NHWC) and/or out_nchw (fp32)
+//   out2 = act2(v * scale2[c] + shift2[c])           (pre-activation ResNets: next unit's bn1+relu)
+// Output pixel (y, x) of the kernel's own loop space lands at (y*osy + ooy, x*osx + oox) of the full
+// output map (OHf x OWf); transposed-conv phases use osy = osx = 2.
+struct Epilogue {
+  const float* scale;
+  const float* shift;
+  int act;
+  const __half* res_hi;
+  const __half* res_lo;
+  int res_ld;
+  __half* out_hi;
+  __half* out_lo;
+  int out_ld;
+  const float* scale2;
+  const float* shift2;
+  int act2;
+  __half* out2_hi;
+  __half* out2_lo;
+  int out2_ld;
+  float* out_nchw;
+  int osy, osx, ooy, oox;
+  int OHf, OWf;
+  int Cout;
+};
+
+// Applies the epilogue to NV (4 or 8) consecutive channels [c0, c0+NV) of full-map pixel `pix`.
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const Epilogue& e, int pix, int c0, float v[NV]) {
+  float r[NV];
+  if (e.res_hi) {
+    if (NV == 8) load8(e.res_hi + (size_t)pix * e.res_ld + c0, e.res_lo + (size_t)pix * e.res_ld + c0, r);
+    else load4(e.res_hi + (size_t)pix * e.res_ld + c0, e.res_lo + (size_t)pix * e.res_ld + c0, r);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = c0 + i;
+    float x = 0.f;
+    if (c < e.Cout) {
+      float s = e.scale ? e.scale[c] : 1.f;
+      float b = e.shift ? e.shift[c] : 0.f;
+      x = fmaf(v[i], s, b);
+      if (e.res_hi) x += r[i];
+      x = apply_act(x, e.act);
+    }
+    v[i] = x;
+  }
+  if (e.out_hi) {
+    if (NV == 8) store8(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
+    else store4(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
+  }
+  if (e.out_nchw) {
+    size_t plane = (size_t)e.OHf * e.OWf;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (c0 + i < e.Cout) e.out_nchw[(size_t)(c0 + i) * plane + pix] = v[i];
+  }
+  if (e.out2_hi) {
+    float w[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = c0 + i;
+      float x = 0.f;
+      if (c < e.Cout) x = apply_act(fmaf(v[i], e.scale2[c], e.shift2[c]), e.act2);
+      w[i] = x;
+    }
+    if (NV == 8) store8(e.out2_hi + (size_t)pix * e.out2_ld + c0, e.out2_lo + (size_t)pix * e.out2_ld + c0, w);
+    else store4(e.out2_hi + (size_t)pix * e.out2_ld + c0, e.out2_lo + (size_t)pix * e.out2_ld + c0, w);
+  }
+}
+
+// Geometry + operands of one convolution-like contraction over the internal format.
+//   out[y, x, n] = sum_t sum_c in[y*stride + dy[t], x*stride + dx[t], c] * w[n][t*Cin_pad + c]
+// Weights are packed K-major per output channel (rows of Kpad = ntaps*Cin_pad fp16, hi and lo planes),
+// rows padded to a multiple of 64 output channels and Cin_pad to a multiple of 64 with zeros.
+struct ConvParams {
+  const __half* in_hi;
+  const __half* in_lo;
+  int in_ld, Hin, Win, Cin;
+  const __half* w_hi;
+  const __half* w_lo;
+  int Kpad, Cin_pad, Cout_pad;
+  int ntaps;
+  int8_t dy[kMaxTaps];
+  int8_t dx[kMaxTaps];
+  int stride;
+  int Ho, Wo;          // loop space (== output size except for transposed-conv phases)
+  int splits;          // split-K factor (1 = epilogue in-kernel)
+  float* partial;      // [splits][Ho*Wo][Cout_pad] fp32 when splits > 1
+  Epilogue epi;
+};
+
+}  // namespace accel

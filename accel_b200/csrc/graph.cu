@@ -1,0 +1,856 @@
+// Plan builder / executor.  See graph.h.
+#include "graph.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace accel {
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+Graph::~Graph() {
+  for (auto& kv : seqs_)
+    for (auto& op : kv.second)
+      if (op.tc) tc_plan_destroy(op.tc);
+  for (void* p : allocs_) cudaFree(p);
+  for (auto e : events_) cudaEventDestroy(e);
+}
+
+int Graph::new_tensor(int C, int H, int W, bool f32) {
+  Buffer b;
+  Tensor t;
+  t.C = C; t.H = H; t.W = W; t.f32 = f32;
+  t.ld = f32 ? C : round_up(C, 8);
+  b.f32 = f32;
+  b.elems = (size_t)H * W * t.ld;
+  bufs_.push_back(b);
+  t.buf = (int)bufs_.size() - 1;
+  tensors_.push_back(t);
+  return (int)tensors_.size() - 1;
+}
+
+int Graph::new_view(int base, int coff, int C) {
+  Tensor t = tensors_[base];
+  t.coff = tensors_[base].coff + coff;
+  t.C = C;
+  tensors_.push_back(t);
+  return (int)tensors_.size() - 1;
+}
+
+int Graph::add_param(const std::string& name, std::vector<int64_t> shape) {
+  auto it = param_index_.find(name);
+  if (it != param_index_.end()) return it->second;
+  params_.push_back({name, std::move(shape)});
+  param_index_[name] = (int)params_.size() - 1;
+  return (int)params_.size() - 1;
+}
+
+static void add_bn_params(Graph& g, const std::string& bn, int c) {
+  g.add_param(bn + "_gamma", {c});
+  g.add_param(bn + "_beta", {c});
+  g.add_param(bn + "_moving_mean", {c});
+  g.add_param(bn + "_moving_var", {c});
+}
+
+static void register_epi_params(Graph& g, const EpiSpec& e, int cout) {
+  if (!e.bn.empty()) add_bn_params(g, e.bn, cout);
+  if (!e.bias.empty()) g.add_param(e.bias, {cout});
+  if (!e.bn2.empty()) add_bn_params(g, e.bn2, cout);
+}
+
+int Graph::stem(std::vector<Op>& s, const std::string& stage, int ext0, int ext1, int Hs, int Ws, bool pool,
+                float in_mul, const std::string& bn_in, const std::string& wname, int cin, EpiSpec e) {
+  Op op{};
+  op.type = OP_STEM;
+  op.stage = stage;
+  op.name = wname;
+  op.ext_in0 = ext0;
+  op.ext_in1 = ext1;
+  op.weight = wname + "_weight";
+  op.bn_in = bn_in;
+  op.stem_pool = pool ? 1 : 0;
+  op.stem_in_mul = in_mul;
+  op.cout = 64;
+  op.ksize = 7;
+  const int Hc = pool ? Hs / 2 : Hs, Wc = pool ? Ws / 2 : Ws;
+  const int Ho = (Hc + 6 - 7) / 2 + 1, Wo = (Wc + 6 - 7) / 2 + 1;
+  if (!bn_in.empty()) add_bn_params(*this, bn_in, cin);      // declared before the conv weight, as the symbol does
+  add_param(op.weight, {64, cin, 7, 7});
+  register_epi_params(*this, e, 64);
+  op.epi = e;
+  op.in = cin;            // stems carry the channel count here
+  op.stem.Hs = Hs;
+  op.stem.Ws = Ws;
+  op.out = new_tensor(64, Ho, Wo);
+  op.flops = 2.0 * 64 * cin * 49 * Ho * Wo;
+  s.push_back(op);
+  return op.out;
+}
+
+int Graph::conv(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname, int cout, int k,
+                int stride, int pad, int dil, EpiSpec e, int out) {
+  const Tensor ti = tensors_[in];
+  Op op{};
+  op.type = OP_CONV;
+  op.stage = stage;
+  op.name = wname;
+  op.kind = 0;
+  op.in = in;
+  op.weight = wname + "_weight";
+  op.cout = cout; op.ksize = k; op.stride = stride; op.pad = pad; op.dilate = dil;
+  add_param(op.weight, {cout, ti.C, k, k});
+  register_epi_params(*this, e, cout);
+  const int Ho = (ti.H + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;
+  const int Wo = (ti.W + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;
+  if (out < 0 && !e.no_split_out) out = new_tensor(cout, Ho, Wo);
+  op.out = out;
+  op.epi = e;
+  op.flops = 2.0 * cout * ti.C * k * k * Ho * Wo;
+  op.conv.Ho = Ho;
+  op.conv.Wo = Wo;
+  s.push_back(op);
+  return out;
+}
+
+int Graph::deconv4(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname, int cout,
+                   EpiSpec e, int out) {
+  const Tensor ti = tensors_[in];
+  add_param(wname + "_weight", {ti.C, cout, 4, 4});
+  register_epi_params(*this, e, cout);
+  if (out < 0) out = new_tensor(cout, 2 * ti.H, 2 * ti.W);
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      Op op{};
+      op.type = OP_CONV;
+      op.stage = stage;
+      op.name = wname;
+      op.kind = 1;
+      op.phase_y = py; op.phase_x = px;
+      op.in = in;
+      op.out = out;
+      op.weight = wname + "_weight";
+      op.cout = cout; op.ksize = 4; op.stride = 1;
+      op.epi = e;
+      op.flops = 2.0 * cout * ti.C * 4 * ti.H * ti.W;
+      op.conv.Ho = ti.H;
+      op.conv.Wo = ti.W;
+      s.push_back(op);
+    }
+  return out;
+}
+
+int Graph::dcn(std::vector<Op>& s, const std::string& stage, int in, int offset_f32, const std::string& wname,
+               int cout, int dg, EpiSpec e) {
+  const Tensor ti = tensors_[in];
+  const int col = new_tensor(9 * ti.C, ti.H, ti.W);
+  Op g{};
+  g.type = OP_DCN_COL;
+  g.stage = stage;
+  g.name = wname + "(im2col)";
+  g.in = in; g.in2 = offset_f32; g.out = col; g.dg = dg; g.dilate = 2; g.pad = 2;
+  s.push_back(g);
+  Op op{};
+  op.type = OP_CONV;
+  op.stage = stage;
+  op.name = wname;
+  op.kind = 2;
+  op.in = col;
+  op.weight = wname + "_weight";
+  op.cout = cout; op.ksize = 3; op.stride = 1;
+  add_param(op.weight, {cout, ti.C, 3, 3});
+  register_epi_params(*this, e, cout);
+  op.out = new_tensor(cout, ti.H, ti.W);
+  op.epi = e;
+  op.flops = 2.0 * cout * ti.C * 9 * ti.H * ti.W;
+  op.conv.Ho = ti.H;
+  op.conv.Wo = ti.W;
+  s.push_back(op);
+  return op.out;
+}
+
+void Graph::require_bilinear(const std::string& name, int num_classes) {
+  add_param(name, {num_classes, 1, 32, 32});
+  bilinear_checks_.push_back(name);
+}
+
+int Graph::pool(std::vector<Op>& s, const std::string& stage, int in, int k, int stride, int pad, bool is_max,
+                bool full, EpiSpec post) {
+  const Tensor ti = tensors_[in];
+  auto osz = [&](int n) {
+    const int num = n + 2 * pad - k;
+    int o = (full ? (num + stride - 1) / stride : num / stride) + 1;
+    if (full && (o - 1) * stride >= n + pad) --o;
+    return o;
+  };
+  Op op{};
+  op.type = OP_POOL;
+  op.stage = stage;
+  op.name = is_max ? "maxpool" : "avgpool";
+  op.in = in;
+  op.ksize = k; op.stride = stride; op.pad = pad; op.pool_max = is_max ? 1 : 0;
+  op.epi = post;
+  register_epi_params(*this, post, ti.C);
+  op.out = new_tensor(ti.C, osz(ti.H), osz(ti.W));
+  s.push_back(op);
+  return op.out;
+}
+
+void Graph::warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, int ext_out) {
+  Op op{};
+  op.type = OP_WARP;
+  op.stage = "warp";
+  op.name = "warping_feat";
+  op.ext_in0 = ext_feat;
+  op.in = flow_f32;
+  op.out = out_split;
+  op.ext_out = ext_out;
+  s.push_back(op);
+}
+
+void Graph::upflow(std::vector<Op>& s, int flow_f32, const std::string& wname, const std::string& bname,
+                   int out_view) {
+  Op op{};
+  op.type = OP_UPFLOW;
+  op.stage = "flownet";
+  op.name = wname;
+  op.in = flow_f32;
+  op.out = out_view;
+  op.weight = wname + "_weight";
+  op.weight2 = bname;
+  add_param(op.weight, {2, 2, 4, 4});
+  add_param(bname, {2});
+  s.push_back(op);
+}
+
+void Graph::fuse(std::vector<Op>& s, int a_f32, int b_f32, const std::string& wname, int out_f32) {
+  Op op{};
+  op.type = OP_FUSE;
+  op.stage = "tail";
+  op.name = wname;
+  op.in = a_f32; op.in2 = b_f32; op.out = out_f32;
+  op.weight = wname + "_weight";
+  const int K = tensors_[a_f32].C;
+  add_param(op.weight, {K, 2 * K, 1, 1});
+  s.push_back(op);
+}
+
+void Graph::tail(std::vector<Op>& s, int score_f32, const std::string& bias_name, int ext_label, int ext_score) {
+  Op op{};
+  op.type = OP_TAIL;
+  op.stage = "tail";
+  op.name = "upsample+argmax";
+  op.in = score_f32;
+  op.weight2 = bias_name;
+  if (!bias_name.empty()) add_param(bias_name, {tensors_[score_f32].C});
+  op.ext_out = ext_label;
+  op.ext_out2 = ext_score;
+  need_label_scratch((size_t)tensors_[score_f32].H * 16 * tensors_[score_f32].W * 16);
+  s.push_back(op);
+}
+
+void Graph::to_split(std::vector<Op>& s, int ext_in, int out) {
+  Op op{};
+  op.type = OP_TO_SPLIT;
+  op.stage = "io";
+  op.name = "nchw->split";
+  op.ext_in0 = ext_in;
+  op.out = out;
+  s.push_back(op);
+}
+
+void Graph::to_nchw(std::vector<Op>& s, int in, int ext_out) {
+  Op op{};
+  op.type = OP_TO_NCHW;
+  op.stage = "io";
+  op.name = "split->nchw";
+  op.in = in;
+  op.ext_out = ext_out;
+  s.push_back(op);
+}
+
+void Graph::copy_f32(std::vector<Op>& s, int ext_in, int out_f32) {
+  Op op{};
+  op.type = OP_COPY_F32;
+  op.stage = "io";
+  op.name = "copy";
+  op.ext_in0 = ext_in;
+  op.out = out_f32;
+  s.push_back(op);
+}
+
+// -------------------------------------------------------------------------------------------------
+bool Graph::set_param(const std::string& name, const float* data, const int64_t* shape, int ndim, std::string* err) {
+  auto it = param_index_.find(name);
+  if (it == param_index_.end()) {
+    *err = "unknown parameter '" + name + "'";
+    return false;
+  }
+  const ParamSpec& ps = params_[it->second];
+  bool ok = (int)ps.shape.size() == ndim;
+  size_t n = 1;
+  for (int i = 0; ok && i < ndim; ++i) {
+    ok = ps.shape[i] == shape[i];
+    n *= (size_t)shape[i];
+  }
+  if (!ok) {
+    *err = "shape mismatch for parameter '" + name + "'";     // cf. check_parameter_shapes, lib/utils/symbol.py:43-55
+    return false;
+  }
+  if (finalized_) {
+    *err = "parameters are frozen after accel_finalize";
+    return false;
+  }
+  host_[name].assign(data, data + n);
+  return true;
+}
+
+const std::vector<float>* Graph::host_param(const std::string& name, std::string* err) const {
+  auto it = host_.find(name);
+  if (it == host_.end()) {
+    *err = "parameter '" + name + "' was never set";
+    return nullptr;
+  }
+  return &it->second;
+}
+
+void* Graph::dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  allocs_.push_back(p);
+  return p;
+}
+
+float* Graph::upload(const std::vector<float>& v) {
+  float* d = (float*)dev_alloc(v.size() * sizeof(float));
+  if (d) cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+  return d;
+}
+
+static bool bn_fold(const Graph& g, const std::unordered_map<std::string, std::vector<float>>& host,
+                    const std::string& bn, float eps, bool fix_gamma, int c, std::vector<float>& scale,
+                    std::vector<float>& shift, std::string* err) {
+  const char* suf[4] = {"_gamma", "_beta", "_moving_mean", "_moving_var"};
+  const std::vector<float>* v[4];
+  for (int i = 0; i < 4; ++i) {
+    auto it = host.find(bn + suf[i]);
+    if (it == host.end() || (int)it->second.size() != c) {
+      *err = "parameter '" + bn + suf[i] + "' was never set";
+      return false;
+    }
+    v[i] = &it->second;
+  }
+  scale.resize(c);
+  shift.resize(c);
+  for (int i = 0; i < c; ++i) {
+    const float gamma = fix_gamma ? 1.f : (*v[0])[i];
+    const float inv = gamma / sqrtf((*v[3])[i] + eps);
+    scale[i] = inv;
+    shift[i] = (*v[1])[i] - (*v[2])[i] * inv;
+  }
+  (void)g;
+  return true;
+}
+
+bool Graph::make_scale_shift(const EpiSpec& e, int cout, const std::vector<float>& prescale, float** scale,
+                             float** shift, std::string* err) {
+  std::vector<float> sc(cout, 1.f), sh(cout, 0.f);
+  if (!e.bn.empty()) {
+    if (!bn_fold(*this, host_, e.bn, e.eps, false, cout, sc, sh, err)) return false;
+  } else if (!e.bias.empty()) {
+    const std::vector<float>* b = host_param(e.bias, err);
+    if (!b) return false;
+    sh = *b;
+  }
+  for (int i = 0; i < cout; ++i) {
+    sc[i] *= e.mul * (prescale.empty() ? 1.f : prescale[i]);
+    sh[i] *= e.mul;
+  }
+  *scale = upload(sc);
+  *shift = upload(sh);
+  return *scale && *shift;
+}
+
+bool Graph::make_scale_shift2(const EpiSpec& e, int cout, float** scale, float** shift, std::string* err) {
+  std::vector<float> sc, sh;
+  if (!bn_fold(*this, host_, e.bn2, e.eps2, false, cout, sc, sh, err)) return false;
+  *scale = upload(sc);
+  *shift = upload(sh);
+  return *scale && *shift;
+}
+
+// Packs one conv's weights K-major per output channel, split into fp16 hi/lo after scaling each
+// row by a power of two so that its largest entry sits in [1, 2) (keeps `lo` out of the fp16
+// subnormal range; the factor goes back in through the epilogue scale).
+static void pack_weights(const float* w, int kind, int cout, int cin, int k, int py, int px, int cout_pad,
+                         int cin_pad, int ntaps, std::vector<__half>& hi, std::vector<__half>& lo,
+                         std::vector<float>& prescale) {
+  const size_t kpad = (size_t)ntaps * cin_pad;
+  hi.assign((size_t)cout_pad * kpad, __float2half_rn(0.f));
+  lo.assign((size_t)cout_pad * kpad, __float2half_rn(0.f));
+  prescale.assign(cout, 1.f);
+  std::vector<float> row(kpad);
+  for (int n = 0; n < cout; ++n) {
+    std::fill(row.begin(), row.end(), 0.f);
+    if (kind == 0) {
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < k * k; ++t) row[(size_t)t * cin_pad + c] = w[((size_t)n * cin + c) * k * k + t];
+    } else if (kind == 1) {
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const int ky = py == 0 ? (a == 0 ? 1 : 3) : (a == 0 ? 2 : 0);
+          const int kx = px == 0 ? (b == 0 ? 1 : 3) : (b == 0 ? 2 : 0);
+          const int t = a * 2 + b;
+          for (int c = 0; c < cin; ++c)
+            row[(size_t)t * cin_pad + c] = w[(((size_t)c * cout + n) * 4 + ky) * 4 + kx];
+        }
+    } else {   // 1x1 over deformable columns: K index = tap*C + c; `cin` here is C
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < 9; ++t) row[(size_t)t * cin + c] = w[((size_t)n * cin + c) * 9 + t];
+    }
+    float m = 0.f;
+    for (float v : row) m = fmaxf(m, fabsf(v));
+    float mult = 1.f;
+    if (m > 0.f && isfinite(m)) {
+      const int ex = ilogbf(m);
+      mult = ldexpf(1.f, -ex);
+      prescale[n] = ldexpf(1.f, ex);
+    }
+    __half* ph = hi.data() + (size_t)n * kpad;
+    __half* pl = lo.data() + (size_t)n * kpad;
+    for (size_t i = 0; i < kpad; ++i) {
+      const float v = row[i] * mult;
+      const __half h = __float2half_rn(v);
+      ph[i] = h;
+      pl[i] = __float2half_rn(v - __half2float(h));
+    }
+  }
+}
+
+bool Graph::resolve_conv(Op& op, std::string* err) {
+  const Tensor& ti = tensors_[op.in];
+  ConvParams& P = op.conv;
+  const int Ho = P.Ho, Wo = P.Wo;
+  P = ConvParams{};
+  P.Ho = Ho; P.Wo = Wo;
+  P.in_hi = bufs_[ti.buf].hi + ti.coff;
+  P.in_lo = bufs_[ti.buf].lo + ti.coff;
+  P.in_ld = ti.ld; P.Hin = ti.H; P.Win = ti.W; P.Cin = ti.C;
+  P.stride = op.stride;
+  int wcin = ti.C;            // channel count in the weight tensor
+  if (op.kind == 0) {
+    P.ntaps = op.ksize * op.ksize;
+    if (P.ntaps > kMaxTaps) { *err = "kernel too large for the generic conv: " + op.name; return false; }
+    for (int ky = 0; ky < op.ksize; ++ky)
+      for (int kx = 0; kx < op.ksize; ++kx) {
+        P.dy[ky * op.ksize + kx] = (int8_t)(ky * op.dilate - op.pad);
+        P.dx[ky * op.ksize + kx] = (int8_t)(kx * op.dilate - op.pad);
+      }
+    P.Cin_pad = round_up(ti.C, 64);
+  } else if (op.kind == 1) {
+    P.ntaps = 4;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        P.dy[a * 2 + b] = (int8_t)(op.phase_y == 0 ? (a == 0 ? 0 : -1) : (a == 0 ? 0 : 1));
+        P.dx[a * 2 + b] = (int8_t)(op.phase_x == 0 ? (b == 0 ? 0 : -1) : (b == 0 ? 0 : 1));
+      }
+    P.Cin_pad = round_up(ti.C, 64);
+  } else {
+    P.ntaps = 1;
+    P.dy[0] = P.dx[0] = 0;
+    wcin = ti.C / 9;
+    P.Cin_pad = round_up(ti.C, 64);
+  }
+  P.Kpad = P.ntaps * P.Cin_pad;
+  P.Cout_pad = round_up(op.cout, 64);
+
+  const std::vector<float>* w = host_param(op.weight, err);
+  if (!w) return false;
+  std::vector<__half> hi, lo;
+  std::vector<float> prescale;
+  pack_weights(w->data(), op.kind, op.cout, wcin, op.ksize, op.phase_y, op.phase_x, P.Cout_pad,
+               op.kind == 2 ? P.Cin_pad : P.Cin_pad, P.ntaps, hi, lo, prescale);
+  __half* dhi = (__half*)dev_alloc(hi.size() * sizeof(__half));
+  __half* dlo = (__half*)dev_alloc(lo.size() * sizeof(__half));
+  if (!dhi || !dlo) { *err = "out of device memory packing " + op.name; return false; }
+  cudaMemcpy(dhi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  cudaMemcpy(dlo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  P.w_hi = dhi;
+  P.w_lo = dlo;
+
+  Epilogue& E = P.epi;
+  E = Epilogue{};
+  float *sc = nullptr, *sh = nullptr;
+  if (!make_scale_shift(op.epi, op.cout, prescale, &sc, &sh, err)) return false;
+  E.scale = sc; E.shift = sh; E.act = op.epi.act; E.Cout = op.cout;
+  if (op.epi.res >= 0) {
+    const Tensor& tr = tensors_[op.epi.res];
+    E.res_hi = bufs_[tr.buf].hi + tr.coff;
+    E.res_lo = bufs_[tr.buf].lo + tr.coff;
+    E.res_ld = tr.ld;
+  }
+  if (op.out >= 0) {
+    const Tensor& to = tensors_[op.out];
+    E.out_hi = bufs_[to.buf].hi + to.coff;
+    E.out_lo = bufs_[to.buf].lo + to.coff;
+    E.out_ld = to.ld;
+  }
+  if (op.epi.out2 >= 0) {
+    const Tensor& t2 = tensors_[op.epi.out2];
+    float *s2 = nullptr, *h2 = nullptr;
+    if (!make_scale_shift2(op.epi, op.cout, &s2, &h2, err)) return false;
+    E.scale2 = s2; E.shift2 = h2; E.act2 = op.epi.act2;
+    E.out2_hi = bufs_[t2.buf].hi + t2.coff;
+    E.out2_lo = bufs_[t2.buf].lo + t2.coff;
+    E.out2_ld = t2.ld;
+  }
+  if (op.epi.out_f32 >= 0) E.out_nchw = bufs_[tensors_[op.epi.out_f32].buf].f;
+  if (op.kind == 1) {
+    E.osy = E.osx = 2; E.ooy = op.phase_y; E.oox = op.phase_x;
+    E.OHf = 2 * ti.H; E.OWf = 2 * ti.W;
+  } else {
+    E.osy = E.osx = 1; E.ooy = E.oox = 0;
+    E.OHf = Ho; E.OWf = Wo;
+  }
+
+  // engine
+  int eng = op.engine;
+  if (eng == ENG_AUTO) {
+    if (op.cout <= 8) eng = ENG_NARROW;
+    else if (!(flags_ & 1) && tc_supported(P)) eng = ENG_TC;
+    else eng = ENG_FFMA;
+  }
+  if (eng == ENG_TC) {
+    char msg[256] = {0};
+    op.tc = tc_plan_create(P, num_sms_, msg, sizeof(msg));
+    if (!op.tc) { *err = std::string("tcgen05 plan failed for ") + op.name + ": " + msg; return false; }
+    const size_t pb = tc_plan_partial_bytes(op.tc);
+    if (pb) {
+      float* part = (float*)dev_alloc(pb);
+      if (!part) { *err = "out of device memory (split-K workspace)"; return false; }
+      tc_plan_set_partial(op.tc, part);
+    }
+  } else if (eng == ENG_FFMA) {
+    P.splits = ffma_pick_splits(P, num_sms_);
+    if (P.splits > 1) {
+      P.partial = (float*)dev_alloc(ffma_partial_bytes(P, P.splits));
+      if (!P.partial) { *err = "out of device memory (split-K workspace)"; return false; }
+    }
+  } else {
+    P.splits = 1;
+  }
+  op.engine = eng;
+  return true;
+}
+
+bool Graph::finalize(std::string* err) {
+  if (finalized_) return true;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    *err = "no CUDA device: accel_b200 has no CPU fallback";
+    return false;
+  }
+  if (cudaSetDevice(device_) != cudaSuccess) { *err = "cudaSetDevice failed"; return false; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device_);
+  num_sms_ = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    *err = "accel_b200 is built for sm_100a only (found sm_" + std::to_string(prop.major * 10 + prop.minor) + ")";
+    return false;
+  }
+  for (auto& b : bufs_) {
+    if (b.f32) {
+      b.f = (float*)dev_alloc(b.elems * sizeof(float));
+      if (!b.f) { *err = "out of device memory"; return false; }
+      cudaMemset(b.f, 0, b.elems * sizeof(float));
+    } else {
+      b.hi = (__half*)dev_alloc(b.elems * sizeof(__half));
+      b.lo = (__half*)dev_alloc(b.elems * sizeof(__half));
+      if (!b.hi || !b.lo) { *err = "out of device memory"; return false; }
+      cudaMemset(b.hi, 0, b.elems * sizeof(__half));
+      cudaMemset(b.lo, 0, b.elems * sizeof(__half));
+    }
+  }
+  if (label_scratch_bytes_) {
+    label_scratch_ptr_ = (uint8_t*)dev_alloc(label_scratch_bytes_);
+    if (!label_scratch_ptr_) { *err = "out of device memory"; return false; }
+  }
+  // The x16 score upsampling is executed as its closed form; insist the checkpoint's fixed kernel
+  // really is the MXNet bilinear initialiser (deeplab/symbols/resnet_v1_101_deeplab.py:820-828).
+  for (const std::string& name : bilinear_checks_) {
+    const std::vector<float>* w = host_param(name, err);
+    if (!w) return false;
+    const size_t n = w->size() / 1024;
+    for (size_t c = 0; c < n; ++c)
+      for (int y = 0; y < 32; ++y)
+        for (int x = 0; x < 32; ++x) {
+          const float ref = (1.f - fabsf(x / 16.f - 31.f / 32.f)) * (1.f - fabsf(y / 16.f - 31.f / 32.f));
+          if (fabsf((*w)[c * 1024 + y * 32 + x] - ref) > 1e-6f) {
+            *err = "'" + name + "' is not the fixed bilinear x16 kernel; the fused upsampling tail does not apply";
+            return false;
+          }
+        }
+  }
+  for (auto& kv : seqs_) {
+    for (auto& op : kv.second) {
+      switch (op.type) {
+        case OP_CONV:
+          if (!resolve_conv(op, err)) return false;
+          break;
+        case OP_STEM: {
+          StemParams& S = op.stem;
+          const int cin = op.in;
+          const int Hs = S.Hs, Ws = S.Ws;
+          S = StemParams{};
+          S.Hs = Hs; S.Ws = Ws; S.pool = op.stem_pool; S.Cin = cin;
+          for (int c = 0; c < 6; ++c) { S.in_scale[c] = op.stem_in_mul; S.in_shift[c] = 0.f; }
+          if (!op.bn_in.empty()) {
+            std::vector<float> sc, sh;
+            if (!bn_fold(*this, host_, op.bn_in, 2e-5f, true, cin, sc, sh, err)) return false;   // fix_gamma=True, eps 2e-5
+            for (int c = 0; c < cin; ++c) { S.in_scale[c] = sc[c]; S.in_shift[c] = sh[c]; }
+          }
+          const std::vector<float>* w = host_param(op.weight, err);
+          if (!w) return false;
+          S.weight = upload(*w);
+          const Tensor& to = tensors_[op.out];
+          S.Ho = to.H; S.Wo = to.W;
+          float *sc = nullptr, *sh = nullptr;
+          if (!make_scale_shift(op.epi, 64, {}, &sc, &sh, err)) return false;
+          Epilogue& E = S.epi;
+          E.scale = sc; E.shift = sh; E.act = op.epi.act; E.Cout = 64;
+          E.out_hi = bufs_[to.buf].hi + to.coff; E.out_lo = bufs_[to.buf].lo + to.coff; E.out_ld = to.ld;
+          E.osy = E.osx = 1; E.OHf = to.H; E.OWf = to.W;
+          break;
+        }
+        case OP_POOL: {
+          const Tensor& ti = tensors_[op.in];
+          const Tensor& to = tensors_[op.out];
+          PoolParams& Q = op.pool;
+          Q.in_hi = bufs_[ti.buf].hi + ti.coff; Q.in_lo = bufs_[ti.buf].lo + ti.coff;
+          Q.in_ld = ti.ld; Q.Hin = ti.H; Q.Win = ti.W; Q.C = ti.C;
+          Q.out_hi = bufs_[to.buf].hi + to.coff; Q.out_lo = bufs_[to.buf].lo + to.coff;
+          Q.out_ld = to.ld; Q.Ho = to.H; Q.Wo = to.W;
+          Q.kernel = op.ksize; Q.stride = op.stride; Q.pad = op.pad; Q.is_max = op.pool_max;
+          Q.scale = Q.shift = nullptr; Q.act = op.epi.act;
+          if (!op.epi.bn.empty()) {
+            float *sc = nullptr, *sh = nullptr;
+            if (!make_scale_shift(op.epi, ti.C, {}, &sc, &sh, err)) return false;
+            Q.scale = sc; Q.shift = sh;
+          }
+          break;
+        }
+        case OP_DCN_COL: {
+          const Tensor& ti = tensors_[op.in];
+          const Tensor& tf = tensors_[op.in2];
+          const Tensor& to = tensors_[op.out];
+          DcnColParams& D = op.dcn;
+          D.in_hi = bufs_[ti.buf].hi + ti.coff; D.in_lo = bufs_[ti.buf].lo + ti.coff;
+          D.in_ld = ti.ld; D.H = ti.H; D.W = ti.W; D.C = ti.C;
+          D.offset = bufs_[tf.buf].f;
+          D.dg = op.dg; D.dilate = op.dilate; D.pad = op.pad;
+          D.col_hi = bufs_[to.buf].hi; D.col_lo = bufs_[to.buf].lo; D.col_ld = to.ld;
+          if (ti.C % (8 * op.dg) != 0) { *err = "deformable conv needs C % (8*dg) == 0"; return false; }
+          break;
+        }
+        case OP_WARP: {
+          const Tensor& tf = tensors_[op.in];
+          WarpParams& Wp = op.warp;
+          Wp.flow = bufs_[tf.buf].f;
+          Wp.H = tf.H; Wp.W = tf.W;
+          if (op.out >= 0) {
+            const Tensor& to = tensors_[op.out];
+            Wp.C = to.C;
+            Wp.out_hi = bufs_[to.buf].hi + to.coff; Wp.out_lo = bufs_[to.buf].lo + to.coff; Wp.out_ld = to.ld;
+          }
+          break;
+        }
+        case OP_UPFLOW: {
+          const Tensor& tf = tensors_[op.in];
+          const Tensor& to = tensors_[op.out];
+          UpflowParams& U = op.upflow;
+          U.flow = bufs_[tf.buf].f; U.H = tf.H; U.W = tf.W;
+          const std::vector<float>* w = host_param(op.weight, err);
+          const std::vector<float>* b = w ? host_param(op.weight2, err) : nullptr;
+          if (!w || !b) return false;
+          memcpy(U.weight, w->data(), sizeof(U.weight));
+          memcpy(U.bias, b->data(), sizeof(U.bias));
+          U.out_hi = bufs_[to.buf].hi + to.coff; U.out_lo = bufs_[to.buf].lo + to.coff; U.out_ld = to.ld;
+          break;
+        }
+        case OP_FUSE: {
+          const Tensor& ta = tensors_[op.in];
+          FuseParams& F = op.fuse;
+          F.a = bufs_[ta.buf].f; F.b = bufs_[tensors_[op.in2].buf].f; F.out = bufs_[tensors_[op.out].buf].f;
+          F.K = ta.C; F.h = ta.H; F.w_ = ta.W;
+          const std::vector<float>* w = host_param(op.weight, err);
+          if (!w) return false;
+          F.w = upload(*w);
+          break;
+        }
+        case OP_TAIL: {
+          const Tensor& ts = tensors_[op.in];
+          TailParams& T = op.tail;
+          T.score = bufs_[ts.buf].f; T.K = ts.C; T.h = ts.H; T.w = ts.W; T.factor = 16;
+          T.bias = nullptr;
+          if (!op.weight2.empty()) {
+            const std::vector<float>* b = host_param(op.weight2, err);
+            if (!b) return false;
+            T.bias = upload(*b);
+          }
+          break;
+        }
+        case OP_TO_SPLIT:
+        case OP_TO_NCHW:
+        case OP_COPY_F32:
+          break;
+      }
+    }
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    *err = std::string("CUDA error during finalize: ") + cudaGetErrorString(cudaGetLastError());
+    return false;
+  }
+  host_.clear();
+  finalized_ = true;
+  return true;
+}
+
+bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err) {
+  auto it = seqs_.find(which);
+  if (it == seqs_.end()) { *err = "no such graph: " + which; return false; }
+  if (!finalized_ && !finalize(err)) return false;
+  std::vector<Op>& ops = it->second;
+  int launches = 0;
+  size_t ev = 0;
+  if (profiling_) {
+    event_stage_.clear();
+    while (events_.size() < ops.size() + 1) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      events_.push_back(e);
+    }
+    cudaEventRecord(events_[ev++], stream);
+  }
+  cudaError_t ce = cudaSuccess;
+  for (auto& op : ops) {
+    switch (op.type) {
+      case OP_STEM: {
+        StemParams S = op.stem;
+        S.src0 = (const float*)ext[op.ext_in0];
+        S.src1 = op.ext_in1 != X_NONE ? (const float*)ext[op.ext_in1] : nullptr;
+        if (!S.src0 || (op.ext_in1 != X_NONE && !S.src1)) { *err = "missing input frame"; return false; }
+        ce = launch_stem(S, stream);
+        ++launches;
+        break;
+      }
+      case OP_CONV: {
+        float* ext_nchw = op.epi.ext_out != X_NONE ? (float*)ext[op.epi.ext_out] : nullptr;
+        if (op.engine == ENG_TC) {
+          ce = launch_conv_tc_ext(op.tc, ext_nchw, stream);
+          launches += tc_plan_launches(op.tc);
+        } else {
+          ConvParams P = op.conv;
+          if (ext_nchw) P.epi.out_nchw = ext_nchw;
+          if (op.engine == ENG_NARROW) {
+            ce = launch_conv_narrow(P, stream);
+            ++launches;
+          } else {
+            ce = launch_conv_ffma(P, stream);
+            launches += P.splits > 1 ? 2 : 1;
+          }
+        }
+        break;
+      }
+      case OP_POOL:
+        ce = launch_pool(op.pool, stream);
+        ++launches;
+        break;
+      case OP_DCN_COL:
+        ce = launch_dcn_col(op.dcn, stream);
+        ++launches;
+        break;
+      case OP_WARP: {
+        WarpParams Wp = op.warp;
+        Wp.feat = (const float*)ext[op.ext_in0];
+        Wp.out_nchw = op.ext_out != X_NONE ? (float*)ext[op.ext_out] : nullptr;
+        if (!Wp.feat) { *err = "missing feat_key"; return false; }
+        if (Wp.out_nchw == Wp.feat) { *err = "feat_out must not alias feat_key"; return false; }
+        ce = launch_warp(Wp, stream);
+        ++launches;
+        break;
+      }
+      case OP_UPFLOW:
+        ce = launch_upflow(op.upflow, stream);
+        ++launches;
+        break;
+      case OP_FUSE:
+        ce = launch_fuse_lowres(op.fuse, stream);
+        ++launches;
+        break;
+      case OP_TAIL: {
+        TailParams T = op.tail;
+        T.label = op.ext_out != X_NONE && ext[op.ext_out] ? (uint8_t*)ext[op.ext_out] : label_scratch_ptr_;
+        T.score_out = op.ext_out2 != X_NONE ? (float*)ext[op.ext_out2] : nullptr;
+        ce = launch_tail(T, stream);
+        ++launches;
+        break;
+      }
+      case OP_TO_SPLIT: {
+        const Tensor& to = tensors_[op.out];
+        const float* src = (const float*)ext[op.ext_in0];
+        if (!src) { *err = "missing input tensor"; return false; }
+        ce = launch_nchw_to_split(src, to.C, to.H, to.W, bufs_[to.buf].hi + to.coff, bufs_[to.buf].lo + to.coff, to.ld,
+                                  stream);
+        ++launches;
+        break;
+      }
+      case OP_COPY_F32: {
+        const Tensor& to = tensors_[op.out];
+        const void* src = ext[op.ext_in0];
+        if (!src) { *err = "missing input tensor"; return false; }
+        ce = cudaMemcpyAsync(bufs_[to.buf].f, src, (size_t)to.C * to.H * to.W * sizeof(float), cudaMemcpyDeviceToDevice,
+                             stream);
+        break;
+      }
+      case OP_TO_NCHW: {
+        const Tensor& ti = tensors_[op.in];
+        float* dst = (float*)ext[op.ext_out];
+        if (dst) {
+          ce = launch_split_to_nchw(bufs_[ti.buf].hi + ti.coff, bufs_[ti.buf].lo + ti.coff, ti.ld, ti.C, ti.H, ti.W, dst,
+                                    stream);
+          ++launches;
+        }
+        break;
+      }
+    }
+    if (ce != cudaSuccess) {
+      *err = "launch of '" + op.name + "' failed: " + cudaGetErrorString(ce);
+      return false;
+    }
+    if (profiling_) {
+      cudaEventRecord(events_[ev++], stream);
+      event_stage_.push_back(op.stage);
+    }
+  }
+  last_launches_ = launches;
+  return true;
+}
+
+const std::vector<std::pair<std::string, float>>& Graph::stage_times() {
+  times_.clear();
+  if (event_stage_.empty()) return times_;
+  cudaEventSynchronize(events_[event_stage_.size()]);
+  for (size_t i = 0; i < event_stage_.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, events_[i], events_[i + 1]);
+    bool found = false;
+    for (auto& kv : times_)
+      if (kv.first == event_stage_[i]) { kv.second += ms; found = true; break; }
+    if (!found) times_.push_back({event_stage_[i], ms});
+  }
+  return times_;
+}
+
+}  // namespace accel

@@ -1,0 +1,172 @@
+// Host-side plan builder and executor: turns an Accel version + frame size into ordered kernel
+// launches over the split-fp16 NHWC activation format.  Pure host logic until finalize().
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.h"
+
+namespace accel {
+
+enum Ext { X_NONE = 0, X_DATA, X_DATA_KEY, X_FEAT_KEY, X_FEAT_OUT, X_SCORE_OUT, X_LABEL_OUT, X_FLOW_OUT, X_AUX_IN,
+           X_AUX_OUT, X_COUNT };
+
+struct Tensor {
+  int C = 0, H = 0, W = 0;
+  int ld = 0;        // channel stride of the underlying buffer
+  int buf = -1;      // buffer index
+  int coff = 0;      // channel offset inside the buffer (zero-copy concat views)
+  bool f32 = false;  // fp32 planar (C,H,W) instead of split NHWC
+};
+
+struct Buffer {
+  size_t elems = 0;  // fp16 elements per plane, or fp32 elements
+  bool f32 = false;
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  float* f = nullptr;
+};
+
+struct ParamSpec {
+  std::string name;
+  std::vector<int64_t> shape;
+};
+
+struct EpiSpec {
+  std::string bn;            // BatchNorm after the contraction (name prefix), or
+  float eps = 1e-5f;
+  std::string bias;          // a bias parameter name
+  float mul = 1.f;           // multiplies the result (FlowNet's `* 2.5`)
+  int act = ACT_NONE;
+  int res = -1;              // residual tensor id (added before act)
+  std::string bn2;           // second output: act2(bn2(v))
+  float eps2 = 2e-5f;
+  int act2 = ACT_RELU;
+  int out2 = -1;
+  int out_f32 = -1;          // also/only write fp32 planar tensor
+  int ext_out = X_NONE;      // also write an external fp32 NCHW output when the caller passed one
+  bool no_split_out = false;
+};
+
+enum OpType { OP_STEM, OP_CONV, OP_POOL, OP_DCN_COL, OP_WARP, OP_UPFLOW, OP_FUSE, OP_TAIL, OP_TO_SPLIT, OP_TO_NCHW, OP_COPY_F32 };
+enum Engine { ENG_AUTO = 0, ENG_FFMA = 1, ENG_TC = 2, ENG_NARROW = 3 };
+
+struct Op {
+  OpType type;
+  std::string stage;         // profiling bucket
+  std::string name;
+  // symbolic operands (tensor ids / parameter names), resolved into the kernel params at finalize
+  int in = -1, in2 = -1, out = -1;
+  std::string weight, weight2;
+  EpiSpec epi;
+  int cout = 0, ksize = 0, stride = 1, pad = 0, dilate = 1;
+  int kind = 0;              // OP_CONV: 0 conv, 1 deconv phase set (expanded), 2 1x1 over dcn columns
+  int phase_y = 0, phase_x = 0;
+  int pool_max = 0;
+  int dg = 1;
+  int ext_in0 = X_NONE, ext_in1 = X_NONE, ext_out = X_NONE, ext_out2 = X_NONE;
+  int engine = ENG_AUTO;
+  std::string bn_in;         // stem: input BatchNorm (bn_data)
+  int stem_pool = 0;
+  float stem_in_mul = 1.f;
+  // resolved
+  ConvParams conv{};
+  StemParams stem{};
+  PoolParams pool{};
+  DcnColParams dcn{};
+  WarpParams warp{};
+  UpflowParams upflow{};
+  FuseParams fuse{};
+  TailParams tail{};
+  TcPlan* tc = nullptr;
+  int partial_buf = -1;
+  double flops = 0.0;
+};
+
+class Graph {
+ public:
+  explicit Graph(int device, int flags) : device_(device), flags_(flags) {}
+  ~Graph();
+
+  // ---- building ----
+  int new_tensor(int C, int H, int W, bool f32 = false);
+  int new_view(int base, int coff, int C);
+  int add_param(const std::string& name, std::vector<int64_t> shape);
+  std::vector<Op>& seq(const std::string& which) { return seqs_[which]; }
+
+  int stem(std::vector<Op>& s, const std::string& stage, int ext0, int ext1, int Hs, int Ws, bool pool,
+           float in_mul, const std::string& bn_in, const std::string& wname, int cin, EpiSpec e);
+  int conv(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname, int cout, int k, int stride,
+           int pad, int dil, EpiSpec e, int out = -1);
+  int deconv4(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname, int cout, EpiSpec e,
+              int out = -1);
+  int dcn(std::vector<Op>& s, const std::string& stage, int in, int offset_f32, const std::string& wname, int cout,
+          int dg, EpiSpec e);
+  int pool(std::vector<Op>& s, const std::string& stage, int in, int k, int stride, int pad, bool is_max, bool full,
+           EpiSpec post = EpiSpec());
+  void require_bilinear(const std::string& name, int num_classes);
+  void warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, int ext_out);
+  void upflow(std::vector<Op>& s, int flow_f32, const std::string& wname, const std::string& bname, int out_view);
+  void fuse(std::vector<Op>& s, int a_f32, int b_f32, const std::string& wname, int out_f32);
+  void tail(std::vector<Op>& s, int score_f32, const std::string& bias_name, int ext_label, int ext_score);
+  void to_split(std::vector<Op>& s, int ext_in, int out);
+  void to_nchw(std::vector<Op>& s, int in, int ext_out);
+  void copy_f32(std::vector<Op>& s, int ext_in, int out_f32);
+
+  // ---- parameters ----
+  const std::vector<ParamSpec>& params() const { return params_; }
+  bool set_param(const std::string& name, const float* data, const int64_t* shape, int ndim, std::string* err);
+
+  // ---- execution ----
+  bool finalize(std::string* err);
+  bool finalized() const { return finalized_; }
+  bool run(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err);
+  int last_launches() const { return last_launches_; }
+  void set_profiling(bool on) { profiling_ = on; }
+  const std::vector<std::pair<std::string, float>>& stage_times();
+  const Tensor& tensor(int id) const { return tensors_[id]; }
+  int flags() const { return flags_; }
+  int num_sms() const { return num_sms_; }
+
+ private:
+  bool resolve_conv(Op& op, std::string* err);
+  bool make_scale_shift(const EpiSpec& e, int cout, const std::vector<float>& prescale, float** scale, float** shift,
+                        std::string* err);
+  bool make_scale_shift2(const EpiSpec& e, int cout, float** scale, float** shift, std::string* err);
+  const std::vector<float>* host_param(const std::string& name, std::string* err) const;
+  float* upload(const std::vector<float>& v);
+  void* dev_alloc(size_t bytes);
+  ActKind dummy_ = ACT_NONE;
+
+  int device_, flags_;
+  int num_sms_ = 148;
+  bool finalized_ = false;
+  bool profiling_ = false;
+  int last_launches_ = 0;
+  std::vector<Tensor> tensors_;
+  std::vector<Buffer> bufs_;
+  std::vector<ParamSpec> params_;
+  std::unordered_map<std::string, int> param_index_;
+  std::unordered_map<std::string, std::vector<float>> host_;
+  std::map<std::string, std::vector<Op>> seqs_;
+  std::vector<void*> allocs_;
+  // profiling
+  std::vector<cudaEvent_t> events_;
+  std::vector<std::string> event_stage_;
+  std::vector<std::pair<std::string, float>> times_;
+  std::vector<std::string> bilinear_checks_;
+  int label_scratch_ = -1;
+  uint8_t* label_scratch_ptr_ = nullptr;
+  size_t label_scratch_bytes_ = 0;
+
+ public:
+  void need_label_scratch(size_t bytes) { if (bytes > label_scratch_bytes_) label_scratch_bytes_ = bytes; }
+};
+
+// Accel graphs (nets.cu)
+bool build_accel(Graph& g, int version, int H, int W, int num_classes, std::string* err);
+
+}  // namespace accel

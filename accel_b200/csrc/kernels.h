@@ -1,0 +1,119 @@
+// Host-callable launchers for the hot-path kernels.  Internal to the library (the public surface is
+// include/accel_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace accel {
+
+// ---- convolution engines -------------------------------------------------------------------------
+int ffma_pick_splits(const ConvParams& P, int num_sms);
+size_t ffma_partial_bytes(const ConvParams& P, int splits);
+cudaError_t launch_conv_ffma(const ConvParams& P, cudaStream_t stream);
+cudaError_t launch_conv_narrow(const ConvParams& P, cudaStream_t stream);
+
+// tcgen05 / TMEM / TMA implicit-GEMM (conv_tc.cu)
+struct TcPlan;   // opaque: tensor maps + tiling chosen at plan time
+bool tc_supported(const ConvParams& P);
+TcPlan* tc_plan_create(const ConvParams& P, int num_sms, char* err, int errlen);
+void tc_plan_destroy(TcPlan* plan);
+size_t tc_plan_partial_bytes(const TcPlan* plan);
+void tc_plan_set_partial(TcPlan* plan, float* partial);
+// ext_nchw: optional fp32 NCHW destination that replaces the plan's epilogue out_nchw for this launch
+cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, cudaStream_t stream);
+int tc_plan_launches(const TcPlan* plan);
+
+// ---- stems (7x7 / stride 2 / pad 3, 64 output channels, fp32 NCHW source) ------------------------
+struct StemParams {
+  const float* src0;       // (3, Hs, Ws) fp32 planar: the frame
+  const float* src1;       // second frame (FlowNet: data_key) or nullptr
+  int Hs, Ws;              // source size
+  int pool;                // 1: average 2x2 blocks of src/255 first (FlowNet `resize_data`), 0: none
+  int Cin;                 // 3, or 6 when src1 is set
+  float in_scale[6];       // per-input-channel affine applied to in-bounds samples (R18/34 `bn_data`)
+  float in_shift[6];
+  const float* weight;     // fp32 (64, Cin, 7, 7)
+  Epilogue epi;            // out = split NHWC (64, Ho, Wo)
+  int Ho, Wo;
+};
+cudaError_t launch_stem(const StemParams& P, cudaStream_t stream);
+
+// ---- pooling ---------------------------------------------------------------------------------------
+struct PoolParams {
+  const __half* in_hi;
+  const __half* in_lo;
+  int in_ld, Hin, Win, C;
+  __half* out_hi;
+  __half* out_lo;
+  int out_ld, Ho, Wo;
+  int kernel, stride, pad;   // max: window clipped at the border; avg: exact tiles only
+  int is_max;
+  const float* scale;        // optional per-channel affine + activation on the pooled value
+  const float* shift;        // (pre-activation ResNets: the next unit's bn1 + relu)
+  int act;
+};
+cudaError_t launch_pool(const PoolParams& P, cudaStream_t stream);
+
+// ---- deformable im2col (DCNv1) ----------------------------------------------------------------------
+struct DcnColParams {
+  const __half* in_hi;
+  const __half* in_lo;
+  int in_ld, H, W, C;
+  const float* offset;       // fp32 planar (dg*18, H, W)
+  int dg, dilate, pad;       // 3x3, stride 1
+  __half* col_hi;            // split NHWC (9*C, H, W): channel = tap*C + c
+  __half* col_lo;
+  int col_ld;
+};
+cudaError_t launch_dcn_col(const DcnColParams& P, cudaStream_t stream);
+
+// ---- flow-guided warp (GridGenerator(warp) + BilinearSampler) -----------------------------------------
+struct WarpParams {
+  const float* feat;         // fp32 NCHW (C, H, W)
+  const float* flow;         // fp32 planar (2, H, W): dx, dy in feature-grid pixels
+  int C, H, W;
+  float* out_nchw;           // fp32 NCHW warped feature (`warping_feat_output`) or nullptr
+  __half* out_hi;            // split NHWC copy feeding the task head, or nullptr
+  __half* out_lo;
+  int out_ld;
+};
+cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream);
+
+// ---- layout conversion --------------------------------------------------------------------------------
+cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,
+                                 cudaStream_t stream);
+cudaError_t launch_split_to_nchw(const __half* hi, const __half* lo, int ld, int C, int H, int W, float* dst,
+                                 cudaStream_t stream);
+
+// ---- tiny 2->2 channel 4x4/s2/p1 transposed conv (FlowNet `upsample_flow*`) ----------------------------
+struct UpflowParams {
+  const float* flow;         // fp32 planar (2, H, W)
+  int H, W;
+  float weight[2 * 2 * 16];  // (cin, cout, 4, 4)
+  float bias[2];
+  __half* out_hi;            // split NHWC view (2 channels) of the 2H x 2W concat buffer
+  __half* out_lo;
+  int out_ld;
+};
+cudaError_t launch_upflow(const UpflowParams& P, cudaStream_t stream);
+
+// ---- score fusion + x16 bilinear upsampling + argmax ---------------------------------------------------
+struct FuseParams {          // low-res 1x1 fusion: out[c] = sum_j wa[c][j] a[j] + sum_j wb[c][j] b[j]
+  const float* a;            // fp32 planar (K, h, w)
+  const float* b;
+  const float* w;            // fp32 (K, 2K) row-major: `corr_weight`
+  float* out;                // fp32 planar (K, h, w)
+  int K, h, w_;
+};
+cudaError_t launch_fuse_lowres(const FuseParams& P, cudaStream_t stream);
+
+struct TailParams {
+  const float* score;        // fp32 planar (K, h, w) low-res scores
+  const float* bias;         // per-class bias added after interpolation (corr_bias) or nullptr
+  int K, h, w;
+  int factor;                // 16
+  uint8_t* label;            // (h*factor, w*factor)
+  float* score_out;          // fp32 planar (K, h*factor, w*factor) or nullptr
+};
+cudaError_t launch_tail(const TailParams& P, cudaStream_t stream);
+
+}  // namespace accel

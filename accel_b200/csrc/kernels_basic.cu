@@ -1,0 +1,465 @@
+// Bandwidth-side kernels of the Accel hot path: stems, pooling, deformable im2col, flow-guided warp,
+// layout conversion, score fusion + x16 upsampling + argmax.  sm_100a only.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace accel {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// 7x7 / s2 / p3 stem, fp32 NCHW source, 64 output channels (R101/R50 `conv1`, R18/34 `conv0`,
+// FlowNet `flow_conv1` with its 2x2 average pool and /255 folded into the patch load).
+// CTA = 8 x 32 output pixels; the input patch and all weights live in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_TH = 8, ST_TW = 32;
+constexpr int ST_PH = (ST_TH - 1) * 2 + 7;   // 21
+constexpr int ST_PW = (ST_TW - 1) * 2 + 7;   // 69
+constexpr int ST_PWP = ST_PW + 2;            // 71: odd row stride
+
+__global__ void __launch_bounds__(256) stem_kernel(const StemParams P) {
+  extern __shared__ __align__(16) float smem[];
+  float* ws = smem;                              // [Cin*49][64]
+  float* patch = smem + P.Cin * 49 * 64;         // [Cin][ST_PH][ST_PWP]
+  const int tid = threadIdx.x;
+  const int Hp = P.pool ? P.Hs / 2 : P.Hs, Wp = P.pool ? P.Ws / 2 : P.Ws;   // size the conv sees
+
+  for (int i = tid; i < P.Cin * 49 * 64; i += 256) {
+    const int n = i & 63, k = i >> 6;            // weight (n, c, ky, kx) -> ws[k][n], k = c*49 + ky*7 + kx
+    ws[i] = P.weight[(size_t)n * P.Cin * 49 + k];
+  }
+  const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = tid; i < P.Cin * ST_PH * ST_PW; i += 256) {
+    const int c = i / (ST_PH * ST_PW);
+    const int r = i - c * (ST_PH * ST_PW);
+    const int py = r / ST_PW, px = r - py * ST_PW;
+    const int iy = iy0 + py, ix = ix0 + px;
+    float v = 0.f;
+    if (iy >= 0 && iy < Hp && ix >= 0 && ix < Wp) {
+      const float* src = (c < 3 ? P.src0 : P.src1) + (size_t)(c < 3 ? c : c - 3) * P.Hs * P.Ws;
+      if (P.pool) {
+        const float* q = src + (size_t)(2 * iy) * P.Ws + 2 * ix;
+        v = ((q[0] + q[1]) + (q[P.Ws] + q[P.Ws + 1])) * 0.25f;
+      } else {
+        v = src[(size_t)iy * P.Ws + ix];
+      }
+      v = fmaf(v, P.in_scale[c], P.in_shift[c]);
+    }
+    patch[(c * ST_PH + py) * ST_PWP + px] = v;
+  }
+  __syncthreads();
+
+  const int ty = tid >> 5, tx = tid & 31;
+  float acc[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+  for (int c = 0; c < P.Cin; ++c) {
+    for (int ky = 0; ky < 7; ++ky) {
+      const float* prow = patch + (c * ST_PH + ty * 2 + ky) * ST_PWP + tx * 2;
+      const float* wrow = ws + (size_t)((c * 7 + ky) * 7) * 64;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float a = prow[kx];
+        const float4* w4 = reinterpret_cast<const float4*>(wrow + kx * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 w = w4[q];
+          acc[4 * q + 0] = fmaf(a, w.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(a, w.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(a, w.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(a, w.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy < P.Ho && ox < P.Wo) {
+    const int pix = oy * P.Wo + ox;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) epilogue_store<8>(P.epi, pix, g * 8, acc + g * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pooling over the split format: one thread per (output pixel, 8 channels).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_kernel(const PoolParams P) {
+  const int groups = (P.C + 7) / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)P.Ho * P.Wo * groups) return;
+  const int g = (int)(idx % groups);
+  const int p = (int)(idx / groups);
+  const int oy = p / P.Wo, ox = p - oy * P.Wo;
+  float best[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) best[i] = P.is_max ? -INFINITY : 0.f;
+  for (int ky = 0; ky < P.kernel; ++ky) {
+    const int iy = oy * P.stride - P.pad + ky;
+    if (iy < 0 || iy >= P.Hin) continue;
+    for (int kx = 0; kx < P.kernel; ++kx) {
+      const int ix = ox * P.stride - P.pad + kx;
+      if (ix < 0 || ix >= P.Win) continue;
+      float v[8];
+      const size_t off = ((size_t)iy * P.Win + ix) * P.in_ld + g * 8;
+      load8(P.in_hi + off, P.in_lo + off, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) best[i] = P.is_max ? fmaxf(best[i], v[i]) : best[i] + v[i];
+    }
+  }
+  if (!P.is_max) {
+    const float inv = 1.f / (float)(P.kernel * P.kernel);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) best[i] *= inv;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = g * 8 + i;
+    if (c >= P.C) best[i] = 0.f;
+    else if (P.scale) best[i] = apply_act(fmaf(best[i], P.scale[c], P.shift[c]), P.act);
+  }
+  const size_t o = (size_t)p * P.out_ld + g * 8;
+  store8(P.out_hi + o, P.out_lo + o, best);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deformable im2col, DCNv1 rule (oracle/ops.py:deformable_convolution): sample = 0 unless
+// 0 <= p < size; inside, bilinear with the high neighbour clamped to size-1.
+// One thread per (pixel, tap, 8 channels); the four neighbours are 16-byte NHWC loads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dcn_col_kernel(const DcnColParams P) {
+  const int groups = P.C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)P.H * P.W * 9 * groups) return;
+  const int g = (int)(idx % groups);
+  const int t = (int)((idx / groups) % 9);
+  const int p = (int)(idx / ((long long)groups * 9));
+  const int oy = p / P.W, ox = p - oy * P.W;
+  const int cpg = P.C / P.dg;
+  const int dgi = (g * 8) / cpg;
+  const int ti = t / 3, tj = t - ti * 3;
+  const size_t plane = (size_t)P.H * P.W;
+  const float offy = P.offset[(size_t)(dgi * 18 + 2 * t) * plane + p];
+  const float offx = P.offset[(size_t)(dgi * 18 + 2 * t + 1) * plane + p];
+  float py = (float)(oy - P.pad) + (float)(ti * P.dilate) + offy;
+  float px = (float)(ox - P.pad) + (float)(tj * P.dilate) + offx;
+  float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (py >= 0.f && px >= 0.f && py < (float)P.H && px < (float)P.W) {
+    int y0 = (int)floorf(py), x0 = (int)floorf(px);
+    int y1, x1;
+    if (y0 >= P.H - 1) { y0 = y1 = P.H - 1; py = (float)y0; } else { y1 = y0 + 1; }
+    if (x0 >= P.W - 1) { x0 = x1 = P.W - 1; px = (float)x0; } else { x1 = x0 + 1; }
+    const float ly = py - (float)y0, lx = px - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
+    float a[8], b[8], c[8], d[8];
+    const int c0 = g * 8;
+    size_t o;
+    o = ((size_t)y0 * P.W + x0) * P.in_ld + c0; load8(P.in_hi + o, P.in_lo + o, a);
+    o = ((size_t)y0 * P.W + x1) * P.in_ld + c0; load8(P.in_hi + o, P.in_lo + o, b);
+    o = ((size_t)y1 * P.W + x0) * P.in_ld + c0; load8(P.in_hi + o, P.in_lo + o, c);
+    o = ((size_t)y1 * P.W + x1) * P.in_ld + c0; load8(P.in_hi + o, P.in_lo + o, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = ((a[i] * w00 + b[i] * w01) + c[i] * w10) + d[i] * w11;
+  }
+  const size_t oo = (size_t)p * P.col_ld + (size_t)t * P.C + g * 8;
+  store8(P.col_hi + oo, P.col_lo + oo, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flow-guided warp: GridGenerator(transform_type='warp') + BilinearSampler
+// (dff_deeplab/symbols/accel_18.py:174-175).  The sampling position is computed with the same fp32
+// operation sequence as the MXNet operators (normalise to [-1,1], de-normalise), un-fused, so the
+// warped feature is bit-identical to the oracle's.  CTA = 32 consecutive pixels x 64 channels: each
+// lane owns a pixel (its 2x2 neighbourhood + weights are computed once and reused down the channel
+// axis, reads and NCHW writes are coalesced along x), then the tile is transposed through shared
+// memory into the split NHWC copy the task head consumes.
+// ------------------------------------------------------------------------------------------------
+constexpr int WP_PIX = 32, WP_CH = 64;
+
+__global__ void __launch_bounds__(256) warp_kernel(const WarpParams P) {
+  __shared__ float tile[WP_CH][WP_PIX + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int npix = P.H * P.W;
+  const int p = blockIdx.x * WP_PIX + lane;
+  const int cb = blockIdx.y * WP_CH;
+  const bool live = p < npix;
+  int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
+  float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+  if (live) {
+    const int y = p / P.W, x = p - y * P.W;
+    const float sx = (float)(P.W - 1) / 2.0f, sy = (float)(P.H - 1) / 2.0f;
+    const float gx = __fsub_rn(__fdiv_rn(__fadd_rn(P.flow[p], (float)x), sx), 1.0f);
+    const float gy = __fsub_rn(__fdiv_rn(__fadd_rn(P.flow[npix + p], (float)y), sy), 1.0f);
+    const float xr = __fmul_rn(__fadd_rn(gx, 1.0f), sx);
+    const float yr = __fmul_rn(__fadd_rn(gy, 1.0f), sy);
+    const float xf = floorf(xr), yf = floorf(yr);
+    const float wx0 = __fsub_rn(1.0f, __fsub_rn(xr, xf)), wy0 = __fsub_rn(1.0f, __fsub_rn(yr, yf));
+    const float wx1 = __fsub_rn(1.0f, wx0), wy1 = __fsub_rn(1.0f, wy0);
+    const bool x0ok = xf >= 0.f && xf <= (float)(P.W - 1), x1ok = xf + 1.f >= 0.f && xf + 1.f <= (float)(P.W - 1);
+    const bool y0ok = yf >= 0.f && yf <= (float)(P.H - 1), y1ok = yf + 1.f >= 0.f && yf + 1.f <= (float)(P.H - 1);
+    const int xi0 = min(max((int)xf, 0), P.W - 1), xi1 = min(max((int)xf + 1, 0), P.W - 1);
+    const int yi0 = min(max((int)yf, 0), P.H - 1), yi1 = min(max((int)yf + 1, 0), P.H - 1);
+    // clamp before the int conversion would overflow for wild flows
+    const float big = 1e9f;
+    const bool sane = fabsf(xr) < big && fabsf(yr) < big;
+    i00 = yi0 * P.W + xi0; i01 = yi0 * P.W + xi1; i10 = yi1 * P.W + xi0; i11 = yi1 * P.W + xi1;
+    w00 = (sane && y0ok && x0ok) ? __fmul_rn(wy0, wx0) : 0.f;
+    w01 = (sane && y0ok && x1ok) ? __fmul_rn(wy0, wx1) : 0.f;
+    w10 = (sane && y1ok && x0ok) ? __fmul_rn(wy1, wx0) : 0.f;
+    w11 = (sane && y1ok && x1ok) ? __fmul_rn(wy1, wx1) : 0.f;
+    if (!sane) { i00 = i01 = i10 = i11 = 0; }
+  }
+#pragma unroll
+  for (int k = 0; k < WP_CH / 8; ++k) {
+    const int cl = wid * (WP_CH / 8) + k;
+    const int c = cb + cl;
+    float v = 0.f;
+    if (live && c < P.C) {
+      const float* f = P.feat + (size_t)c * npix;
+      v = __fmul_rn(__ldg(f + i00), w00);
+      v = __fadd_rn(v, __fmul_rn(__ldg(f + i01), w01));
+      v = __fadd_rn(v, __fmul_rn(__ldg(f + i10), w10));
+      v = __fadd_rn(v, __fmul_rn(__ldg(f + i11), w11));
+      if (P.out_nchw) P.out_nchw[(size_t)c * npix + p] = v;
+    }
+    tile[cl][lane] = v;
+  }
+  if (!P.out_hi) return;
+  __syncthreads();
+  const int pl = threadIdx.x >> 3, g = threadIdx.x & 7;
+  const int pp = blockIdx.x * WP_PIX + pl;
+  if (pp < npix && cb + g * 8 < P.C) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tile[g * 8 + i][pl];
+    const size_t o = (size_t)pp * P.out_ld + cb + g * 8;
+    store8(P.out_hi + o, P.out_lo + o, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 NCHW <-> split NHWC (32 pixels x 32 channels per CTA through shared memory)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ src, int C, int npix,
+                                                            __half* hi, __half* lo, int ld) {
+  __shared__ float tile[32][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + wid * 4 + k, p = p0 + lane;
+    tile[wid * 4 + k][lane] = (c < C && p < npix) ? src[(size_t)c * npix + p] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int pl = threadIdx.x >> 2, g = threadIdx.x & 3;
+    const int p = p0 + pl;
+    if (p < npix && c0 + g * 8 < ld) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = tile[g * 8 + i][pl];
+      const size_t o = (size_t)p * ld + c0 + g * 8;
+      store8(hi + o, lo + o, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) split_to_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                            int ld, int C, int npix, float* dst) {
+  __shared__ float tile[32][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (threadIdx.x < 128) {
+    const int pl = threadIdx.x >> 2, g = threadIdx.x & 3;
+    const int p = p0 + pl;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p < npix && c0 + g * 8 < ld) {
+      const size_t o = (size_t)p * ld + c0 + g * 8;
+      load8(hi + o, lo + o, v);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[g * 8 + i][pl] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + wid * 4 + k, p = p0 + lane;
+    if (c < C && p < npix) dst[(size_t)c * npix + p] = tile[wid * 4 + k][lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FlowNet `upsample_flow*`: Deconvolution(2 -> 2, k4, s2, p0) + Crop(1,1) == transposed conv pad 1.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upflow_kernel(const UpflowParams P) {
+  const int OW = 2 * P.W, OH = 2 * P.H;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= OW * OH) return;
+  const int oy = idx / OW, ox = idx - oy * OW;
+  float acc[2] = {P.bias[0], P.bias[1]};
+  for (int ky = 0; ky < 4; ++ky) {
+    const int ty = oy + 1 - ky;
+    if (ty < 0 || (ty & 1)) continue;
+    const int iy = ty >> 1;
+    if (iy >= P.H) continue;
+    for (int kx = 0; kx < 4; ++kx) {
+      const int tx = ox + 1 - kx;
+      if (tx < 0 || (tx & 1)) continue;
+      const int ix = tx >> 1;
+      if (ix >= P.W) continue;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const float v = P.flow[(size_t)ci * P.H * P.W + iy * P.W + ix];
+        acc[0] = fmaf(v, P.weight[(ci * 2 + 0) * 16 + ky * 4 + kx], acc[0]);
+        acc[1] = fmaf(v, P.weight[(ci * 2 + 1) * 16 + ky * 4 + kx], acc[1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 2; ++co) {
+    __half h, l;
+    split_f32(acc[co], h, l);
+    P.out_hi[(size_t)idx * P.out_ld + co] = h;
+    P.out_lo[(size_t)idx * P.out_ld + co] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Score-level fusion at feature resolution.  Both x16 upsamplings use the same channel-independent
+// bilinear kernel, so correction(concat(up(a), up(b))) == up(Wa a + Wb b) + bias: the 38 -> 19 conv
+// (accel_18.py:229-235) runs on the 64x128 maps and the bias is added after interpolation.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) fuse_lowres_kernel(const FuseParams P) {
+  extern __shared__ float wsm[];
+  for (int i = threadIdx.x; i < P.K * 2 * P.K; i += blockDim.x) wsm[i] = P.w[i];
+  __syncthreads();
+  const int npix = P.h * P.w_;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float in[64];
+  for (int j = 0; j < P.K; ++j) {
+    in[j] = P.a[(size_t)j * npix + p];
+    in[P.K + j] = P.b[(size_t)j * npix + p];
+  }
+  for (int c = 0; c < P.K; ++c) {
+    float acc = 0.f;
+    for (int j = 0; j < 2 * P.K; ++j) acc = fmaf(wsm[c * 2 * P.K + j], in[j], acc);
+    P.out[(size_t)c * npix + p] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x16 bilinear upsampling (grouped 32x32/s16 Deconvolution + Crop(8,8), accel_18.py:193-197) fused
+// with the per-pixel argmax (demo.py:238,245,252).  out[Y] = sum_i s[i] * w1[Y + 8 - 16 i] with
+// w1[k] = 1 - |k/16 - 31/32|: two taps per axis, zero beyond the map (no clamping).  One thread owns
+// four horizontally adjacent pixels (they share the same source columns); labels leave as uchar4.
+// The fp32 score volume is written only when the caller asks for it (parity mode).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tail_kernel(const TailParams P) {
+  const int OW = P.w * P.factor, OH = P.h * P.factor;
+  const int qw = OW / 4;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= qw * OH) return;
+  const int Y = idx / qw, X0 = (idx - Y * qw) * 4;
+  const int f = P.factor, half = f / 2;
+  const float inv = 1.f / (float)f, cen = (float)(2 * f - 1) / (float)(2 * f);
+  const int i0 = (Y + half) / f, ky = (Y + half) - i0 * f;
+  const float wy0 = (i0 < P.h) ? 1.f - fabsf((float)ky * inv - cen) : 0.f;            // source row i0
+  const float wy1 = (i0 >= 1) ? 1.f - fabsf((float)(ky + f) * inv - cen) : 0.f;       // source row i0-1
+  const int j0 = (X0 + half) / f, kx = (X0 + half) - j0 * f;
+  const bool c0ok = j0 < P.w, c1ok = j0 >= 1;
+  float wx0[4], wx1[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    wx0[q] = c0ok ? 1.f - fabsf((float)(kx + q) * inv - cen) : 0.f;
+    wx1[q] = c1ok ? 1.f - fabsf((float)(kx + q + f) * inv - cen) : 0.f;
+  }
+  const int r0 = min(i0, P.h - 1), r1 = max(i0 - 1, 0), q0 = min(j0, P.w - 1), q1 = max(j0 - 1, 0);
+  const size_t plane = (size_t)P.h * P.w, oplane = (size_t)OH * OW;
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int arg[4] = {0, 0, 0, 0};
+  for (int c = 0; c < P.K; ++c) {
+    const float* s = P.score + c * plane;
+    const float s00 = s[r0 * P.w + q0], s01 = s[r0 * P.w + q1], s10 = s[r1 * P.w + q0], s11 = s[r1 * P.w + q1];
+    const float b = P.bias ? P.bias[c] : 0.f;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = ((s00 * (wy0 * wx0[q]) + s01 * (wy0 * wx1[q])) + s10 * (wy1 * wx0[q])) + s11 * (wy1 * wx1[q]) + b;
+      if (v[q] > best[q]) { best[q] = v[q]; arg[q] = c; }      // strict: ties keep the lowest class
+    }
+    if (P.score_out)
+      *reinterpret_cast<float4*>(P.score_out + c * oplane + (size_t)Y * OW + X0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  *reinterpret_cast<uchar4*>(P.label + (size_t)Y * OW + X0) =
+      make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
+}
+
+}  // namespace
+
+cudaError_t launch_stem(const StemParams& P, cudaStream_t stream) {
+  const size_t smem = ((size_t)P.Cin * 49 * 64 + (size_t)P.Cin * ST_PH * ST_PWP) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((P.Wo + ST_TW - 1) / ST_TW, (P.Ho + ST_TH - 1) / ST_TH);
+  stem_kernel<<<grid, 256, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool(const PoolParams& P, cudaStream_t stream) {
+  const long long work = (long long)P.Ho * P.Wo * ((P.C + 7) / 8);
+  pool_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dcn_col(const DcnColParams& P, cudaStream_t stream) {
+  const long long work = (long long)P.H * P.W * 9 * (P.C / 8);
+  dcn_col_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
+  dim3 grid((P.H * P.W + WP_PIX - 1) / WP_PIX, (P.C + WP_CH - 1) / WP_CH);
+  warp_kernel<<<grid, 256, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,
+                                 cudaStream_t stream) {
+  dim3 grid((H * W + 31) / 32, (ld + 31) / 32);
+  nchw_to_split_kernel<<<grid, 256, 0, stream>>>(src, C, H * W, hi, lo, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_to_nchw(const __half* hi, const __half* lo, int ld, int C, int H, int W, float* dst,
+                                 cudaStream_t stream) {
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32);
+  split_to_nchw_kernel<<<grid, 256, 0, stream>>>(hi, lo, ld, C, H * W, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upflow(const UpflowParams& P, cudaStream_t stream) {
+  const int work = 4 * P.H * P.W;
+  upflow_kernel<<<(work + 255) / 256, 256, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fuse_lowres(const FuseParams& P, cudaStream_t stream) {
+  if (P.K > 32) return cudaErrorInvalidValue;
+  const int npix = P.h * P.w_;
+  fuse_lowres_kernel<<<(npix + 127) / 128, 128, (size_t)P.K * 2 * P.K * sizeof(float), stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tail(const TailParams& P, cudaStream_t stream) {
+  const int work = (P.w * P.factor / 4) * (P.h * P.factor);
+  tail_kernel<<<(work + 255) / 256, 256, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace accel

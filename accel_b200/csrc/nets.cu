@@ -1,0 +1,284 @@
+// The Accel inference graphs expressed over the plan builder: which layer feeds which, under the
+// reference's parameter names.  Structure follows
+//   dff_deeplab/symbols/resnet_v1_101_flownet_deeplab.py  (get_flownet :1751-1808, residual_unit/resnet
+//     :29-130, get_resnet_dcn_{18,34}_conv5 :132-233, get_resnet_dcn_50 :235-574, get_resnet_dcn :576-1300)
+//   dff_deeplab/symbols/accel_{18,34,50,101}.py           (get_key_test_symbol, get_cur_test_symbol)
+// Concats are zero-copy channel views, BatchNorm/bias/activation/residual live in conv epilogues,
+// Deconvolution(k4,s2)+Crop(1,1) is run as four 2x2-tap phase convolutions, and the x16 score
+// upsampling + fusion + argmax is one tail kernel.
+#include <string>
+
+#include "graph.h"
+
+namespace accel {
+
+namespace {
+
+using Seq = std::vector<Op>;
+
+EpiSpec bn_epi(const std::string& bn, int act, float eps = 1e-5f) {
+  EpiSpec e;
+  e.bn = bn;
+  e.eps = eps;
+  e.act = act;
+  return e;
+}
+
+EpiSpec bias_epi(const std::string& conv, int act) {
+  EpiSpec e;
+  e.bias = conv + "_bias";
+  e.act = act;
+  return e;
+}
+
+// ---- FlowNet-S -----------------------------------------------------------------------------------
+int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out) {
+  const std::string st = "flownet";
+  int r1 = g.stem(s, st, X_DATA, X_DATA_KEY, H, W, true, 1.0f / 255.0f, "", "flow_conv1", 6,
+                  bias_epi("flow_conv1", ACT_LEAKY));
+  const Tensor t1 = g.tensor(r1);                                   // (64, H/4, W/4)
+  const int c5 = g.new_tensor(128 + 64 + 2, t1.H / 2, t1.W / 2);     // Concat5
+  const int c4 = g.new_tensor(256 + 128 + 2, t1.H / 4, t1.W / 4);    // Concat4
+  const int c3 = g.new_tensor(512 + 256 + 2, t1.H / 8, t1.W / 8);    // Concat3
+  const int c2 = g.new_tensor(512 + 512 + 2, t1.H / 16, t1.W / 16);  // Concat2
+  int r2 = g.conv(s, st, r1, "conv2", 128, 5, 2, 2, 1, bias_epi("conv2", ACT_LEAKY), g.new_view(c5, 0, 128));
+  int r3 = g.conv(s, st, r2, "conv3", 256, 5, 2, 2, 1, bias_epi("conv3", ACT_LEAKY));
+  int r4 = g.conv(s, st, r3, "conv3_1", 256, 3, 1, 1, 1, bias_epi("conv3_1", ACT_LEAKY), g.new_view(c4, 0, 256));
+  int r5 = g.conv(s, st, r4, "conv4", 512, 3, 2, 1, 1, bias_epi("conv4", ACT_LEAKY));
+  int r6 = g.conv(s, st, r5, "conv4_1", 512, 3, 1, 1, 1, bias_epi("conv4_1", ACT_LEAKY), g.new_view(c3, 0, 512));
+  int r7 = g.conv(s, st, r6, "conv5", 512, 3, 2, 1, 1, bias_epi("conv5", ACT_LEAKY));
+  int r8 = g.conv(s, st, r7, "conv5_1", 512, 3, 1, 1, 1, bias_epi("conv5_1", ACT_LEAKY), g.new_view(c2, 0, 512));
+  int r9 = g.conv(s, st, r8, "conv6", 1024, 3, 2, 1, 1, bias_epi("conv6", ACT_LEAKY));
+  int r10 = g.conv(s, st, r9, "conv6_1", 1024, 3, 1, 1, 1, bias_epi("conv6_1", ACT_LEAKY));
+  (void)r8; (void)r6; (void)r4; (void)r2;
+
+  auto refine = [&](int feat, int cat, int skip_c, int deconv_c, const char* flow_name, const char* deconv_name,
+                    const char* up_name) {
+    const Tensor tf = g.tensor(feat);
+    const int f = g.new_tensor(2, tf.H, tf.W, true);
+    EpiSpec fe = bias_epi(flow_name, ACT_NONE);
+    fe.out_f32 = f;
+    fe.no_split_out = true;
+    g.conv(s, st, feat, flow_name, 2, 3, 1, 1, 1, fe);
+    g.deconv4(s, st, feat, deconv_name, deconv_c, bias_epi(deconv_name, ACT_LEAKY), g.new_view(cat, skip_c, deconv_c));
+    g.upflow(s, f, up_name, std::string(up_name) + "_bias", g.new_view(cat, skip_c + deconv_c, 2));
+  };
+  refine(r10, c2, 512, 512, "Convolution1", "deconv5", "upsample_flow6to5");
+  refine(c2, c3, 512, 256, "Convolution2", "deconv4", "upsample_flow5to4");
+  refine(c3, c4, 256, 128, "Convolution3", "deconv3", "upsample_flow4to3");
+  refine(c4, c5, 128, 64, "Convolution4", "deconv2", "upsample_flow3to2");
+  const int p5 = g.pool(s, st, c5, 2, 2, 0, false, true);           // resize_concat5
+  const Tensor tp = g.tensor(p5);
+  EpiSpec fe = bias_epi("Convolution5", ACT_NONE);
+  fe.mul = 2.5f;                                                    // `Convolution5 * 2.5`, :1808
+  fe.no_split_out = true;
+  int flow = -1;
+  if (ext_flow_out != X_NONE) {
+    fe.ext_out = ext_flow_out;
+  } else {
+    flow = g.new_tensor(2, tp.H, tp.W, true);
+    fe.out_f32 = flow;
+  }
+  g.conv(s, st, p5, "Convolution5", 2, 3, 1, 1, 1, fe);
+  return flow;
+}
+
+// ---- caffe-style bottleneck nets (R101-DCN, R50-DCN) --------------------------------------------------
+struct DeformCfg {
+  int off_ch, off_pad, off_dil, dg;
+};
+
+int bottleneck_net(Graph& g, Seq& s, const std::string& st, int H, int W, const std::string& prefix,
+                   const std::vector<std::vector<std::string>>& stage_units, DeformCfg d, int ext_feat_out,
+                   int final_out_view) {
+  int x = g.stem(s, st, X_DATA, X_NONE, H, W, false, 1.f, "", prefix + "conv1", 3, bn_epi(prefix + "bn_conv1", ACT_RELU));
+  x = g.pool(s, st, x, 3, 2, 0, true, true);                        // pool1: 3x3/s2, pooling_convention='full'
+  const int mids[4] = {64, 128, 256, 512};
+  for (int si = 0; si < 4; ++si) {
+    const int stage = si + 2, mid = mids[si];
+    const auto& units = stage_units[si];
+    for (size_t n = 0; n < units.size(); ++n) {
+      const int stride = (n == 0 && (stage == 3 || stage == 4)) ? 2 : 1;
+      const std::string r = prefix + "res" + std::to_string(stage) + units[n];
+      const std::string b = prefix + "bn" + std::to_string(stage) + units[n];
+      const bool last = si == 3 && n + 1 == units.size();
+      int sc = x;
+      if (n == 0) sc = g.conv(s, st, x, r + "_branch1", 4 * mid, 1, stride, 0, 1, bn_epi(b + "_branch1", ACT_NONE));
+      int a = g.conv(s, st, x, r + "_branch2a", mid, 1, stride, 0, 1, bn_epi(b + "_branch2a", ACT_RELU));
+      int m;
+      if (stage == 5) {
+        const Tensor ta = g.tensor(a);
+        const int off = g.new_tensor(d.off_ch, ta.H, ta.W, true);
+        EpiSpec oe = bias_epi(r + "_branch2b_offset", ACT_NONE);
+        oe.out_f32 = off;
+        oe.no_split_out = true;
+        g.conv(s, st, a, r + "_branch2b_offset", d.off_ch, 3, 1, d.off_pad, d.off_dil, oe);
+        m = g.dcn(s, st, a, off, r + "_branch2b", mid, d.dg, bn_epi(b + "_branch2b", ACT_RELU));
+      } else {
+        m = g.conv(s, st, a, r + "_branch2b", mid, 3, 1, 1, 1, bn_epi(b + "_branch2b", ACT_RELU));
+      }
+      EpiSpec ce = bn_epi(b + "_branch2c", ACT_RELU);
+      ce.res = sc;
+      if (last) ce.ext_out = ext_feat_out;
+      x = g.conv(s, st, m, r + "_branch2c", 4 * mid, 1, 1, 0, 1, ce, last ? final_out_view : -1);
+    }
+  }
+  return x;
+}
+
+std::vector<std::vector<std::string>> units_101() {
+  std::vector<std::string> r4 = {"a"};
+  for (int i = 1; i <= 22; ++i) r4.push_back("b" + std::to_string(i));
+  return {{"a", "b", "c"}, {"a", "b1", "b2", "b3"}, r4, {"a", "b", "c"}};
+}
+
+std::vector<std::vector<std::string>> units_50() {
+  return {{"a", "b", "c"}, {"a", "b", "c", "d"}, {"a", "b", "c", "d", "e", "f"}, {"a", "b", "c"}};
+}
+
+// ---- pre-activation basic-block trunk + deformable conv5 (Accel-18 / Accel-34 R branch) ----------------
+int preact_branch(Graph& g, Seq& s, const std::string& st, int H, int W, const std::string& pre,
+                  const std::vector<int>& units, const std::string& letters) {
+  const float eps = 2e-5f;
+  int x = g.stem(s, st, X_DATA, X_NONE, H, W, false, 1.f, pre + "bn_data", pre + "conv0", 3,
+                 bn_epi(pre + "bn0", ACT_RELU, eps));
+  // max pool, then stage1_unit1's bn1 + relu on the pooled map (unit 1 never reads the raw input:
+  // its shortcut conv also takes act1, :80-81)
+  int act = g.pool(s, st, x, 3, 2, 1, true, false, bn_epi(pre + "stage1_unit1_bn1", ACT_RELU, eps));
+  int raw = -1;
+  const int chans[3] = {64, 128, 256};
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < units[i]; ++j) {
+      const std::string name = pre + "stage" + std::to_string(i + 1) + "_unit" + std::to_string(j + 1);
+      const int c = chans[i];
+      const int stride = (j == 0 && i > 0) ? 2 : 1;
+      const bool dim_match = j > 0;
+      int c1 = g.conv(s, st, act, name + "_conv1", c, 3, stride, 1, 1, bn_epi(name + "_bn2", ACT_RELU, eps));
+      int shortcut = dim_match ? raw : g.conv(s, st, act, name + "_sc", c, 1, stride, 0, 1, EpiSpec());
+      // what follows this unit?
+      const bool last_unit = i == 2 && j + 1 == units[i];
+      std::string next;
+      bool next_needs_raw = last_unit;
+      if (!last_unit) {
+        if (j + 1 < units[i]) {
+          next = pre + "stage" + std::to_string(i + 1) + "_unit" + std::to_string(j + 2);
+          next_needs_raw = true;                                   // identity shortcut reads the raw sum
+        } else {
+          next = pre + "stage" + std::to_string(i + 2) + "_unit1";
+        }
+      }
+      const Tensor t1 = g.tensor(c1);
+      EpiSpec e;
+      e.res = shortcut;
+      if (!next.empty()) {
+        e.bn2 = next + "_bn1";
+        e.eps2 = eps;
+        e.act2 = ACT_RELU;
+        e.out2 = g.new_tensor(c, t1.H, t1.W);
+      }
+      e.no_split_out = !next_needs_raw;
+      raw = g.conv(s, st, c1, name + "_conv2", c, 3, 1, 1, 1, e);
+      act = e.out2;
+    }
+  }
+  // conv5: post-activation basic units, deformable second conv (3x3, dil 2, dg 4)
+  int xx = raw;
+  for (size_t n = 0; n < letters.size(); ++n) {
+    const std::string L(1, letters[n]);
+    const bool first = n == 0;
+    int sc = xx;
+    if (first) sc = g.conv(s, st, xx, pre + "res5" + L + "_branch1", 512, 1, 2, 0, 1, bn_epi(pre + "bn5" + L + "_branch1", ACT_NONE));
+    int a = g.conv(s, st, xx, pre + "res5" + L + "_branch2a", 512, 3, first ? 2 : 1, 1, 1,
+                   bn_epi(pre + "bn5" + L + "_branch2a", ACT_RELU));
+    const Tensor ta = g.tensor(a);
+    const int off = g.new_tensor(72, ta.H, ta.W, true);
+    EpiSpec oe = bias_epi(pre + "res5" + L + "_branch2b_offset", ACT_NONE);
+    oe.out_f32 = off;
+    oe.no_split_out = true;
+    g.conv(s, st, a, pre + "res5" + L + "_branch2b_offset", 72, 3, 1, 2, 2, oe);
+    EpiSpec be = bn_epi(pre + "bn5" + L + "_branch2b", ACT_RELU);
+    be.res = sc;
+    xx = g.dcn(s, st, a, off, pre + "res5" + L + "_branch2b", 512, 4, be);
+  }
+  return g.deconv4(s, st, xx, pre + "feat_upsampling", 2048, EpiSpec());
+}
+
+// ---- DeepLab head: fc6 1x1 + ReLU -> score 1x1; returns the low-res fp32 score map ----------------------
+int head(Graph& g, Seq& s, const std::string& st, int feat, const std::string& fc6, const std::string& score,
+         const std::string& upsampling, int K) {
+  int x = g.conv(s, st, feat, fc6, 1024, 1, 1, 0, 1, bias_epi(fc6, ACT_RELU));
+  const Tensor tx = g.tensor(x);
+  const int sc = g.new_tensor(K, tx.H, tx.W, true);
+  EpiSpec e = bias_epi(score, ACT_NONE);
+  e.out_f32 = sc;
+  e.no_split_out = true;
+  g.conv(s, st, x, score, K, 1, 1, 0, 1, e);
+  g.require_bilinear(upsampling + "_weight", K);
+  return sc;
+}
+
+}  // namespace
+
+bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
+  if (H <= 0 || W <= 0 || H % 128 || W % 128) {
+    *err = "frame height and width must be positive multiples of 128";
+    return false;
+  }
+  if (K < 1 || K > 32) { *err = "num_classes must be in [1, 32]"; return false; }
+  if (version != 0 && version != 18 && version != 34 && version != 50 && version != 101) {
+    *err = "unknown Accel version (expected 0=dff, 18, 34, 50, 101)";
+    return false;
+  }
+  const int h = H / 16, w = W / 16;
+
+  // key frame: R101-DCN + head (get_key_test_symbol)
+  {
+    Seq& s = g.seq("key");
+    int feat = bottleneck_net(g, s, "backbone", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_FEAT_OUT, -1);
+    int sc = head(g, s, "head", feat, "fc6", "score", "upsampling", K);
+    g.tail(s, sc, "", X_LABEL_OUT, X_SCORE_OUT);
+  }
+  // FlowNet alone (accel_flownet)
+  {
+    Seq& s = g.seq("flow");
+    flownet(g, s, H, W, X_FLOW_OUT);
+  }
+  // cur frame (get_cur_test_symbol)
+  {
+    Seq& s = g.seq("cur");
+    const int flow = flownet(g, s, H, W, X_NONE);
+    if (version == 101) {
+      const int cat = g.new_tensor(4096, h, w);
+      g.warp(s, X_FEAT_KEY, flow, g.new_view(cat, 0, 2048), X_FEAT_OUT);
+      bottleneck_net(g, s, "rbranch", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_NONE, g.new_view(cat, 2048, 2048));
+      int fused = g.conv(s, "fusion", cat, "corr", 2048, 1, 1, 0, 1, bias_epi("corr", ACT_NONE));
+      int sc = head(g, s, "head", fused, "fc6", "score", "upsampling", K);
+      g.tail(s, sc, "", X_LABEL_OUT, X_SCORE_OUT);
+    } else {
+      const int warped = g.new_tensor(2048, h, w);
+      g.warp(s, X_FEAT_KEY, flow, warped, X_FEAT_OUT);
+      const int sl = head(g, s, "head", warped, "fc6", "score", "upsampling", K);
+      if (version == 0) {
+        g.tail(s, sl, "", X_LABEL_OUT, X_SCORE_OUT);
+      } else {
+        int sr;
+        if (version == 50) {
+          int f = bottleneck_net(g, s, "rbranch", H, W, "50_", units_50(), DeformCfg{72, 2, 2, 4}, X_NONE, -1);
+          sr = head(g, s, "rhead", f, "curr_fc6", "curr_score", "curr_upsampling", K);
+        } else {
+          const std::string pre = std::to_string(version) + "_";
+          int f = preact_branch(g, s, "rbranch", H, W, pre,
+                                version == 18 ? std::vector<int>{2, 2, 2} : std::vector<int>{3, 4, 6},
+                                version == 18 ? "ab" : "abc");
+          sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K);
+        }
+        const int fused = g.new_tensor(K, h, w, true);
+        g.fuse(s, sl, sr, "corr", fused);
+        g.tail(s, fused, "corr_bias", X_LABEL_OUT, X_SCORE_OUT);
+      }
+    }
+  }
+  return true;
+}
+
+}  // namespace accel

@@ -1,0 +1,210 @@
+"""Engine: one AccelHandle (weights + plans for one Accel version and frame size on one GPU).
+
+PyTorch is only the device-memory / stream plumbing here: tensors go to the C ABI as raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .netspec import FEAT_DIM, NUM_CLASSES
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _check_f32_cuda(name, t, shape):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA float32 tensor" % name)
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+
+
+class Engine:
+    """Owns the device copies of the weights and the key/cur plans; the caller owns all I/O tensors
+    (SURVEY.md section 8b "Ownership")."""
+
+    def __init__(self, version, height, width, params=None, device=0, num_classes=NUM_CLASSES, flags=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("accel_b200: no CUDA device visible -- this path has no CPU fallback")
+        self.version = str(version)
+        if self.version not in _lib.VERSION_CODE:
+            raise ValueError("unknown Accel version %r" % (version,))
+        self.height, self.width, self.num_classes, self.device = int(height), int(width), int(num_classes), int(device)
+        cfg = _lib.AccelConfig(_lib.VERSION_CODE[self.version], self.height, self.width, self.num_classes, self.device,
+                               int(flags))
+        h = C.c_void_p()
+        if self.lib.accel_create(C.byref(cfg), C.byref(h)) != 0:
+            raise RuntimeError("accel_create failed: %s" % self.lib.accel_last_error(None).decode())
+        self._h = h
+        self.torch_device = torch.device("cuda", self.device)
+        if params is not None:
+            self.set_params(params)
+
+    # ---- parameters -----------------------------------------------------------------------------
+    def param_spec(self):
+        out = {}
+        name, shape, ndim = C.c_char_p(), (C.c_int64 * 4)(), C.c_int()
+        for i in range(self.lib.accel_param_count(self._h)):
+            self.lib.accel_param_info(self._h, i, C.byref(name), shape, C.byref(ndim))
+            out[name.value.decode()] = tuple(shape[j] for j in range(ndim.value))
+        return out
+
+    def set_params(self, params, finalize=True):
+        """params: {reference parameter name: array-like fp32}; arg_params and aux_params merged
+        (lib/utils/load_model.py:73-93).  Unknown names are ignored the way MXNet's
+        init_params(allow_extra) would; missing ones fail at finalize."""
+        spec = self.param_spec()
+        for name, value in params.items():
+            if name not in spec:
+                continue
+            a = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            if self.lib.accel_set_param(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim) != 0:
+                raise RuntimeError(self._err())
+        if finalize:
+            self.finalize()
+
+    def finalize(self):
+        with torch.cuda.device(self.torch_device):
+            if self.lib.accel_finalize(self._h) != 0:
+                raise RuntimeError("accel_finalize failed: %s" % self._err())
+
+    # ---- forward ------------------------------------------------------------------------------------
+    @property
+    def feat_shape(self):
+        return (1, FEAT_DIM, self.height // 16, self.width // 16)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.torch_device).cuda_stream)
+
+    def key_forward(self, data, feat_out=None, score_out=None, label_out=None):
+        _check_f32_cuda("data", data, (1, 3, self.height, self.width))
+        if feat_out is not None:
+            _check_f32_cuda("feat_out", feat_out, self.feat_shape)
+        if score_out is not None:
+            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width))
+        with torch.cuda.device(self.torch_device):
+            rc = self.lib.accel_key_forward(self._h, _ptr(data), _ptr(feat_out), _ptr(score_out), _ptr(label_out),
+                                            self._stream())
+        if rc != 0:
+            raise RuntimeError("accel_key_forward failed: %s" % self._err())
+
+    def cur_forward(self, data, data_key, feat_key, feat_out=None, score_out=None, label_out=None):
+        _check_f32_cuda("data", data, (1, 3, self.height, self.width))
+        _check_f32_cuda("data_key", data_key, (1, 3, self.height, self.width))
+        _check_f32_cuda("feat_key", feat_key, self.feat_shape)
+        if feat_out is not None:
+            _check_f32_cuda("feat_out", feat_out, self.feat_shape)
+        if score_out is not None:
+            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width))
+        with torch.cuda.device(self.torch_device):
+            rc = self.lib.accel_cur_forward(self._h, _ptr(data), _ptr(data_key), _ptr(feat_key), _ptr(feat_out),
+                                            _ptr(score_out), _ptr(label_out), self._stream())
+        if rc != 0:
+            raise RuntimeError("accel_cur_forward failed: %s" % self._err())
+
+    def flownet(self, data, data_key, flow_out=None):
+        if flow_out is None:
+            flow_out = torch.empty(1, 2, self.height // 16, self.width // 16, device=self.torch_device)
+        with torch.cuda.device(self.torch_device):
+            rc = self.lib.accel_flownet(self._h, _ptr(data), _ptr(data_key), _ptr(flow_out), self._stream())
+        if rc != 0:
+            raise RuntimeError("accel_flownet failed: %s" % self._err())
+        return flow_out
+
+    # ---- introspection ------------------------------------------------------------------------------------
+    def last_launch_count(self):
+        return self.lib.accel_last_launch_count(self._h)
+
+    def set_profiling(self, on):
+        self.lib.accel_set_profiling(self._h, 1 if on else 0)
+
+    def stage_times(self):
+        names, ms = (C.c_char_p * 32)(), (C.c_float * 32)()
+        n = self.lib.accel_stage_times(self._h, names, ms, 32)
+        return {names[i].decode(): float(ms[i]) for i in range(max(n, 0))}
+
+    def _err(self):
+        return self.lib.accel_last_error(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.accel_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- operator-level wrappers (mirror the MXNet built-ins the symbol files call) ------------------------
+def warp(feat, flow, out=None):
+    """GridGenerator(transform_type='warp') + BilinearSampler, accel_18.py:174-175."""
+    lib = _lib.load()
+    n, c, h, w = feat.shape
+    assert n == 1 and tuple(flow.shape) == (1, 2, h, w)
+    if out is None:
+        out = torch.empty_like(feat)
+    st = C.c_void_p(torch.cuda.current_stream(feat.device).cuda_stream)
+    with torch.cuda.device(feat.device):
+        rc = lib.accel_warp(_ptr(feat.contiguous()), _ptr(flow.contiguous()), _ptr(out), c, h, w, st)
+    if rc != 0:
+        raise RuntimeError("accel_warp failed (%d)" % rc)
+    return out
+
+
+def fuse_argmax(score_a, score_b=None, corr_weight=None, corr_bias=None, want_scores=False):
+    """x16 upsampling + Crop(8,8) of the low-res score map(s), 1x1 `correction` fusion, argmax."""
+    lib = _lib.load()
+    n, k, h, w = score_a.shape
+    dev = score_a.device
+    label = torch.empty(16 * h, 16 * w, dtype=torch.uint8, device=dev)
+    full = torch.empty(1, k, 16 * h, 16 * w, device=dev) if want_scores else None
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    cw = corr_weight.reshape(k, 2 * k).contiguous() if corr_weight is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.accel_fuse_argmax(_ptr(score_a.contiguous()), _ptr(score_b.contiguous() if score_b is not None else None),
+                                   _ptr(cw), _ptr(corr_bias), k, h, w, _ptr(label), _ptr(full), st)
+    if rc != 0:
+        raise RuntimeError("accel_fuse_argmax failed (%d)" % rc)
+    return (label, full) if want_scores else label
+
+
+def conv_layer(x, weight, kind="conv", stride=1, pad=0, dilate=1, scale=None, shift=None, act=0, residual=None,
+               offset=None, deform_groups=1, engine=0):
+    """One layer through the library's kernels (parity-test hook, accel_conv_layer)."""
+    lib = _lib.load()
+    kinds = {"conv": 0, "deconv": 1, "deform": 2}
+    n, cin, hin, win = x.shape
+    w = np.ascontiguousarray(weight.detach().cpu().numpy(), dtype=np.float32)
+    if kind == "deconv":
+        cout, k = w.shape[1], 4
+        ho, wo = 2 * hin, 2 * win
+    else:
+        cout, k = w.shape[0], w.shape[2]
+        ho = (hin + 2 * pad - (dilate * (k - 1) + 1)) // stride + 1
+        wo = (win + 2 * pad - (dilate * (k - 1) + 1)) // stride + 1
+    out = torch.empty(1, cout, ho, wo, device=x.device)
+    sc = np.ascontiguousarray(scale.detach().cpu().numpy(), dtype=np.float32) if scale is not None else None
+    sh = np.ascontiguousarray(shift.detach().cpu().numpy(), dtype=np.float32) if shift is not None else None
+    err = C.create_string_buffer(512)
+    with torch.cuda.device(x.device):
+        torch.cuda.synchronize()
+        rc = lib.accel_conv_layer(kinds[kind], _ptr(x.contiguous()), cin, hin, win, w.ctypes.data_as(C.c_void_p), cout, k,
+                                  stride, pad, dilate, deform_groups, _ptr(offset.contiguous() if offset is not None else None),
+                                  sc.ctypes.data_as(C.c_void_p) if sc is not None else None,
+                                  sh.ctypes.data_as(C.c_void_p) if sh is not None else None, act,
+                                  _ptr(residual.contiguous() if residual is not None else None), engine, _ptr(out),
+                                  x.device.index or 0, err, 512)
+    if rc != 0:
+        raise RuntimeError("accel_conv_layer failed: %s" % err.value.decode())
+    return out

@@ -1,0 +1,116 @@
+"""Keyframe scheduling for the Accel hot path: the control flow of the reference's two loops.
+
+chained   -- dff_deeplab/demo.py:165-250.  Frame idx is a key frame when idx % interval == 0;
+             otherwise the cur graph runs with data_key = the PREVIOUS frame and feat_key = the
+             feature returned by the previous call (key feature or warped feature).
+unchained -- dff_deeplab/core/loader.py:259-303 + core/tester.py:246-256 (pred_eval).  data_key is
+             the KEY frame and feat_key stays the key frame's res5c feature for the whole interval.
+
+`key_frame_flags` reproduces TestLoader's flag stream (0 first key frame of a video, 1 later key
+frames, 2 non-key frames).  `shard_streams` is the per-GPU assignment of whole videos
+(dff_rfcn/function/test_rcnn.py:60-67: greedy, least-loaded GPU first).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .predictor import DataBatch, feat_key_placeholder, im_segment
+
+SCHEDULES = ("chained", "unchained")
+
+
+def key_frame_flags(num_frames, interval):
+    if interval < 1:
+        raise ValueError("Invalid interval %d - must be >=1" % interval)     # demo.py:120-121
+    flags, key = [], 0
+    for cur in range(num_frames):
+        if cur - key == interval:                                             # loader.py:268-269
+            key = cur
+        flags.append((0 if key == 0 else 1) if key == cur else 2)
+    return flags
+
+
+def shard_streams(stream_lengths, num_gpus):
+    """Greedy assignment of whole streams to the least-loaded GPU (test_rcnn.py:60-67).
+    Returns a list (per GPU) of stream indices."""
+    load = [0] * num_gpus
+    shards = [[] for _ in range(num_gpus)]
+    for idx, n in enumerate(stream_lengths):
+        g = int(np.argmin(load))
+        shards[g].append(idx)
+        load[g] += int(n)
+    return shards
+
+
+def run_reference_loop(key_predictor, cur_predictor, frames, interval, version, schedule="chained"):
+    """The demo.py:228-250 loop, literally, over Predictor objects: returns per-frame dicts with the
+    score volume and the argmax'ed uint8 label map (np.uint8(argmax), demo.py:245,252)."""
+    if schedule not in SCHEDULES:
+        raise ValueError("schedule must be one of %s" % (SCHEDULES,))
+    dev = frames[0].device
+    results = []
+    feat = None
+    prev = key_img = None
+    for idx, data in enumerate(frames):
+        if prev is None:
+            prev = data
+        is_key = idx % interval == 0
+        if is_key:
+            key_img = data
+        data_key = prev if schedule == "chained" else key_img
+        batch = DataBatch(data=[[data, data_key, feat_key_placeholder(dev)]])
+        if is_key:
+            output_all, feat_new = im_segment(key_predictor, batch)
+            score = output_all[0]["croped_score_output"]
+            feat = feat_new
+        else:
+            batch.data[0][-1] = feat                                           # demo.py:241
+            output_all, feat_new = im_segment(cur_predictor, batch)
+            output_key = "croped_score_output" if version in ("101", "dff") else "correction_output"
+            score = output_all[0][output_key]
+            if schedule == "chained":
+                feat = feat_new
+        label = torch.argmax(score, dim=1).to(torch.uint8)[0]
+        results.append({"is_key": is_key, "label": label.clone(), "score": score.clone(),
+                        "label_output": output_all[0]["label_output"].clone(), "feat": feat.clone()})
+        prev = data
+    return results
+
+
+class StreamState:
+    """Per-video state the schedule carries between frames: {feat, data_key}."""
+
+    def __init__(self, engine):
+        dev = engine.torch_device
+        self.feat = [torch.empty(engine.feat_shape, device=dev) for _ in range(2)]
+        self.cur = 0
+        self.key_frame = None
+        self.prev_frame = None
+        self.index = 0
+
+
+def segment_frame(engine, state, data, interval, schedule, label_out, score_out=None):
+    """Production step (no score volume unless asked): one frame of one stream through the
+    key/cur plans with double-buffered features.  Returns True when it was a key frame."""
+    is_key = state.index % interval == 0
+    if is_key:
+        engine.key_forward(data, state.feat[state.cur], score_out, label_out)
+        state.key_frame = data
+    elif schedule == "chained":
+        nxt = state.cur ^ 1
+        engine.cur_forward(data, state.prev_frame, state.feat[state.cur], state.feat[nxt], score_out, label_out)
+        state.cur = nxt
+    else:
+        engine.cur_forward(data, state.key_frame, state.feat[state.cur], None, score_out, label_out)
+    state.prev_frame = data
+    state.index += 1
+    return is_key
+
+
+def confusion_matrix(pred, label, n):
+    """fast_hist of demo.py:50-53 on the GPU (int64 n x n; rows = label)."""
+    pred = pred.reshape(-1).long()
+    label = label.reshape(-1).long()
+    k = (label >= 0) & (label < n)
+    return torch.bincount(n * label[k] + pred[k], minlength=n * n).reshape(n, n)

@@ -1,0 +1,127 @@
+/* accel_b200 -- C ABI of the B200-native Accel (dff_deeplab) per-frame hot path.
+ *
+ * Everything the reference does per video frame between "two preprocessed frames are in device
+ * memory" and "a label map exists" happens behind these calls.  File:line citations are relative
+ * to the reference tree (SamvitJ/Accel @ d1d7bb1).
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers to dense fp32 NCHW data (batch 1), exactly the arrays
+ *     the reference's Predictor exchanges (dff_deeplab/core/tester.py:22-35, demo.py:184), except
+ *     where a parameter is documented as host memory.
+ *   - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream).  A handle is bound to one device and must not be used from two threads at once.
+ *   - Every function returns 0 on success, non-zero on failure; accel_last_error() returns the
+ *     message.  No C++ exception crosses this boundary.  There is no CPU fallback: without a CUDA
+ *     device accel_create succeeds only far enough to enumerate parameters, and every compute entry
+ *     point fails with an error.
+ */
+#ifndef ACCEL_B200_H_
+#define ACCEL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct AccelHandle AccelHandle;
+
+/* Which `accel_<version>` symbol file the cur-frame graph follows
+ * (dff_deeplab/symbols/accel_{18,34,50,101}.py; demo.py:126-132 `--version`).
+ * ACCEL_VERSION_DFF = the L branch alone: FlowNet + warp + task head (Deep Feature Flow). */
+enum { ACCEL_VERSION_DFF = 0, ACCEL_VERSION_18 = 18, ACCEL_VERSION_34 = 34, ACCEL_VERSION_50 = 50,
+       ACCEL_VERSION_101 = 101 };
+
+/* accel_create flags */
+enum { ACCEL_FLAG_NO_TENSOR_CORES = 1 /* run every contraction on the CUDA-core (fp32 FFMA) kernels */,
+       ACCEL_FLAG_NO_GRAPH = 2        /* launch kernels one by one instead of replaying a CUDA graph */ };
+
+typedef struct AccelConfig {
+  int version;      /* ACCEL_VERSION_* */
+  int height;       /* frame size; multiples of 128 (config.SCALES 1024x2048, dff_deeplab_vid_demo.yaml:5-7) */
+  int width;
+  int num_classes;  /* 19 (cfg.dataset.NUM_CLASSES) */
+  int device;       /* CUDA device ordinal */
+  int flags;
+} AccelConfig;
+
+/* Replaces Predictor.__init__ -> MutableModule.bind (tester.py:22-30): builds the key-frame and
+ * cur-frame plans for the configured frame size. */
+int accel_create(const AccelConfig* config, AccelHandle** out);
+void accel_destroy(AccelHandle* h);
+/* Message of the last failure on `h` (or of the last failed accel_create when h == NULL). */
+const char* accel_last_error(const AccelHandle* h);
+
+/* Parameter inventory: the `arg:`/`aux:` tensors of the two reference checkpoints this version
+ * reads (lib/utils/load_model.py:15-30, demo.py:192-195), by reference name. */
+int accel_param_count(const AccelHandle* h);
+int accel_param_info(const AccelHandle* h, int index, const char** name, int64_t shape[4], int* ndim);
+
+/* Replaces MutableModule.init_params(arg_params, aux_params) (tester.py:30) for one tensor.
+ * `data` is HOST memory, fp32, dense, in the reference's own layout; shape must match. */
+int accel_set_param(AccelHandle* h, const char* name, const float* data, const int64_t* shape, int ndim);
+/* Folds BatchNorm statistics, splits and packs the weights, uploads them, allocates workspaces.
+ * Fails if a parameter is missing.  Called implicitly by the first forward. */
+int accel_finalize(AccelHandle* h);
+
+/* Key-frame graph, get_key_test_symbol (accel_18.py:121-159): R101-DCN -> fc6 -> score -> x16
+ * upsampling -> crop, plus the argmax of demo.py:238.
+ *   data       in  (1,3,H,W)
+ *   feat_out   out (1,2048,H/16,W/16)  `res5c_relu_output`;            may be NULL
+ *   score_out  out (1,19,H,W)          `croped_score_output`;          may be NULL (production)
+ *   label_out  out (H,W) uint8         argmax over classes (demo.py:238,252); may be NULL */
+int accel_key_forward(AccelHandle* h, const float* data, float* feat_out, float* score_out, uint8_t* label_out,
+                      void* stream);
+
+/* Cur-frame graph, get_cur_test_symbol (accel_18.py:161-239, accel_101.py:144-193): FlowNet(data,
+ * data_key) -> warp(feat_key) -> L head [-> R branch -> fusion] -> argmax (demo.py:243-245).
+ *   feat_key   in  (1,2048,H/16,W/16)  previous frame's feature (chained, demo.py:241) or the key
+ *                                      frame's (un-chained, tester.py:252-256)
+ *   feat_out   out `warping_feat_output`; must not alias feat_key;     may be NULL
+ *   score_out  out `correction_output` (18/34/50) or `croped_score_output` (101, dff); may be NULL */
+int accel_cur_forward(AccelHandle* h, const float* data, const float* data_key, const float* feat_key,
+                      float* feat_out, float* score_out, uint8_t* label_out, void* stream);
+
+/* FlowNet-S alone, get_flownet (resnet_v1_101_flownet_deeplab.py:1751-1808): flow_out (1,2,H/16,W/16),
+ * channel 0 = dx, 1 = dy in feature-grid pixels, already multiplied by 2.5. */
+int accel_flownet(AccelHandle* h, const float* data, const float* data_key, float* flow_out, void* stream);
+
+/* ---- operator-level entry points (no handle; mirror the MXNet built-ins the symbols call) ---- */
+
+/* mx.sym.GridGenerator(data=flow, transform_type='warp') + mx.sym.BilinearSampler(data=feat, grid)
+ * (accel_18.py:174-175).  feat, out: (1,C,H,W); flow: (1,2,H,W). */
+int accel_warp(const float* feat, const float* flow, float* out, int channels, int height, int width,
+               void* stream);
+
+/* Concat(dim=1) -> correction 1x1 (2K -> K, +bias) on the x16-upsampled, cropped score maps, then
+ * argmax (accel_18.py:193-197,223-235; demo.py:245).  score_a/score_b: low-res (1,K,h,w) outputs of
+ * the `score` / `<v>_score` convs; corr_weight (K,2K) and corr_bias (K) are DEVICE pointers, NULL
+ * for both = no fusion (key / Accel-101 tail: score_b ignored).  label: (16h,16w) uint8;
+ * score_full: (1,K,16h,16w) or NULL. */
+int accel_fuse_argmax(const float* score_a, const float* score_b, const float* corr_weight,
+                      const float* corr_bias, int num_classes, int h, int w, uint8_t* label,
+                      float* score_full, void* stream);
+
+/* One convolution-like layer through the same kernels the graphs use; parity-test hook.
+ *   kind: 0 Convolution, 1 Deconvolution(k4,s2,p1 after crop), 2 DeformableConvolution(3x3,s1)
+ *   in (1,cin,hin,win) device; weight/scale/shift HOST (weight in MXNet layout; scale/shift per
+ *   output channel, NULL = 1/0); offset (device, deformable only); residual (device, NCHW, or NULL)
+ *   act: 0 none, 1 relu, 2 leaky(0.1); engine: 0 auto, 1 CUDA-core, 2 tcgen05
+ *   out (1,cout,hout,wout) device. */
+int accel_conv_layer(int kind, const float* in, int cin, int hin, int win, const float* weight, int cout,
+                     int ksize, int stride, int pad, int dilate, int deform_groups, const float* offset,
+                     const float* scale, const float* shift, int act, const float* residual, int engine,
+                     float* out, int device, char* err, int errlen);
+
+/* Number of kernel launches issued by the most recent forward on `h` (bench.py's gpu_launches). */
+int accel_last_launch_count(const AccelHandle* h);
+/* Per-stage device time of the most recent forward, when profiling was enabled with
+ * accel_set_profiling(h, 1): fills up to `cap` (name, milliseconds) pairs, returns the count. */
+int accel_set_profiling(AccelHandle* h, int enabled);
+int accel_stage_times(AccelHandle* h, const char** names, float* ms, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACCEL_B200_H_ */

@@ -1,0 +1,80 @@
+"""C-ABI library: loads, exports every declared symbol, enumerates parameters without a GPU, and
+refuses to compute without one (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from accel_b200 import _lib, netspec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported(lib):
+    header = open(os.path.join(ROOT, "include", "accel_b200.h")).read()
+    declared = set(re.findall(r"\b(accel_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def _create(lib, version, h=128, w=256, flags=0):
+    cfg = _lib.AccelConfig(_lib.VERSION_CODE[version], h, w, 19, 0, flags)
+    handle = C.c_void_p()
+    rc = lib.accel_create(C.byref(cfg), C.byref(handle))
+    return rc, handle
+
+
+@pytest.mark.parametrize("version", netspec.VERSIONS)
+def test_param_inventory_matches_python_spec(lib, version):
+    rc, h = _create(lib, version)
+    assert rc == 0, lib.accel_last_error(None)
+    got = {}
+    name, shape, ndim = C.c_char_p(), (C.c_int64 * 4)(), C.c_int()
+    for i in range(lib.accel_param_count(h)):
+        assert lib.accel_param_info(h, i, C.byref(name), shape, C.byref(ndim)) == 0
+        got[name.value.decode()] = tuple(shape[j] for j in range(ndim.value))
+    want = {k: tuple(v[0]) for k, v in netspec.param_spec(version).items()}
+    assert set(got) == set(want), (sorted(set(got) - set(want))[:5], sorted(set(want) - set(got))[:5])
+    for k in want:
+        assert got[k] == want[k], k
+    lib.accel_destroy(h)
+
+
+def test_create_rejects_bad_config(lib):
+    rc, _ = _create(lib, "18", h=100, w=256)
+    assert rc != 0 and b"multiples of 128" in lib.accel_last_error(None)
+    cfg = _lib.AccelConfig(77, 128, 256, 19, 0, 0)
+    handle = C.c_void_p()
+    assert lib.accel_create(C.byref(cfg), C.byref(handle)) != 0
+
+
+def test_set_param_checks_names_and_shapes(lib):
+    rc, h = _create(lib, "dff")
+    assert rc == 0
+    import numpy as np
+    a = np.zeros((1024, 2048, 1, 1), dtype=np.float32)
+    shp = (C.c_int64 * 4)(*a.shape)
+    assert lib.accel_set_param(h, b"fc6_weight", a.ctypes.data_as(C.c_void_p), shp, 4) == 0
+    assert lib.accel_set_param(h, b"no_such_weight", a.ctypes.data_as(C.c_void_p), shp, 4) != 0
+    assert b"unknown parameter" in lib.accel_last_error(h)
+    bad = (C.c_int64 * 4)(1024, 2047, 1, 1)
+    assert lib.accel_set_param(h, b"fc6_weight", a.ctypes.data_as(C.c_void_p), bad, 4) != 0
+    assert b"shape mismatch" in lib.accel_last_error(h)
+    lib.accel_destroy(h)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    rc, h = _create(lib, "dff")
+    assert rc == 0
+    assert lib.accel_finalize(h) != 0
+    assert b"no CUDA device" in lib.accel_last_error(h) or b"never set" in lib.accel_last_error(h)
+    buf = (C.c_float * 16)()
+    assert lib.accel_warp(buf, buf, (C.c_float * 16)(), 1, 2, 2, None) != 0
+    lib.accel_destroy(h)
+    from accel_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine("dff", 128, 256)

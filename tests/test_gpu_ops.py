@@ -1,0 +1,138 @@
+"""Operator-level parity of the CUDA kernels against the CPU oracle, through the C ABI (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from accel_b200 import engine as E
+from oracle import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+# ----------------------------------------------------------------------------- warp (a2)
+@pytest.mark.parametrize("c,h,w", [(64, 8, 16), (2048, 8, 16), (96, 13, 37), (2048, 64, 128)])
+def test_warp_is_bit_exact_vs_oracle(c, h, w):
+    feat = _rand(1, c, h, w, seed=1)
+    flow = _rand(1, 2, h, w, seed=2, scale=3.0)                 # several samples leave the map
+    flow[0, :, 0, 0] = torch.tensor([1e12, -1e12])              # absurd flow: every tap out of range -> 0
+    ref = ops.bilinear_sampler(feat, ops.grid_generator_warp(flow))
+    out = E.warp(feat.to(DEV), flow.to(DEV)).cpu()
+    assert torch.equal(out, ref)
+
+
+def test_warp_zero_flow_identity_and_integer_shift():
+    feat = _rand(1, 32, 16, 32, seed=3)
+    zero = torch.zeros(1, 2, 16, 32)
+    assert torch.allclose(E.warp(feat.to(DEV), zero.to(DEV)).cpu(), feat, atol=1e-5)
+    flow = zero.clone()
+    flow[:, 0] = 3.0
+    out = E.warp(feat.to(DEV), flow.to(DEV)).cpu()
+    assert torch.allclose(out[..., :29], feat[..., 3:], atol=1e-4) and torch.all(out[..., 29:] == 0)
+
+
+# ----------------------------------------------------------------------------- tail (a3/a10/a12)
+def _oracle_tail(a, b, wc, bc):
+    k = a.shape[1]
+    up = lambda s: ops.deconvolution(s, ops.bilinear_upsampling_weight(k), None, 16, 0, num_group=k)[
+        :, :, 8:8 + 16 * s.shape[2], 8:8 + 16 * s.shape[3]]
+    if wc is None:
+        return up(a)
+    return ops.convolution(torch.cat([up(a), up(b)], dim=1), wc, bc)
+
+
+@pytest.mark.parametrize("h,w", [(8, 16), (5, 7), (64, 128)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_tail_scores_and_labels(h, w, fused):
+    k = 19
+    a, b = _rand(1, k, h, w, seed=4, scale=3.0), _rand(1, k, h, w, seed=5, scale=3.0)
+    wc = (_rand(k, 2 * k, 1, 1, seed=6, scale=0.05) + torch.cat([torch.eye(k), torch.eye(k)], 1).view(k, 2 * k, 1, 1) * 0.5) if fused else None
+    bc = _rand(k, seed=7, scale=0.1) if fused else None
+    ref = _oracle_tail(a, b, wc, bc)
+    label, full = E.fuse_argmax(a.to(DEV), b.to(DEV) if fused else None, wc.to(DEV) if fused else None,
+                                bc.to(DEV) if fused else None, want_scores=True)
+    full, label = full.cpu(), label.cpu().numpy()
+    assert (full - ref).abs().max().item() < 2e-5
+    # integer work: the label map is bit-exactly the lowest-index argmax of the emitted score volume
+    assert np.array_equal(label, ops.argmax_channel(full)[0])
+    # and agrees with the oracle's labels wherever the oracle's top-2 margin exceeds the fp32 noise
+    top2 = ref.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])[0].numpy()
+    assert np.array_equal(label[margin > 1e-4], ops.argmax_channel(ref)[0][margin > 1e-4])
+
+
+def test_tail_ties_take_lowest_class():
+    s = torch.zeros(1, 19, 4, 4)
+    s[0, 7] = 1.0
+    s[0, 11] = 1.0
+    label = E.fuse_argmax(s.to(DEV)).cpu().numpy()
+    assert label.shape == (64, 64) and label.dtype == np.uint8
+    assert np.all(label == 7)
+    label0 = E.fuse_argmax(torch.zeros(1, 19, 4, 4).to(DEV)).cpu().numpy()
+    assert np.all(label0 == 0)
+
+
+# ----------------------------------------------------------------------------- conv engines (a1, a3-a9)
+CONV_CASES = [
+    # cin, cout, h, w, k, stride, pad, dil
+    (64, 64, 16, 32, 3, 1, 1, 1),
+    (64, 128, 16, 32, 3, 2, 1, 1),
+    (64, 128, 16, 32, 1, 2, 0, 1),
+    (128, 256, 16, 16, 5, 2, 2, 1),
+    (256, 72, 8, 16, 3, 1, 2, 2),
+    (194, 2, 8, 16, 3, 1, 1, 1),
+    (1026, 2, 2, 4, 3, 1, 1, 1),
+    (2048, 1024, 8, 16, 1, 1, 0, 1),
+    (1024, 19, 8, 16, 1, 1, 0, 1),
+    (512, 512, 2, 4, 3, 1, 1, 1),
+    (386, 64, 9, 11, 3, 1, 1, 1),
+]
+
+
+def _tol(ref):
+    return 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_layer_matches_torch(case, engine):
+    cin, cout, h, w, k, s, p, d = case
+    if engine == 2 and cout <= 8:
+        pytest.skip("narrow outputs always take the CUDA-core kernel")
+    x = _rand(1, cin, h, w, seed=10)
+    wt = _rand(cout, cin, k, k, seed=11, scale=(2.0 / (cin * k * k)) ** 0.5)
+    scale, shift = torch.rand(cout, generator=torch.Generator().manual_seed(12)) + 0.5, _rand(cout, seed=13, scale=0.1)
+    ref = F.conv2d(x, wt, None, s, p, d) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = _rand(*ref.shape, seed=14)
+    ref = F.relu(ref + res)
+    out = E.conv_layer(x.to(DEV), wt, "conv", s, p, d, scale, shift, act=1, residual=res.to(DEV), engine=engine).cpu()
+    assert (out - ref).abs().max().item() < _tol(ref)
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("cin,cout,h,w", [(1024, 512, 2, 4), (386, 64, 8, 16), (512, 2048, 4, 8)])
+def test_deconv_layer_matches_torch(cin, cout, h, w, engine):
+    x = _rand(1, cin, h, w, seed=20)
+    wt = _rand(cin, cout, 4, 4, seed=21, scale=(2.0 / (cin * 4)) ** 0.5)
+    shift = _rand(cout, seed=22, scale=0.1)
+    ref = ops.leaky_relu(F.conv_transpose2d(x, wt, shift, stride=2, padding=1))
+    out = E.conv_layer(x.to(DEV), wt, "deconv", shift=shift, act=2, engine=engine).cpu()
+    assert (out - ref).abs().max().item() < _tol(ref)
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("dg", [1, 4])
+def test_deformable_layer_matches_oracle(dg, engine):
+    cin, cout, h, w = 64, 64, 12, 20
+    x = _rand(1, cin, h, w, seed=30)
+    wt = _rand(cout, cin, 3, 3, seed=31, scale=(2.0 / (cin * 9)) ** 0.5)
+    off = _rand(1, dg * 18, h, w, seed=32, scale=1.5)           # some taps leave the map / hit the border ring
+    ref = ops.deformable_convolution(x, off, wt, 1, 2, 2, dg)
+    out = E.conv_layer(x.to(DEV), wt, "deform", 1, 2, 2, offset=off.to(DEV), deform_groups=dg, engine=engine).cpu()
+    assert (out - ref).abs().max().item() < _tol(ref)
