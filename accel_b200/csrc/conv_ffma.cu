@@ -224,6 +224,13 @@ cudaError_t launch_conv_ffma(const ConvParams& P, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_splitk_epilogue(const float* partial, int splits, int npix, int Cout_pad, int Wo, const Epilogue& epi,
+                                   cudaStream_t stream) {
+  const long long work = (long long)npix * ((epi.Cout + 3) / 4);
+  splitk_epilogue_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(partial, splits, npix, Cout_pad, Wo, epi);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_conv_narrow(const ConvParams& P, cudaStream_t stream) {
   const int npix = P.Ho * P.Wo;
   const unsigned blocks = (unsigned)(((long long)npix * 32 + 255) / 256);

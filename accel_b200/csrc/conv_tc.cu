@@ -1,20 +1,462 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution -- placeholder until the kernel lands.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution over the split-fp16 NHWC format (sm_100a).
+//
+//   D[pixel, n] = sum over (tap, channel)  A[pixel @ tap, channel] * W[n, tap, channel]
+//
+// * M = 128 output pixels (a BH x BW spatial box), N = up to 256 output channels, K = 64 channels of
+//   one filter tap per pipeline stage.  Nothing is im2col'ed: the A tile of a tap is ONE TMA box load
+//   from the NHWC activation at the tap's spatial offset; out-of-image rows/columns (the conv padding)
+//   and channels past the end arrive as zeros from TMA's out-of-bounds fill.  Stride-2 layers view the
+//   activation as [H/2][2][W/2][2][C] so a tap is still a dense box.
+// * fp16x3: operands are (hi, lo) fp16 pairs; each K=16 slice issues three tcgen05.mma
+//   (hi*hi + hi*lo + lo*hi) into one fp32 TMEM accumulator -- fp32-grade products at 1/3 of the fp16
+//   tensor rate instead of falling back to CUDA cores.
+// * Warp-specialised persistent CTAs: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and
+//   TMEM owner, warps 2-5 = epilogue (tcgen05.ld -> scale/shift/residual/activation -> split NHWC and/or
+//   fp32 NCHW).  The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
+//   mainloop of tile i+1.  Small maps use deterministic split-K through an fp32 workspace.
+#include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "kernels.h"
 
 namespace accel {
 
-struct TcPlan { int unused; };
-bool tc_supported(const ConvParams&) { return false; }
-TcPlan* tc_plan_create(const ConvParams&, int, char* err, int errlen) {
-  if (err && errlen > 0) snprintf(err, errlen, "tcgen05 engine not built");
-  return nullptr;
+cudaError_t launch_splitk_epilogue(const float* partial, int splits, int npix, int Cout_pad, int Wo, const Epilogue& epi,
+                                   cudaStream_t stream);
+
+namespace {
+
+constexpr int BM = 128;          // pixels per tile (UMMA M)
+constexpr int BK = 64;           // channels per stage: 128 bytes of fp16 = one SWIZZLE_128B row
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+constexpr int kSmemBudget = 227 * 1024 - 2048;
+
+struct alignas(64) TcParams {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  Epilogue epi;
+  float* partial;
+  int BW, BH, BN, stages;
+  int tiles_x, tiles_y, n_tiles, splits, kiters, chunks, ntaps;
+  int stride2, Cin_pad, Ho, Wo, Cout_pad, tmem_cols;
+  int8_t dy[kMaxTaps];
+  int8_t dx[kMaxTaps];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-void tc_plan_destroy(TcPlan* p) { delete p; }
-size_t tc_plan_partial_bytes(const TcPlan*) { return 0; }
-void tc_plan_set_partial(TcPlan*, float*) {}
-cudaError_t launch_conv_tc_ext(const TcPlan*, float*, cudaStream_t) { return cudaErrorNotSupported; }
-int tc_plan_launches(const TcPlan*) { return 0; }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("accel_b200: conv_tc mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+         bar, parity);
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  // operand ring: [stage][A_hi | A_lo | B_hi | B_lo]
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = BM * 128u, b_bytes = (uint32_t)P.BN * 128u;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * kMaxStages]), tempty0 = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles = P.tiles_x * P.tiles_y * P.n_tiles;
+  const int items = tiles * P.splits;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % P.splits, tile = item / P.splits;
+        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
+        const int kb = (int)(((long long)P.kiters * split) / P.splits);
+        const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
+        for (int it = kb; it < ke; ++it) {
+          const int t = it / P.chunks, kc = it - t * P.chunks;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t fb = full0 + 8 * s;
+          mbar_arrive_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem0 + s * stage_bytes;
+          const int dy = P.dy[t], dx = P.dx[t];
+          if (P.stride2) {
+            tma_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+            tma_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+          } else {
+            tma_load_3d(sa, &P.a_hi, fb, kc * BK, x0 + dx, y0 + dy);
+            tma_load_3d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, y0 + dy);
+          }
+          const int kcol = t * P.Cin_pad + kc * BK;
+          tma_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nt * P.BN);
+          tma_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nt * P.BN);
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, accph = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % P.splits;
+        const int kb = (int)(((long long)P.kiters * split) / P.splits);
+        const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
+        mbar_wait(tempty0 + 8 * acc, accph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_base + (uint32_t)(acc * P.BN);
+        for (int it = kb; it < ke; ++it) {
+          mbar_wait(full0 + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem0 + s * stage_bytes;
+          const uint64_t ah = umma_desc(sa), al = umma_desc(sa + a_bytes);
+          const uint64_t bh = umma_desc(sa + 2 * a_bytes), bl = umma_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes along K inside the swizzle atom
+            umma_f16(d, ah + adv, bh + adv, idesc, (it > kb || k > 0) ? 1u : 0u);
+            umma_f16(d, ah + adv, bl + adv, idesc, 1u);
+            umma_f16(d, al + adv, bh + adv, idesc, 1u);
+          }
+          umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull0 + 8 * acc);                    // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue ==========================================
+    const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
+    const int r = quarter * 32 + lane;                     // tile row = pixel inside the box
+    const int by = r / P.BW, bx = r - by * P.BW;
+    const int npix = P.Ho * P.Wo;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int split = item % P.splits, tile = item / P.splits;
+      const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+      const int x = (mt % P.tiles_x) * P.BW + bx, y = (mt / P.tiles_x) * P.BH + by;
+      const bool valid = x < P.Wo && y < P.Ho;
+      mbar_wait(tfull0 + 8 * acc, accph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN);
+      for (int cc = 0; cc < P.BN; cc += 32) {
+        float v[32];
+        tmem_ld32(taddr + cc, v);
+        const int n0 = nt * P.BN + cc;
+        if (!valid || n0 >= P.Cout_pad) continue;
+        if (P.splits > 1) {
+          float4* dst = reinterpret_cast<float4*>(P.partial + ((size_t)split * npix + (size_t)y * P.Wo + x) * P.Cout_pad + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+          const int pix = (y * P.epi.osy + P.epi.ooy) * P.epi.OWf + x * P.epi.osx + P.epi.oox;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (n0 + g * 8 < P.epi.Cout) epilogue_store<8>(P.epi, pix, n0 + g * 8, v + g * 8);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; accph ^= 1; }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+            const cuuint32_t* box, char* err, int errlen) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled is unavailable");
+    return false;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu] box [%u %u %u]", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull, box[0],
+             box[1], rank > 2 ? box[2] : 0u);
+    return false;
+  }
+  return true;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct TcPlan {
+  TcParams p;
+  int grid;
+  size_t smem;
+  size_t partial_bytes;
+  int launches;
+};
+
+bool tc_supported(const ConvParams& P) {
+  if (P.epi.Cout <= 8) return false;
+  if (P.stride != 1 && P.stride != 2) return false;
+  if (P.stride == 2 && ((P.Hin & 1) || (P.Win & 1))) return false;
+  if (P.in_ld % 8 || P.Cin_pad % BK || P.Kpad % 8) return false;
+  if (((uintptr_t)P.in_hi & 15) || ((uintptr_t)P.in_lo & 15)) return false;
+  return true;
+}
+
+TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) {
+  if (!tc_supported(C)) {
+    snprintf(err, errlen, "shape not supported by the tcgen05 engine");
+    return nullptr;
+  }
+  TcPlan* plan = new TcPlan();
+  TcParams& P = plan->p;
+  memset(&P, 0, sizeof(P));
+  P.epi = C.epi;
+  P.ntaps = C.ntaps;
+  memcpy(P.dy, C.dy, sizeof(P.dy));
+  memcpy(P.dx, C.dx, sizeof(P.dx));
+  P.stride2 = C.stride == 2;
+  P.Cin_pad = C.Cin_pad;
+  P.Ho = C.Ho; P.Wo = C.Wo; P.Cout_pad = C.Cout_pad;
+  P.chunks = (C.Cin + BK - 1) / BK;            // channel chunks that hold real data (padding chunks are all-zero)
+  P.kiters = P.ntaps * P.chunks;
+
+  // spatial box: BW x BH = 128 pixels, BW the largest power of two <= min(Wo, 128)
+  int bw = 1;
+  while (bw * 2 <= C.Wo && bw * 2 <= BM) bw *= 2;
+  P.BW = bw; P.BH = BM / bw;
+  P.tiles_x = (C.Wo + P.BW - 1) / P.BW;
+  P.tiles_y = (C.Ho + P.BH - 1) / P.BH;
+  int bn = C.Cout_pad <= 64 ? 64 : (C.Cout_pad <= 128 ? 128 : env_int("ACCEL_TC_BN", 256));
+  P.BN = bn;
+  P.n_tiles = (C.Cout_pad + bn - 1) / bn;
+  const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)bn * 128;
+  int stages = (int)(kSmemBudget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  P.stages = stages;
+  plan->smem = stages * stage_bytes + 1024;
+  int cols = 32;
+  while (cols < 2 * bn) cols *= 2;
+  P.tmem_cols = cols;
+
+  const int tiles = P.tiles_x * P.tiles_y * P.n_tiles;
+  int splits = 1;
+  if (tiles < num_sms && P.kiters >= 8) {
+    splits = num_sms / tiles;
+    if (splits > P.kiters / 4) splits = P.kiters / 4;
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
+  }
+  splits = env_int("ACCEL_TC_SPLITS", splits);
+  if (splits > P.kiters) splits = P.kiters;
+  P.splits = splits;
+  plan->partial_bytes = splits > 1 ? (size_t)splits * C.Ho * C.Wo * C.Cout_pad * sizeof(float) : 0;
+  const int items = tiles * splits;
+  plan->grid = items < num_sms ? items : num_sms;
+  plan->launches = splits > 1 ? 2 : 1;
+
+  // tensor maps ------------------------------------------------------------------------------------
+  bool ok = true;
+  const cuuint64_t e = sizeof(__half);
+  if (!P.stride2) {
+    cuuint64_t dims[3] = {(cuuint64_t)C.Cin, (cuuint64_t)C.Win, (cuuint64_t)C.Hin};
+    cuuint64_t str[2] = {(cuuint64_t)C.in_ld * e, (cuuint64_t)C.in_ld * C.Win * e};
+    cuuint32_t box[3] = {BK, (cuuint32_t)P.BW, (cuuint32_t)P.BH};
+    ok = ok && encode(&P.a_hi, C.in_hi, 3, dims, str, box, err, errlen);
+    ok = ok && encode(&P.a_lo, C.in_lo, 3, dims, str, box, err, errlen);
+  } else {
+    cuuint64_t dims[5] = {(cuuint64_t)C.Cin, 2, (cuuint64_t)C.Win / 2, 2, (cuuint64_t)C.Hin / 2};
+    cuuint64_t str[4] = {(cuuint64_t)C.in_ld * e, 2 * (cuuint64_t)C.in_ld * e, (cuuint64_t)C.in_ld * C.Win * e,
+                         2 * (cuuint64_t)C.in_ld * C.Win * e};
+    cuuint32_t box[5] = {BK, 1, (cuuint32_t)P.BW, 1, (cuuint32_t)P.BH};
+    ok = ok && encode(&P.a_hi, C.in_hi, 5, dims, str, box, err, errlen);
+    ok = ok && encode(&P.a_lo, C.in_lo, 5, dims, str, box, err, errlen);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)C.Kpad, (cuuint64_t)C.Cout_pad};
+    cuuint64_t str[1] = {(cuuint64_t)C.Kpad * e};
+    cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    ok = ok && encode(&P.b_hi, C.w_hi, 2, dims, str, box, err, errlen);
+    ok = ok && encode(&P.b_lo, C.w_lo, 2, dims, str, box, err, errlen);
+  }
+  if (!ok) {
+    delete plan;
+    return nullptr;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) {
+      snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+      delete plan;
+      return nullptr;
+    }
+    configured = true;
+  }
+  return plan;
+}
+
+void tc_plan_destroy(TcPlan* plan) { delete plan; }
+size_t tc_plan_partial_bytes(const TcPlan* plan) { return plan->partial_bytes; }
+void tc_plan_set_partial(TcPlan* plan, float* partial) { plan->p.partial = partial; }
+int tc_plan_launches(const TcPlan* plan) { return plan->launches; }
+
+cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, cudaStream_t stream) {
+  TcParams P = plan->p;
+  if (ext_nchw) P.epi.out_nchw = ext_nchw;
+  conv_tc_kernel<<<plan->grid, kThreads, plan->smem, stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (P.splits > 1) return launch_splitk_epilogue(P.partial, P.splits, P.Ho * P.Wo, P.Cout_pad, P.Wo, P.epi, stream);
+  return cudaSuccess;
+}
 
 }  // namespace accel
