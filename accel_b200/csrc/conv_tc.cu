@@ -32,7 +32,8 @@ constexpr int BM = 128;          // pixels per tile (UMMA M)
 constexpr int BK = 64;           // channels per stage: 128 bytes of fp16 = one SWIZZLE_128B row
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 6;
-constexpr int kSmemBudget = 227 * 1024 - 2048;
+constexpr int kSmemMaxDynamic = 227 * 1024 - 1024;   // 227 KB per CTA minus the static barriers/slots
+constexpr int kSmemBudget = kSmemMaxDynamic - 1024;      // minus the 1024-byte alignment slack
 
 struct alignas(64) TcParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -433,7 +434,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
       delete plan;
