@@ -1,0 +1,65 @@
+"""Committed golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py from the CPU
+oracle): the oracle must keep reproducing them (CPU), and the CUDA path must match them through the
+C ABI (-m gpu) -- without running the oracle on the GPU box."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from accel_b200 import scheduler, synthetic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+VERSIONS = ["dff", "18", "34", "50", "101"]
+SCORE_TOL = 1e-3      # north-star tolerance on the fp32 score volume
+
+
+def _load(version):
+    g = np.load(os.path.join(GOLDEN, "accel_%s_128x256.npz" % version))
+    return g, int(g["height"]), int(g["width"]), int(g["interval"]), int(g["sub"])
+
+
+def _check_frame(g, i, sub, label, score, feat, score_tol, flow=None):
+    assert np.abs(score[0, :, ::sub, ::sub] - g["score_sub_%d" % i]).max() < score_tol
+    assert np.abs(feat[0, ::64] - g["feat_sub_%d" % i]).max() < score_tol
+    rel = abs(float(feat.astype(np.float64).sum()) - float(g["feat_sum_%d" % i])) / float(g["feat_abs_sum_%d" % i])
+    assert rel < 1e-5
+    decided = g["margin_%d" % i] > 2 * score_tol          # bit-exact wherever the oracle's top-2 margin is decided
+    assert np.array_equal(label[decided], g["label_%d" % i][decided])
+    assert decided.mean() > 0.97
+    if flow is not None and ("flow_%d" % i) in g:
+        assert np.abs(flow - g["flow_%d" % i]).max() < 1e-4
+
+
+@pytest.mark.parametrize("version", VERSIONS)
+def test_oracle_reproduces_golden(version):
+    from oracle import schedule as oracle_schedule
+    g, H, W, interval, sub = _load(version)
+    params = synthetic.make_params(version)
+    frames = synthetic.make_frames(3, H, W)
+    with torch.no_grad():
+        res = oracle_schedule.run(params, version, frames, interval, "chained", keep=("label", "score", "feat", "flow"))
+    for i, r in enumerate(res):
+        _check_frame(g, i, sub, np.asarray(r["label"]), r["score"].numpy(), r["feat"].numpy(), 1e-4,
+                     r["flow"][0].numpy() if "flow" in r else None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("version", VERSIONS)
+def test_cuda_path_matches_golden(version):
+    from accel_b200.engine import Engine
+    g, H, W, interval, sub = _load(version)
+    eng = Engine(version, H, W, params=synthetic.make_params(version))
+    dev = eng.torch_device
+    frames = [f.to(dev) for f in synthetic.make_frames(3, H, W)]
+    state = scheduler.StreamState(eng)
+    score = torch.empty(1, 19, H, W, device=dev)
+    label = torch.empty(H, W, dtype=torch.uint8, device=dev)
+    for i, f in enumerate(frames):
+        flow = None
+        if i % interval:
+            flow = eng.flownet(f, frames[i - 1])[0].cpu().numpy()
+        scheduler.segment_frame(eng, state, f, interval, "chained", label, score)
+        feat = state.feat[state.cur]
+        _check_frame(g, i, sub, label.cpu().numpy(), score.cpu().numpy(), feat.cpu().numpy(), SCORE_TOL, flow)
+    eng.close()
