@@ -13,7 +13,7 @@ SYMBOLS = (
     "accel_create", "accel_destroy", "accel_last_error", "accel_param_count", "accel_param_info",
     "accel_set_param", "accel_finalize", "accel_key_forward", "accel_cur_forward", "accel_flownet",
     "accel_warp", "accel_fuse_argmax", "accel_conv_layer", "accel_last_launch_count",
-    "accel_set_profiling", "accel_stage_times",
+    "accel_set_profiling", "accel_stage_times", "accel_op_times",
 )
 
 
@@ -58,5 +58,6 @@ def load():
     lib.accel_last_launch_count.argtypes = [vp]
     lib.accel_set_profiling.argtypes = [vp, ip]
     lib.accel_stage_times.argtypes = [vp, C.POINTER(cp), fp, ip]
+    lib.accel_op_times.argtypes = [vp, C.POINTER(cp), fp, C.POINTER(C.c_double), ip]
     _lib = lib
     return lib

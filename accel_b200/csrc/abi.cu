@@ -1,5 +1,6 @@
 // extern "C" surface declared in include/accel_b200.h.  No C++ exception leaves this file.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -12,6 +13,7 @@
 using namespace accel;
 
 struct AccelHandle {
+  std::vector<OpTime> ops;
   AccelConfig cfg;
   Graph* graph;
   std::string err;
@@ -180,6 +182,24 @@ extern "C" int accel_stage_times(AccelHandle* h, const char** names, float* ms, 
   }
 }
 
+extern "C" int accel_op_times(AccelHandle* h, const char** names, float* ms, double* flops, int cap) {
+  if (!h) return -1;
+  try {
+    h->ops = h->graph->op_times();
+    int n = 0;
+    for (auto& o : h->ops) {
+      if (n >= cap) break;
+      names[n] = o.name.c_str();
+      ms[n] = o.ms;
+      if (flops) flops[n] = o.flops;
+      ++n;
+    }
+    return n;
+  } catch (...) {
+    return -1;
+  }
+}
+
 // ---- operator-level entry points -------------------------------------------------------------------
 
 static int no_device(char* err, int errlen) {
@@ -290,6 +310,24 @@ extern "C" int accel_conv_layer(int kind, const float* in, int cin, int hin, int
     ext[X_AUX_OUT] = out;
     ext[X_FEAT_KEY] = (void*)offset;
     if (!g.run("layer", ext, 0, &msg)) return fail(msg, 1);
+    if (const char* reps_s = getenv("ACCEL_LAYER_REPS")) {   // tuning aid: best-of-n device time of the contraction itself
+      const int reps = atoi(reps_s);
+      std::vector<OpTime> best;
+      g.set_profiling(true);
+      for (int i = 0; i < reps; ++i) {
+        if (!g.run("layer", ext, 0, &msg)) return fail(msg, 1);
+        std::vector<OpTime> cur = g.op_times();
+        if (best.empty()) best = cur;
+        for (size_t j = 0; j < cur.size() && j < best.size(); ++j)
+          if (cur[j].ms < best[j].ms) best[j].ms = cur[j].ms;
+      }
+      g.set_profiling(false);
+      double ms = 0.0, fl = 0.0;
+      for (auto& o : best)
+        if (o.flops > 0) { ms += o.ms; fl += o.flops; }
+      fprintf(stderr, "ACCEL_LAYER kind=%d cin=%d cout=%d hw=%dx%d k=%d s=%d: %.2f us, %.2f GF, %.1f TF16/s\n", kind, cin, cout, hin,
+              win, ksize, stride, ms * 1e3, fl / 1e9, ms > 0 ? 3.0 * fl / (ms * 1e-3) / 1e12 : 0.0);
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()), 5);
     return 0;
   } catch (const std::exception& e) {

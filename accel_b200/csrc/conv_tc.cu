@@ -30,7 +30,8 @@ namespace {
 
 constexpr int BM = 128;          // pixels per tile (UMMA M)
 constexpr int BK = 64;           // channels per stage: 128 bytes of fp16 = one SWIZZLE_128B row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;      // two warps per TMEM lane quarter; they interleave the 32-column chunks of a tile
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 constexpr int kSmemMaxDynamic = 227 * 1024 - 1024;   // 227 KB per CTA minus the static barriers/slots
 constexpr int kSmemBudget = kSmemMaxDynamic - 1024;      // minus the 1024-byte alignment slack
@@ -42,6 +43,8 @@ struct alignas(64) TcParams {
   int BW, BH, BN, stages;
   int tiles_x, tiles_y, n_tiles, splits, kiters, chunks, ntaps;
   int stride2, Cin_pad, Ho, Wo, Cout_pad, tmem_cols;
+  int krot;
+  int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
   int8_t dy[kMaxTaps];
   int8_t dx[kMaxTaps];
 };
@@ -140,6 +143,105 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- 256-bit global accesses (one full 32-byte sector per thread) ----------------------------------
+struct alignas(32) U8 {
+  uint32_t v[8];
+};
+
+__device__ __forceinline__ U8 ld256(const void* p) {
+  U8 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void st256(void* p, const U8& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
+               "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
+}
+
+// residual of one 32-channel chunk of one pixel: 64 bytes of hi + 64 bytes of lo
+struct ResChunk {
+  U8 h[2];
+  U8 l[2];
+};
+
+__device__ __forceinline__ void load_res(const Epilogue& e, int pix, int c0, ResChunk& rc) {
+  const __half* ph = e.res_hi + (size_t)pix * e.res_ld + c0;
+  const __half* pl = e.res_lo + (size_t)pix * e.res_ld + c0;
+  rc.h[0] = ld256(ph);
+  rc.h[1] = ld256(ph + 16);
+  rc.l[0] = ld256(pl);
+  rc.l[1] = ld256(pl + 16);
+}
+
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+
+// split 32 fp32 values into hi/lo fp16 planes and store them as 2 + 2 sectors
+__device__ __forceinline__ void store_split32(__half* hi, __half* lo, const float v[32]) {
+  U8 a[2], b[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __half h0, l0, h1, l1;
+    split_f32(v[2 * i], h0, l0);
+    split_f32(v[2 * i + 1], h1, l1);
+    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+    a[i >> 3].v[i & 7] = *reinterpret_cast<uint32_t*>(&hh);
+    b[i >> 3].v[i & 7] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  st256(hi, a[0]);
+  st256(hi + 16, a[1]);
+  st256(lo, b[0]);
+  st256(lo + 16, b[1]);
+}
+
+// Epilogue of 32 consecutive channels [c0, c0+32) (all < Cout) of full-map pixel `pix`.
+__device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int c0, float v[32], const ResChunk& rc) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 s = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 b = e.shift ? __ldg(reinterpret_cast<const float4*>(e.shift + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, b.x);
+    v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, b.y);
+    v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, b.z);
+    v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, b.w);
+  }
+  if (e.res_hi) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 h = unpack_h2(rc.h[i >> 3].v[i & 7]);
+      const float2 l = unpack_h2(rc.l[i >> 3].v[i & 7]);
+      v[2 * i] += h.x + l.x;
+      v[2 * i + 1] += h.y + l.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
+  if (e.out_hi) store_split32(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
+  if (e.out_nchw) {
+    const size_t plane = (size_t)e.OHf * e.OWf;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) e.out_nchw[(size_t)(c0 + i) * plane + pix] = v[i];
+  }
+  if (e.out2_hi) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(e.scale2 + c0) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.shift2 + c0) + q);
+      v[4 * q + 0] = apply_act(fmaf(v[4 * q + 0], s.x, b.x), e.act2);
+      v[4 * q + 1] = apply_act(fmaf(v[4 * q + 1], s.y, b.y), e.act2);
+      v[4 * q + 2] = apply_act(fmaf(v[4 * q + 2], s.z, b.z), e.act2);
+      v[4 * q + 3] = apply_act(fmaf(v[4 * q + 3], s.w, b.w), e.act2);
+    }
+    store_split32(e.out2_hi + (size_t)pix * e.out2_ld + c0, e.out2_lo + (size_t)pix * e.out2_ld + c0, v);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
@@ -161,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);
+      mbar_init(tempty0 + 8 * a, kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -191,7 +293,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
         const int kb = (int)(((long long)P.kiters * split) / P.splits);
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
-        for (int it = kb; it < ke; ++it) {
+        const int rot = P.krot ? (int)(((unsigned)item * 5u) % (unsigned)(ke - kb)) : 0;
+        for (int i = kb; i < ke; ++i) {
+          int it = i + rot;                               // each CTA walks K from its own offset: neighbours do not
+          if (it >= ke) it -= ke - kb;                    // stream the same weight lines at the same moment
           const int t = it / P.chunks, kc = it - t * P.chunks;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t fb = full0 + 8 * s;
@@ -247,10 +352,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else {
     // ===================================== epilogue ==========================================
+    // Lane = pixel (TMEM lane), 32 consecutive output channels per chunk: 64 contiguous bytes per
+    // plane per thread, moved as 256-bit accesses; the residual of the next chunk is in flight
+    // while the current one is converted.
     const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
+    const int cset = (warp - 2) >> 2;                      // which interleaved chunk set (0 / 1)
     const int r = quarter * 32 + lane;                     // tile row = pixel inside the box
     const int by = r / P.BW, bx = r - by * P.BW;
     const int npix = P.Ho * P.Wo;
+    const Epilogue& E = P.epi;
     int acc = 0;
     uint32_t accph = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -258,24 +368,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
       const int x = (mt % P.tiles_x) * P.BW + bx, y = (mt / P.tiles_x) * P.BH + by;
       const bool valid = x < P.Wo && y < P.Ho;
+      const int pix = (y * E.osy + E.ooy) * E.OWf + x * E.osx + E.oox;
+      const int nbase = nt * P.BN;
+      const bool use_res = P.splits == 1 && E.res_hi != nullptr && P.vec32;
+      ResChunk rc{};
+      if (use_res && valid && nbase + cset * 32 + 32 <= E.Cout)
+        load_res(E, pix, nbase + cset * 32, rc);
       mbar_wait(tfull0 + 8 * acc, accph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN);
-      for (int cc = 0; cc < P.BN; cc += 32) {
+      for (int cc = cset * 32; cc < P.BN; cc += 64) {
+        const int n0 = nbase + cc;
+        if (n0 >= P.Cout_pad) break;
         float v[32];
         tmem_ld32(taddr + cc, v);
-        const int n0 = nt * P.BN + cc;
-        if (!valid || n0 >= P.Cout_pad) continue;
-        if (P.splits > 1) {
-          float4* dst = reinterpret_cast<float4*>(P.partial + ((size_t)split * npix + (size_t)y * P.Wo + x) * P.Cout_pad + n0);
+        ResChunk rn{};
+        const int nn = n0 + 64;
+        if (use_res && valid && cc + 64 < P.BN && nn + 32 <= E.Cout) load_res(E, pix, nn, rn);
+        if (valid) {
+          if (P.splits > 1) {
+            float4* dst = reinterpret_cast<float4*>(P.partial + ((size_t)split * npix + (size_t)y * P.Wo + x) * P.Cout_pad + n0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-          const int pix = (y * P.epi.osy + P.epi.ooy) * P.epi.OWf + x * P.epi.osx + P.epi.oox;
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else if (P.vec32 && n0 + 32 <= E.Cout) {
+            epilogue_chunk32(E, pix, n0, v, rc);
+          } else {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (n0 + g * 8 < P.epi.Cout) epilogue_store<8>(P.epi, pix, n0 + g * 8, v + g * 8);
+            for (int g = 0; g < 4; ++g)
+              if (n0 + g * 8 < E.Cout) epilogue_store<8>(E, pix, n0 + g * 8, v + g * 8);
+          }
         }
+        rc = rn;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -344,7 +467,6 @@ struct TcPlan {
 };
 
 bool tc_supported(const ConvParams& P) {
-  if (P.epi.Cout <= 8) return false;
   if (P.stride != 1 && P.stride != 2) return false;
   if (P.stride == 2 && ((P.Hin & 1) || (P.Win & 1))) return false;
   if (P.in_ld % 8 || P.Cin_pad % BK || P.Kpad % 8) return false;
@@ -376,7 +498,32 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   P.BW = bw; P.BH = BM / bw;
   P.tiles_x = (C.Wo + P.BW - 1) / P.BW;
   P.tiles_y = (C.Ho + P.BH - 1) / P.BH;
-  int bn = C.Cout_pad <= 64 ? 64 : (C.Cout_pad <= 128 ? 128 : env_int("ACCEL_TC_BN", 256));
+  // Tile width / split-K from a small cost model (cycles per CTA).  Measured on B200 (tools/bench_layer.py):
+  // the fp16x3 mainloop is bound by shared-memory bandwidth -- per 64-channel K step the tensor core reads
+  // 12 x (4 KB of A + 32*BN bytes of B) and TMA writes 32 KB + 256*BN bytes, at ~88 B/cycle effective --
+  // so wide tiles are cheaper per output channel, but only if the tile count still fills the 148 SMs.
+  const int tiles_m = P.tiles_x * P.tiles_y;
+  int best_bn = 64, best_splits = 1;
+  double best_cost = 1e30;
+  const int split_opts[10] = {1, 2, 3, 4, 5, 6, 8, 9, 12, 16};
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (bn > C.Cout_pad && bn != 64) continue;
+    const int n_tiles = (C.Cout_pad + bn - 1) / bn;
+    const int tiles = tiles_m * n_tiles;
+    const double per_k = (12.0 * (4096.0 + 32.0 * bn) + 32768.0 + 256.0 * bn) / 88.0;
+    for (int si = 0; si < 10; ++si) {
+      const int sp = split_opts[si];
+      const int kps = (P.kiters + sp - 1) / sp;
+      if (sp > 1 && kps < 4) continue;
+      const long long work = (long long)tiles * sp;
+      const int waves = (int)((work + num_sms - 1) / num_sms);
+      double cost = (double)waves * (kps * per_k + 10.0 * bn) + 6000.0;
+      if (sp > 1) cost += 8000.0 + 2.0 * sp * (double)C.Ho * C.Wo * C.Cout_pad * 4.0 / 3000.0;
+      if (cost < best_cost) { best_cost = cost; best_bn = bn; best_splits = sp; }
+    }
+  }
+  int bn = env_int("ACCEL_TC_BN", best_bn);
+  if (bn != 64 && bn != 128 && bn != 256) bn = best_bn;
   P.BN = bn;
   P.n_tiles = (C.Cout_pad + bn - 1) / bn;
   const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)bn * 128;
@@ -388,21 +535,25 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   while (cols < 2 * bn) cols *= 2;
   P.tmem_cols = cols;
 
-  const int tiles = P.tiles_x * P.tiles_y * P.n_tiles;
-  int splits = 1;
-  if (tiles < num_sms && P.kiters >= 8) {
-    splits = num_sms / tiles;
-    if (splits > P.kiters / 4) splits = P.kiters / 4;
-    if (splits > 16) splits = 16;
-    if (splits < 1) splits = 1;
-  }
-  splits = env_int("ACCEL_TC_SPLITS", splits);
+  const int tiles = tiles_m * P.n_tiles;
+  int splits = env_int("ACCEL_TC_SPLITS", bn == best_bn ? best_splits : 1);
   if (splits > P.kiters) splits = P.kiters;
+  if (splits < 1) splits = 1;
   P.splits = splits;
   plan->partial_bytes = splits > 1 ? (size_t)splits * C.Ho * C.Wo * C.Cout_pad * sizeof(float) : 0;
   const int items = tiles * splits;
   plan->grid = items < num_sms ? items : num_sms;
   plan->launches = splits > 1 ? 2 : 1;
+  {
+    auto al32 = [](const void* p) { return ((uintptr_t)p & 31) == 0; };
+    const Epilogue& E = C.epi;
+    bool v = true;
+    if (E.out_hi) v = v && al32(E.out_hi) && al32(E.out_lo) && E.out_ld % 16 == 0;
+    if (E.res_hi) v = v && al32(E.res_hi) && al32(E.res_lo) && E.res_ld % 16 == 0;
+    if (E.out2_hi) v = v && al32(E.out2_hi) && al32(E.out2_lo) && E.out2_ld % 16 == 0;
+    P.vec32 = v ? 1 : 0;
+    P.krot = env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
+  }
 
   // tensor maps ------------------------------------------------------------------------------------
   bool ok = true;

@@ -14,6 +14,8 @@ Graph::~Graph() {
   for (auto& kv : seqs_)
     for (auto& op : kv.second)
       if (op.tc) tc_plan_destroy(op.tc);
+  for (auto& c : graph_cache_) cudaGraphExecDestroy(c.exec);
+  if (capture_stream_) cudaStreamDestroy(capture_stream_);
   for (void* p : allocs_) cudaFree(p);
   for (auto e : events_) cudaEventDestroy(e);
 }
@@ -22,7 +24,7 @@ int Graph::new_tensor(int C, int H, int W, bool f32) {
   Buffer b;
   Tensor t;
   t.C = C; t.H = H; t.W = W; t.f32 = f32;
-  t.ld = f32 ? C : round_up(C, 8);
+  t.ld = f32 ? C : round_up(C, 16);   // 32-byte pixel rows: the conv epilogues move 256-bit sectors
   b.f32 = f32;
   b.elems = (size_t)H * W * t.ld;
   bufs_.push_back(b);
@@ -204,9 +206,18 @@ void Graph::warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, 
   op.name = "warping_feat";
   op.ext_in0 = ext_feat;
   op.in = flow_f32;
-  op.out = out_split;
+  op.out = out_split;        // only sizes the scratch; the split copy is the next op
   op.ext_out = ext_out;
   s.push_back(op);
+  // fp32 NCHW warped feature -> split NHWC input of the task head (reads mostly hit L2)
+  Op cv{};
+  cv.type = OP_TO_SPLIT;
+  cv.stage = "warp_to_head";
+  cv.name = "warping_feat(nchw->split)";
+  cv.ext_in0 = ext_out;
+  cv.src_warp = 1;
+  cv.out = out_split;
+  s.push_back(cv);
 }
 
 void Graph::upflow(std::vector<Op>& s, int flow_f32, const std::string& wname, const std::string& bname,
@@ -518,8 +529,8 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
   // engine
   int eng = op.engine;
   if (eng == ENG_AUTO) {
-    if (op.cout <= 8) eng = ENG_NARROW;
-    else if (!(flags_ & 1) && tc_supported(P)) eng = ENG_TC;
+    if (!(flags_ & 1) && tc_supported(P)) eng = ENG_TC;
+    else if (op.cout <= 8) eng = ENG_NARROW;
     else eng = ENG_FFMA;
   }
   if (eng == ENG_TC) {
@@ -657,13 +668,14 @@ bool Graph::finalize(std::string* err) {
         case OP_WARP: {
           const Tensor& tf = tensors_[op.in];
           WarpParams& Wp = op.warp;
+          if (!warp_scratch_ && op.out >= 0) {
+            const Tensor& to = tensors_[op.out];
+            warp_scratch_ = (float*)dev_alloc((size_t)to.C * to.H * to.W * sizeof(float));
+            if (!warp_scratch_) { *err = "out of device memory"; return false; }
+          }
           Wp.flow = bufs_[tf.buf].f;
           Wp.H = tf.H; Wp.W = tf.W;
-          if (op.out >= 0) {
-            const Tensor& to = tensors_[op.out];
-            Wp.C = to.C;
-            Wp.out_hi = bufs_[to.buf].hi + to.coff; Wp.out_lo = bufs_[to.buf].lo + to.coff; Wp.out_ld = to.ld;
-          }
+          if (op.out >= 0) Wp.C = tensors_[op.out].C;
           break;
         }
         case OP_UPFLOW: {
@@ -717,7 +729,60 @@ bool Graph::finalize(std::string* err) {
   return true;
 }
 
+// CUDA-graph front end: the launch sequence of a plan is fixed once finalized, so each distinct set of
+// caller pointers is captured once (on the handle's own capture stream: the legacy default stream cannot
+// be captured) and replayed with one cudaGraphLaunch on the caller's stream afterwards.
 bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err) {
+  if ((flags_ & 2) || profiling_) return run_eager(which, ext, stream, err);
+  if (!finalized_ && !finalize(err)) return false;
+  if (!warmed_.count(which)) {                       // first use of a plan: eager (one-time kernel attribute setup)
+    if (!run_eager(which, ext, stream, err)) return false;
+    warmed_.insert(which);
+    return true;
+  }
+  for (auto& c : graph_cache_) {
+    if (c.which == which && memcmp(c.ext, ext, sizeof(c.ext)) == 0) {
+      c.stamp = ++graph_clock_;
+      last_launches_ = c.launches;
+      cudaError_t ce = cudaGraphLaunch(c.exec, stream);
+      if (ce != cudaSuccess) { *err = std::string("cudaGraphLaunch failed: ") + cudaGetErrorString(ce); return false; }
+      return true;
+    }
+  }
+  if (!capture_stream_ && cudaStreamCreateWithFlags(&capture_stream_, cudaStreamNonBlocking) != cudaSuccess) {
+    *err = "cudaStreamCreate failed";
+    return false;
+  }
+  cudaError_t ce = cudaStreamBeginCapture(capture_stream_, cudaStreamCaptureModeThreadLocal);
+  if (ce != cudaSuccess) { *err = std::string("cudaStreamBeginCapture failed: ") + cudaGetErrorString(ce); return false; }
+  const bool ok = run_eager(which, ext, capture_stream_, err);
+  cudaGraph_t graph = nullptr;
+  ce = cudaStreamEndCapture(capture_stream_, &graph);
+  if (!ok) { if (graph) cudaGraphDestroy(graph); return false; }
+  if (ce != cudaSuccess || !graph) { *err = std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(ce); return false; }
+  CachedGraph c;
+  c.which = which;
+  memcpy(c.ext, ext, sizeof(c.ext));
+  c.launches = last_launches_;
+  c.stamp = ++graph_clock_;
+  ce = cudaGraphInstantiate(&c.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { *err = std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce); return false; }
+  if (graph_cache_.size() >= 48) {                   // evict the least recently used capture
+    size_t lru = 0;
+    for (size_t i = 1; i < graph_cache_.size(); ++i)
+      if (graph_cache_[i].stamp < graph_cache_[lru].stamp) lru = i;
+    cudaGraphExecDestroy(graph_cache_[lru].exec);
+    graph_cache_[lru] = c;
+  } else {
+    graph_cache_.push_back(c);
+  }
+  ce = cudaGraphLaunch(c.exec, stream);
+  if (ce != cudaSuccess) { *err = std::string("cudaGraphLaunch failed: ") + cudaGetErrorString(ce); return false; }
+  return true;
+}
+
+bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err) {
   auto it = seqs_.find(which);
   if (it == seqs_.end()) { *err = "no such graph: " + which; return false; }
   if (!finalized_ && !finalize(err)) return false;
@@ -726,6 +791,7 @@ bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t
   size_t ev = 0;
   if (profiling_) {
     event_stage_.clear();
+    event_op_.clear();
     while (events_.size() < ops.size() + 1) {
       cudaEvent_t e;
       cudaEventCreate(&e);
@@ -777,6 +843,7 @@ bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t
         Wp.out_nchw = op.ext_out != X_NONE ? (float*)ext[op.ext_out] : nullptr;
         if (!Wp.feat) { *err = "missing feat_key"; return false; }
         if (Wp.out_nchw == Wp.feat) { *err = "feat_out must not alias feat_key"; return false; }
+        if (!Wp.out_nchw) Wp.out_nchw = warp_scratch_;          // caller does not keep `warping_feat_output`
         ce = launch_warp(Wp, stream);
         ++launches;
         break;
@@ -800,6 +867,7 @@ bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t
       case OP_TO_SPLIT: {
         const Tensor& to = tensors_[op.out];
         const float* src = (const float*)ext[op.ext_in0];
+        if (!src && op.src_warp) src = warp_scratch_;
         if (!src) { *err = "missing input tensor"; return false; }
         ce = launch_nchw_to_split(src, to.C, to.H, to.W, bufs_[to.buf].hi + to.coff, bufs_[to.buf].lo + to.coff, to.ld,
                                   stream);
@@ -832,6 +900,7 @@ bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t
     if (profiling_) {
       cudaEventRecord(events_[ev++], stream);
       event_stage_.push_back(op.stage);
+      event_op_.push_back(&op);
     }
   }
   last_launches_ = launches;
@@ -851,6 +920,21 @@ const std::vector<std::pair<std::string, float>>& Graph::stage_times() {
     if (!found) times_.push_back({event_stage_[i], ms});
   }
   return times_;
+}
+
+std::vector<OpTime> Graph::op_times() {
+  std::vector<OpTime> out;
+  if (event_stage_.empty()) return out;
+  cudaEventSynchronize(events_[event_stage_.size()]);
+  for (size_t i = 0; i < event_op_.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, events_[i], events_[i + 1]);
+    const Op* op = event_op_[i];
+    std::string nm = op->stage + "/" + op->name;
+    if (op->type == OP_CONV && op->kind == 1) nm += "[" + std::to_string(op->phase_y) + std::to_string(op->phase_x) + "]";
+    out.push_back({nm, ms, op->flops});
+  }
+  return out;
 }
 
 }  // namespace accel

@@ -2,6 +2,7 @@
 // launches over the split-fp16 NHWC activation format.  Pure host logic until finalize().
 #pragma once
 #include <map>
+#include <set>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -71,6 +72,7 @@ struct Op {
   int engine = ENG_AUTO;
   std::string bn_in;         // stem: input BatchNorm (bn_data)
   int stem_pool = 0;
+  int src_warp = 0;          // OP_TO_SPLIT: read the warp op's fp32 output (caller's feat_out or the scratch)
   float stem_in_mul = 1.f;
   // resolved
   ConvParams conv{};
@@ -84,6 +86,12 @@ struct Op {
   TcPlan* tc = nullptr;
   int partial_buf = -1;
   double flops = 0.0;
+};
+
+struct OpTime {
+  std::string name;
+  float ms;
+  double flops;
 };
 
 class Graph {
@@ -124,9 +132,11 @@ class Graph {
   bool finalize(std::string* err);
   bool finalized() const { return finalized_; }
   bool run(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err);
+  bool run_eager(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err);
   int last_launches() const { return last_launches_; }
   void set_profiling(bool on) { profiling_ = on; }
   const std::vector<std::pair<std::string, float>>& stage_times();
+  std::vector<OpTime> op_times();   // per launch group of the last profiled run
   const Tensor& tensor(int id) const { return tensors_[id]; }
   int flags() const { return flags_; }
   int num_sms() const { return num_sms_; }
@@ -156,11 +166,24 @@ class Graph {
   // profiling
   std::vector<cudaEvent_t> events_;
   std::vector<std::string> event_stage_;
+  std::vector<const Op*> event_op_;
   std::vector<std::pair<std::string, float>> times_;
   std::vector<std::string> bilinear_checks_;
   int label_scratch_ = -1;
   uint8_t* label_scratch_ptr_ = nullptr;
   size_t label_scratch_bytes_ = 0;
+  float* warp_scratch_ = nullptr;
+  struct CachedGraph {
+    std::string which;
+    void* ext[X_COUNT];
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    unsigned long long stamp = 0;
+  };
+  std::vector<CachedGraph> graph_cache_;
+  std::set<std::string> warmed_;
+  cudaStream_t capture_stream_ = nullptr;
+  unsigned long long graph_clock_ = 0;   // fp32 NCHW warped feature when the caller passes no feat_out
 
  public:
   void need_label_scratch(size_t bytes) { if (bytes > label_scratch_bytes_) label_scratch_bytes_ = bytes; }

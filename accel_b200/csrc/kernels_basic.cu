@@ -175,93 +175,91 @@ __global__ void __launch_bounds__(256) dcn_col_kernel(const DcnColParams P) {
 // axis, reads and NCHW writes are coalesced along x), then the tile is transposed through shared
 // memory into the split NHWC copy the task head consumes.
 // ------------------------------------------------------------------------------------------------
-constexpr int WP_PIX = 32, WP_CH = 64;
+// One thread = one output pixel; its 2x2 neighbourhood and weights are computed once and reused down
+// a run of WP_CH channels.  Loads are issued in batches of 8 channels x 4 taps before any use, so a
+// warp keeps 32 independent 128-byte requests in flight (the kernel is pure HBM streaming:
+// 2 * C*H*W*4 + 2*H*W*4 algorithmic bytes); reads and NCHW writes are coalesced along x.
+constexpr int WP_THREADS = 128, WP_CH = 32, WP_UNROLL = 8;
 
-__global__ void __launch_bounds__(256) warp_kernel(const WarpParams P) {
-  __shared__ float tile[WP_CH][WP_PIX + 1];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int npix = P.H * P.W;
-  const int p = blockIdx.x * WP_PIX + lane;
-  const int cb = blockIdx.y * WP_CH;
-  const bool live = p < npix;
+__global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restrict__ feat, const float* __restrict__ flow,
+                                                          float* __restrict__ out, int C, int H, int W) {
+  const int npix = H * W;
+  const int p = blockIdx.x * WP_THREADS + threadIdx.x;
+  if (p >= npix) return;
+  const int y = p / W, x = p - y * W;
+  const float sx = (float)(W - 1) / 2.0f, sy = (float)(H - 1) / 2.0f;
+  const float gx = __fsub_rn(__fdiv_rn(__fadd_rn(flow[p], (float)x), sx), 1.0f);
+  const float gy = __fsub_rn(__fdiv_rn(__fadd_rn(flow[npix + p], (float)y), sy), 1.0f);
+  const float xr = __fmul_rn(__fadd_rn(gx, 1.0f), sx);
+  const float yr = __fmul_rn(__fadd_rn(gy, 1.0f), sy);
+  const float xf = floorf(xr), yf = floorf(yr);
+  const float wx0 = __fsub_rn(1.0f, __fsub_rn(xr, xf)), wy0 = __fsub_rn(1.0f, __fsub_rn(yr, yf));
+  const float wx1 = __fsub_rn(1.0f, wx0), wy1 = __fsub_rn(1.0f, wy0);
+  const bool x0ok = xf >= 0.f && xf <= (float)(W - 1), x1ok = xf + 1.f >= 0.f && xf + 1.f <= (float)(W - 1);
+  const bool y0ok = yf >= 0.f && yf <= (float)(H - 1), y1ok = yf + 1.f >= 0.f && yf + 1.f <= (float)(H - 1);
+  // clamp before the int conversion would overflow for wild flows
+  const bool sane = fabsf(xr) < 1e9f && fabsf(yr) < 1e9f;
   int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
-  float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
-  if (live) {
-    const int y = p / P.W, x = p - y * P.W;
-    const float sx = (float)(P.W - 1) / 2.0f, sy = (float)(P.H - 1) / 2.0f;
-    const float gx = __fsub_rn(__fdiv_rn(__fadd_rn(P.flow[p], (float)x), sx), 1.0f);
-    const float gy = __fsub_rn(__fdiv_rn(__fadd_rn(P.flow[npix + p], (float)y), sy), 1.0f);
-    const float xr = __fmul_rn(__fadd_rn(gx, 1.0f), sx);
-    const float yr = __fmul_rn(__fadd_rn(gy, 1.0f), sy);
-    const float xf = floorf(xr), yf = floorf(yr);
-    const float wx0 = __fsub_rn(1.0f, __fsub_rn(xr, xf)), wy0 = __fsub_rn(1.0f, __fsub_rn(yr, yf));
-    const float wx1 = __fsub_rn(1.0f, wx0), wy1 = __fsub_rn(1.0f, wy0);
-    const bool x0ok = xf >= 0.f && xf <= (float)(P.W - 1), x1ok = xf + 1.f >= 0.f && xf + 1.f <= (float)(P.W - 1);
-    const bool y0ok = yf >= 0.f && yf <= (float)(P.H - 1), y1ok = yf + 1.f >= 0.f && yf + 1.f <= (float)(P.H - 1);
-    const int xi0 = min(max((int)xf, 0), P.W - 1), xi1 = min(max((int)xf + 1, 0), P.W - 1);
-    const int yi0 = min(max((int)yf, 0), P.H - 1), yi1 = min(max((int)yf + 1, 0), P.H - 1);
-    // clamp before the int conversion would overflow for wild flows
-    const float big = 1e9f;
-    const bool sane = fabsf(xr) < big && fabsf(yr) < big;
-    i00 = yi0 * P.W + xi0; i01 = yi0 * P.W + xi1; i10 = yi1 * P.W + xi0; i11 = yi1 * P.W + xi1;
-    w00 = (sane && y0ok && x0ok) ? __fmul_rn(wy0, wx0) : 0.f;
-    w01 = (sane && y0ok && x1ok) ? __fmul_rn(wy0, wx1) : 0.f;
-    w10 = (sane && y1ok && x0ok) ? __fmul_rn(wy1, wx0) : 0.f;
-    w11 = (sane && y1ok && x1ok) ? __fmul_rn(wy1, wx1) : 0.f;
-    if (!sane) { i00 = i01 = i10 = i11 = 0; }
+  if (sane) {
+    const int xi0 = min(max((int)xf, 0), W - 1), xi1 = min(max((int)xf + 1, 0), W - 1);
+    const int yi0 = min(max((int)yf, 0), H - 1), yi1 = min(max((int)yf + 1, 0), H - 1);
+    i00 = yi0 * W + xi0; i01 = yi0 * W + xi1; i10 = yi1 * W + xi0; i11 = yi1 * W + xi1;
   }
+  const float w00 = (sane && y0ok && x0ok) ? __fmul_rn(wy0, wx0) : 0.f;
+  const float w01 = (sane && y0ok && x1ok) ? __fmul_rn(wy0, wx1) : 0.f;
+  const float w10 = (sane && y1ok && x0ok) ? __fmul_rn(wy1, wx0) : 0.f;
+  const float w11 = (sane && y1ok && x1ok) ? __fmul_rn(wy1, wx1) : 0.f;
+
+  const int c_begin = blockIdx.y * WP_CH;
+  const int c_end = min(c_begin + WP_CH, C);
+  for (int c0 = c_begin; c0 < c_end; c0 += WP_UNROLL) {
+    float a[WP_UNROLL], b[WP_UNROLL], c[WP_UNROLL], d[WP_UNROLL];
 #pragma unroll
-  for (int k = 0; k < WP_CH / 8; ++k) {
-    const int cl = wid * (WP_CH / 8) + k;
-    const int c = cb + cl;
-    float v = 0.f;
-    if (live && c < P.C) {
-      const float* f = P.feat + (size_t)c * npix;
-      v = __fmul_rn(__ldg(f + i00), w00);
-      v = __fadd_rn(v, __fmul_rn(__ldg(f + i01), w01));
-      v = __fadd_rn(v, __fmul_rn(__ldg(f + i10), w10));
-      v = __fadd_rn(v, __fmul_rn(__ldg(f + i11), w11));
-      if (P.out_nchw) P.out_nchw[(size_t)c * npix + p] = v;
+    for (int k = 0; k < WP_UNROLL; ++k) {
+      const float* f = feat + (size_t)min(c0 + k, C - 1) * npix;
+      a[k] = __ldg(f + i00);
+      b[k] = __ldg(f + i01);
+      c[k] = __ldg(f + i10);
+      d[k] = __ldg(f + i11);
     }
-    tile[cl][lane] = v;
-  }
-  if (!P.out_hi) return;
-  __syncthreads();
-  const int pl = threadIdx.x >> 3, g = threadIdx.x & 7;
-  const int pp = blockIdx.x * WP_PIX + pl;
-  if (pp < npix && cb + g * 8 < P.C) {
-    float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = tile[g * 8 + i][pl];
-    const size_t o = (size_t)pp * P.out_ld + cb + g * 8;
-    store8(P.out_hi + o, P.out_lo + o, v);
+    for (int k = 0; k < WP_UNROLL; ++k) {
+      float v = __fmul_rn(a[k], w00);
+      v = __fadd_rn(v, __fmul_rn(b[k], w01));
+      v = __fadd_rn(v, __fmul_rn(c[k], w10));
+      v = __fadd_rn(v, __fmul_rn(d[k], w11));
+      if (c0 + k < c_end) out[(size_t)(c0 + k) * npix + p] = v;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// fp32 NCHW <-> split NHWC (32 pixels x 32 channels per CTA through shared memory)
+// fp32 NCHW <-> split NHWC.  nchw -> split: CTA = 32 pixels x 64 channels; lanes read along x
+// (coalesced), the tile is transposed through shared memory and leaves as 128 contiguous bytes per
+// pixel and plane.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ src, int C, int npix,
                                                             __half* hi, __half* lo, int ld) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  float v[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c0 + wid * 4 + k, p = p0 + lane;
-    tile[wid * 4 + k][lane] = (c < C && p < npix) ? src[(size_t)c * npix + p] : 0.f;
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + wid * 8 + k, p = p0 + lane;
+    v[k] = (c < C && p < npix) ? __ldg(src + (size_t)c * npix + p) : 0.f;
   }
-  __syncthreads();
-  if (threadIdx.x < 128) {
-    const int pl = threadIdx.x >> 2, g = threadIdx.x & 3;
-    const int p = p0 + pl;
-    if (p < npix && c0 + g * 8 < ld) {
-      float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = tile[g * 8 + i][pl];
-      const size_t o = (size_t)p * ld + c0 + g * 8;
-      store8(hi + o, lo + o, v);
-    }
+  for (int k = 0; k < 8; ++k) tile[wid * 8 + k][lane] = v[k];
+  __syncthreads();
+  const int pl = threadIdx.x >> 3, g = threadIdx.x & 7;
+  const int p = p0 + pl;
+  if (p < npix && c0 + g * 8 < ld) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = tile[g * 8 + i][pl];
+    const size_t off = (size_t)p * ld + c0 + g * 8;
+    store8(hi + off, lo + off, o);
   }
 }
 
@@ -424,14 +422,19 @@ cudaError_t launch_dcn_col(const DcnColParams& P, cudaStream_t stream) {
 }
 
 cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
-  dim3 grid((P.H * P.W + WP_PIX - 1) / WP_PIX, (P.C + WP_CH - 1) / WP_CH);
-  warp_kernel<<<grid, 256, 0, stream>>>(P);
-  return cudaGetLastError();
+  // The warped feature always lands as fp32 NCHW (`warping_feat_output`, or the handle's scratch when the
+  // caller does not want it); the split NHWC copy the task head consumes is a second, L2-fed pass.
+  if (!P.out_nchw) return cudaErrorInvalidValue;
+  dim3 grid((P.H * P.W + WP_THREADS - 1) / WP_THREADS, (P.C + WP_CH - 1) / WP_CH);
+  warp_kernel<<<grid, WP_THREADS, 0, stream>>>(P.feat, P.flow, P.out_nchw, P.C, P.H, P.W);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !P.out_hi) return e;
+  return launch_nchw_to_split(P.out_nchw, P.C, P.H, P.W, P.out_hi, P.out_lo, P.out_ld, stream);
 }
 
 cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,
                                  cudaStream_t stream) {
-  dim3 grid((H * W + 31) / 32, (ld + 31) / 32);
+  dim3 grid((H * W + 31) / 32, (ld + 63) / 64);
   nchw_to_split_kernel<<<grid, 256, 0, stream>>>(src, C, H * W, hi, lo, ld);
   return cudaGetLastError();
 }

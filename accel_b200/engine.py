@@ -131,6 +131,13 @@ class Engine:
         n = self.lib.accel_stage_times(self._h, names, ms, 32)
         return {names[i].decode(): float(ms[i]) for i in range(max(n, 0))}
 
+    def op_times(self):
+        """[(layer name, ms, reference flops)] of the last profiled forward, in launch order."""
+        cap = 1024
+        names, ms, fl = (C.c_char_p * cap)(), (C.c_float * cap)(), (C.c_double * cap)()
+        n = self.lib.accel_op_times(self._h, names, ms, fl, cap)
+        return [(names[i].decode(), float(ms[i]), float(fl[i])) for i in range(max(n, 0))]
+
     def _err(self):
         return self.lib.accel_last_error(self._h).decode()
 

@@ -120,6 +120,9 @@ int accel_last_launch_count(const AccelHandle* h);
  * accel_set_profiling(h, 1): fills up to `cap` (name, milliseconds) pairs, returns the count. */
 int accel_set_profiling(AccelHandle* h, int enabled);
 int accel_stage_times(AccelHandle* h, const char** names, float* ms, int cap);
+/* Same, per layer (one entry per op of the plan, in launch order): name = "<stage>/<reference layer name>",
+ * device milliseconds, and the layer's reference-graph flops (2*MAC; 0 for non-contractions). */
+int accel_op_times(AccelHandle* h, const char** names, float* ms, double* flops, int cap);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ def _check_frame(g, i, sub, label, score, feat, score_tol, flow=None):
     assert np.abs(score[0, :, ::sub, ::sub] - g["score_sub_%d" % i]).max() < score_tol
     assert np.abs(feat[0, ::64] - g["feat_sub_%d" % i]).max() < score_tol
     rel = abs(float(feat.astype(np.float64).sum()) - float(g["feat_sum_%d" % i])) / float(g["feat_abs_sum_%d" % i])
-    assert rel < 1e-5
+    assert rel < 5e-5
     decided = g["margin_%d" % i] > 2 * score_tol          # bit-exact wherever the oracle's top-2 margin is decided
     assert np.array_equal(label[decided], g["label_%d" % i][decided])
     assert decided.mean() > 0.97

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Times single layers through accel_conv_layer under different planner knobs (tuning aid, GPU only).
+
+    python tools/bench_layer.py [--set NAME] 2> layer_times.txt
+
+Each line printed by the library (stderr, prefix ACCEL_LAYER) is the best-of-n device time of the
+contraction kernels of that layer; the knobs in effect are echoed before it."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from accel_b200 import engine as E  # noqa: E402
+
+# name: (cin, cout, h, w, k, stride, pad, dil, residual)
+LAYERS = {
+    "res2_2c": (64, 256, 256, 512, 1, 1, 0, 1, True),
+    "res2_2b": (64, 64, 256, 512, 3, 1, 1, 1, False),
+    "res3_2c": (128, 512, 128, 256, 1, 1, 0, 1, True),
+    "res3_2b": (128, 128, 128, 256, 3, 1, 1, 1, False),
+    "res4_2a": (1024, 256, 64, 128, 1, 1, 0, 1, False),
+    "res4_2b": (256, 256, 64, 128, 3, 1, 1, 1, False),
+    "res4_2c": (256, 1024, 64, 128, 1, 1, 0, 1, True),
+    "res5_2a": (2048, 512, 64, 128, 1, 1, 0, 1, False),
+    "res5_2c": (512, 2048, 64, 128, 1, 1, 0, 1, True),
+    "fc6": (2048, 1024, 64, 128, 1, 1, 0, 1, False),
+    "flow_conv3": (128, 256, 128, 256, 5, 2, 2, 1, False),
+    "flow_conv4_1": (512, 512, 32, 64, 3, 1, 1, 1, False),
+    "flow_conv6_1": (1024, 1024, 8, 16, 3, 1, 1, 1, False),
+}
+SWEEP = [
+    {},
+    {"ACCEL_TC_KROT": "0"},
+    {"ACCEL_TC_BN": "128"},
+    {"ACCEL_TC_BN": "128", "ACCEL_TC_KROT": "0"},
+    {"ACCEL_TC_BN": "64"},
+    {"ACCEL_TC_BN": "256", "ACCEL_TC_SPLITS": "2"},
+    {"ACCEL_TC_BN": "128", "ACCEL_TC_SPLITS": "2"},
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--set", default="")
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    os.environ["ACCEL_LAYER_REPS"] = str(a.reps)
+    names = [n for n in LAYERS if not a.set or n in a.set.split(",")]
+    dev = "cuda:0"
+    for name in names:
+        cin, cout, h, w, k, s, p, d, res = LAYERS[name]
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(1, cin, h, w, generator=g).to(dev)
+        wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+        ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
+        wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
+        r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
+        for knobs in SWEEP:
+            for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES"):
+                os.environ.pop(kk, None)
+            os.environ.update(knobs)
+            sys.stderr.write("%-14s %-44s " % (name, knobs))
+            sys.stderr.flush()
+            try:
+                E.conv_layer(x, wt, "conv", s, p, d, act=1, residual=r, engine=2)
+            except RuntimeError as e:
+                sys.stderr.write("FAILED %s\n" % e)
+
+
+if __name__ == "__main__":
+    main()
