@@ -169,18 +169,15 @@ def run_reference(a):
 def run_native(a):
     import torch
     import torch.distributed as dist
-    from accel_b200 import scheduler, synthetic
+    from accel_b200 import multigpu, scheduler, synthetic
     from accel_b200.engine import Engine
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = multigpu.world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the native arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    multigpu.init("nccl", dev)
 
     H, W, I = a.height, a.width, a.interval
     params = synthetic.make_params(a.version)
@@ -291,14 +288,10 @@ def run_native(a):
         e2e_ms = None
 
     # ---- reduce: max time over ranks, total frames --------------------------------------------------
-    t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0], device=dev, dtype=torch.float64)
-    if world > 1:
-        gathered = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(gathered, t)                                           # the single metric collective
-        t = torch.stack(gathered).max(dim=0).values
-    ms_max, e2e_max = float(t[0]), float(t[1])
-    frames_total = world * a.steps * I
-    fps = frames_total / (ms_max / 1000.0)
+    rows = multigpu.gather_rows([a.steps * I, ms, e2e_ms if e2e_ms is not None else 0.0], dev)   # the single metric collective
+    fps, ms_max = multigpu.aggregate_throughput(rows[:, 0].tolist(), rows[:, 1].tolist())
+    e2e_max = float(rows[:, 2].max())
+    frames_total = float(rows[:, 0].sum())
 
     if rank == 0:
         peaks = {}
