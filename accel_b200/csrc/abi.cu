@@ -258,6 +258,36 @@ extern "C" int accel_conv_layer(int kind, const float* in, int cin, int hin, int
     if (no_device(err, errlen)) return 6;
     Graph g(device, engine == 1 ? 1 : 0);
     std::vector<Op>& s = g.seq("layer");
+    if (kind == 3 || kind == 4) {
+      // 7x7/s2/p3 stem over fp32 NCHW frames: kind 3 = one frame (cin 3); kind 4 = FlowNet's stem: the frame
+      // pair (`in`, `offset`), each 2x2 average-pooled and divided by 255 first (cin 6)
+      if (ksize != 7 || stride != 2 || pad != 3 || cout != 64 || cin != (kind == 3 ? 3 : 6) || (kind == 4 && !offset))
+        return fail("stem test hook: 7x7, stride 2, pad 3, 64 output channels, cin 3 (kind 3) or 6 (kind 4)", 1);
+      EpiSpec se;
+      se.bn = "post";
+      se.eps = 0.f;
+      se.act = act;
+      const int y = g.stem(s, "layer", X_DATA, kind == 4 ? X_DATA_KEY : X_NONE, hin, win, kind == 4,
+                           kind == 4 ? 1.0f / 255.0f : 1.f, "", "w", cin, se);
+      g.to_nchw(s, y, X_AUX_OUT);
+      std::string msg;
+      std::vector<float> ones(cout, 1.f), zeros(cout, 0.f);
+      const int64_t c1[1] = {cout};
+      const int64_t wshape[4] = {cout, cin, 7, 7};
+      bool ok = g.set_param("w_weight", weight, wshape, 4, &msg) &&
+                g.set_param("post_gamma", scale ? scale : ones.data(), c1, 1, &msg) &&
+                g.set_param("post_beta", shift ? shift : zeros.data(), c1, 1, &msg) &&
+                g.set_param("post_moving_mean", zeros.data(), c1, 1, &msg) &&
+                g.set_param("post_moving_var", ones.data(), c1, 1, &msg);
+      if (!ok) return fail(msg, 1);
+      void* ext[X_COUNT] = {nullptr};
+      ext[X_DATA] = (void*)in;
+      ext[X_DATA_KEY] = (void*)offset;
+      ext[X_AUX_OUT] = out;
+      if (!g.run("layer", ext, 0, &msg)) return fail(msg, 1);
+      if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()), 5);
+      return 0;
+    }
     const int x = g.new_tensor(cin, hin, win);
     g.to_split(s, X_DATA, x);
     EpiSpec e;

@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace accel {
 
@@ -27,6 +28,8 @@ cudaError_t launch_splitk_epilogue(const float* partial, int splits, int npix, i
                                    cudaStream_t stream);
 
 namespace {
+
+using namespace tc;
 
 constexpr int BM = 128;          // pixels per tile (UMMA M)
 constexpr int BK = 64;           // channels per stage: 128 bytes of fp16 = one SWIZZLE_128B row
@@ -49,198 +52,6 @@ struct alignas(64) TcParams {
   int8_t dx[kMaxTaps];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-// Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  printf("accel_b200: conv_tc mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-         bar, parity);
-  __trap();
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-      "[%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// ---- 256-bit global accesses (one full 32-byte sector per thread) ----------------------------------
-struct alignas(32) U8 {
-  uint32_t v[8];
-};
-
-__device__ __forceinline__ U8 ld256(const void* p) {
-  U8 r;
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-               : "l"(p));
-  return r;
-}
-
-__device__ __forceinline__ void st256(void* p, const U8& r) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
-               "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
-               : "memory");
-}
-
-// residual of one 32-channel chunk of one pixel: 64 bytes of hi + 64 bytes of lo
-struct ResChunk {
-  U8 h[2];
-  U8 l[2];
-};
-
-__device__ __forceinline__ void load_res(const Epilogue& e, int pix, int c0, ResChunk& rc) {
-  const __half* ph = e.res_hi + (size_t)pix * e.res_ld + c0;
-  const __half* pl = e.res_lo + (size_t)pix * e.res_ld + c0;
-  rc.h[0] = ld256(ph);
-  rc.h[1] = ld256(ph + 16);
-  rc.l[0] = ld256(pl);
-  rc.l[1] = ld256(pl + 16);
-}
-
-__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
-  __half2 h = *reinterpret_cast<__half2*>(&u);
-  return __half22float2(h);
-}
-
-// split 32 fp32 values into hi/lo fp16 planes and store them as 2 + 2 sectors
-__device__ __forceinline__ void store_split32(__half* hi, __half* lo, const float v[32]) {
-  U8 a[2], b[2];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    __half h0, l0, h1, l1;
-    split_f32(v[2 * i], h0, l0);
-    split_f32(v[2 * i + 1], h1, l1);
-    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-    a[i >> 3].v[i & 7] = *reinterpret_cast<uint32_t*>(&hh);
-    b[i >> 3].v[i & 7] = *reinterpret_cast<uint32_t*>(&ll);
-  }
-  st256(hi, a[0]);
-  st256(hi + 16, a[1]);
-  st256(lo, b[0]);
-  st256(lo + 16, b[1]);
-}
-
-// Epilogue of 32 consecutive channels [c0, c0+32) (all < Cout) of full-map pixel `pix`.
-__device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int c0, float v[32], const ResChunk& rc) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 s = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-    const float4 b = e.shift ? __ldg(reinterpret_cast<const float4*>(e.shift + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, b.x);
-    v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, b.y);
-    v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, b.z);
-    v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, b.w);
-  }
-  if (e.res_hi) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float2 h = unpack_h2(rc.h[i >> 3].v[i & 7]);
-      const float2 l = unpack_h2(rc.l[i >> 3].v[i & 7]);
-      v[2 * i] += h.x + l.x;
-      v[2 * i + 1] += h.y + l.y;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
-  if (e.out_hi) store_split32(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
-  if (e.out_nchw) {
-    const size_t plane = (size_t)e.OHf * e.OWf;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) e.out_nchw[(size_t)(c0 + i) * plane + pix] = v[i];
-  }
-  if (e.out2_hi) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 s = __ldg(reinterpret_cast<const float4*>(e.scale2 + c0) + q);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(e.shift2 + c0) + q);
-      v[4 * q + 0] = apply_act(fmaf(v[4 * q + 0], s.x, b.x), e.act2);
-      v[4 * q + 1] = apply_act(fmaf(v[4 * q + 1], s.y, b.y), e.act2);
-      v[4 * q + 2] = apply_act(fmaf(v[4 * q + 2], s.z, b.z), e.act2);
-      v[4 * q + 3] = apply_act(fmaf(v[4 * q + 3], s.w, b.w), e.act2);
-    }
-    store_split32(e.out2_hi + (size_t)pix * e.out2_ld + c0, e.out2_lo + (size_t)pix * e.out2_ld + c0, v);
-  }
-}
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -413,47 +224,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-            const cuuint32_t* box, char* err, int errlen) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) {
-    snprintf(err, errlen, "cuTensorMapEncodeTiled is unavailable");
-    return false;
-  }
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu] box [%u %u %u]", (int)r, rank,
-             (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull, box[0],
-             box[1], rank > 2 ? box[2] : 0u);
-    return false;
-  }
-  return true;
-}
-
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
 }
 
 }  // namespace

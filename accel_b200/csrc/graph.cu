@@ -14,6 +14,9 @@ Graph::~Graph() {
   for (auto& kv : seqs_)
     for (auto& op : kv.second)
       if (op.tc) tc_plan_destroy(op.tc);
+  for (auto& kv : seqs_)
+    for (auto& op : kv.second)
+      if (op.stem_tc) stem_tc_plan_destroy(op.stem_tc);
   for (auto& c : graph_cache_) cudaGraphExecDestroy(c.exec);
   if (capture_stream_) cudaStreamDestroy(capture_stream_);
   for (void* p : allocs_) cudaFree(p);
@@ -627,12 +630,29 @@ bool Graph::finalize(std::string* err) {
           S.weight = upload(*w);
           const Tensor& to = tensors_[op.out];
           S.Ho = to.H; S.Wo = to.W;
+          const bool use_tc = !(flags_ & 1) && stem_tc_supported(S);
+          std::vector<float> prescale;
+          __half *dhi = nullptr, *dlo = nullptr;
+          if (use_tc) {
+            std::vector<__half> hi, lo;
+            stem_tc_pack_weights(w->data(), cin, hi, lo, prescale);
+            dhi = (__half*)dev_alloc(hi.size() * sizeof(__half));
+            dlo = (__half*)dev_alloc(lo.size() * sizeof(__half));
+            if (!dhi || !dlo) { *err = "out of device memory packing " + op.name; return false; }
+            cudaMemcpy(dhi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
+            cudaMemcpy(dlo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
+          }
           float *sc = nullptr, *sh = nullptr;
-          if (!make_scale_shift(op.epi, 64, {}, &sc, &sh, err)) return false;
+          if (!make_scale_shift(op.epi, 64, prescale, &sc, &sh, err)) return false;
           Epilogue& E = S.epi;
           E.scale = sc; E.shift = sh; E.act = op.epi.act; E.Cout = 64;
           E.out_hi = bufs_[to.buf].hi + to.coff; E.out_lo = bufs_[to.buf].lo + to.coff; E.out_ld = to.ld;
           E.osy = E.osx = 1; E.OHf = to.H; E.OWf = to.W;
+          if (use_tc) {
+            char msg[256] = {0};
+            op.stem_tc = stem_tc_plan_create(S, dhi, dlo, num_sms_, msg, sizeof(msg));
+            if (!op.stem_tc) { *err = std::string("tcgen05 stem plan failed for ") + op.name + ": " + msg; return false; }
+          }
           break;
         }
         case OP_POOL: {
@@ -807,7 +827,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
         S.src0 = (const float*)ext[op.ext_in0];
         S.src1 = op.ext_in1 != X_NONE ? (const float*)ext[op.ext_in1] : nullptr;
         if (!S.src0 || (op.ext_in1 != X_NONE && !S.src1)) { *err = "missing input frame"; return false; }
-        ce = launch_stem(S, stream);
+        ce = op.stem_tc ? launch_stem_tc(op.stem_tc, S.src0, S.src1, stream) : launch_stem(S, stream);
         ++launches;
         break;
       }

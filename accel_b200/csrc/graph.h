@@ -84,6 +84,7 @@ struct Op {
   FuseParams fuse{};
   TailParams tail{};
   TcPlan* tc = nullptr;
+  StemTcPlan* stem_tc = nullptr;
   int partial_buf = -1;
   double flops = 0.0;
 };

@@ -1,6 +1,8 @@
 // Host-callable launchers for the hot-path kernels.  Internal to the library (the public surface is
 // include/accel_b200.h).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace accel {
@@ -35,7 +37,18 @@ struct StemParams {
   Epilogue epi;            // out = split NHWC (64, Ho, Wo)
   int Ho, Wo;
 };
-cudaError_t launch_stem(const StemParams& P, cudaStream_t stream);
+cudaError_t launch_stem(const StemParams& P, cudaStream_t stream);   // CUDA-core cross-check path
+
+// tcgen05 stem (stem_tc.cu): software-built A operand, weights packed by stem_tc_pack_weights
+struct StemTcPlan;
+int stem_tc_kpad(int cin);
+void stem_tc_pack_weights(const float* w, int cin, std::vector<__half>& hi, std::vector<__half>& lo,
+                          std::vector<float>& prescale);
+bool stem_tc_supported(const StemParams& S);
+StemTcPlan* stem_tc_plan_create(const StemParams& S, const __half* w_hi, const __half* w_lo, int num_sms, char* err,
+                                int errlen);
+void stem_tc_plan_destroy(StemTcPlan* plan);
+cudaError_t launch_stem_tc(const StemTcPlan* plan, const float* src0, const float* src1, cudaStream_t stream);
 
 // ---- pooling ---------------------------------------------------------------------------------------
 struct PoolParams {

@@ -190,16 +190,21 @@ def conv_layer(x, weight, kind="conv", stride=1, pad=0, dilate=1, scale=None, sh
                offset=None, deform_groups=1, engine=0):
     """One layer through the library's kernels (parity-test hook, accel_conv_layer)."""
     lib = _lib.load()
-    kinds = {"conv": 0, "deconv": 1, "deform": 2}
+    kinds = {"conv": 0, "deconv": 1, "deform": 2, "stem": 3, "flowstem": 4}
     n, cin, hin, win = x.shape
     w = np.ascontiguousarray(weight.detach().cpu().numpy(), dtype=np.float32)
     if kind == "deconv":
         cout, k = w.shape[1], 4
         ho, wo = 2 * hin, 2 * win
+    elif kind == "flowstem":
+        cin, cout, k = 6, w.shape[0], 7
+        ho, wo = hin // 4, win // 4
     else:
         cout, k = w.shape[0], w.shape[2]
         ho = (hin + 2 * pad - (dilate * (k - 1) + 1)) // stride + 1
         wo = (win + 2 * pad - (dilate * (k - 1) + 1)) // stride + 1
+    if kind == "flowstem":
+        ho, wo = hin // 4, win // 4
     out = torch.empty(1, cout, ho, wo, device=x.device)
     sc = np.ascontiguousarray(scale.detach().cpu().numpy(), dtype=np.float32) if scale is not None else None
     sh = np.ascontiguousarray(shift.detach().cpu().numpy(), dtype=np.float32) if shift is not None else None

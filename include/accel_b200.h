@@ -104,7 +104,9 @@ int accel_fuse_argmax(const float* score_a, const float* score_b, const float* c
                       float* score_full, void* stream);
 
 /* One convolution-like layer through the same kernels the graphs use; parity-test hook.
- *   kind: 0 Convolution, 1 Deconvolution(k4,s2,p1 after crop), 2 DeformableConvolution(3x3,s1)
+ *   kind: 0 Convolution, 1 Deconvolution(k4,s2,p1 after crop), 2 DeformableConvolution(3x3,s1),
+ *         3 the 7x7/s2/p3 stem over one fp32 NCHW frame (cin 3), 4 FlowNet's stem over the frame pair
+ *         (`in`, `offset`), 2x2 average-pooled and divided by 255 first (cin 6; hin/win = frame size)
  *   in (1,cin,hin,win) device; weight/scale/shift HOST (weight in MXNet layout; scale/shift per
  *   output channel, NULL = 1/0); offset (device, deformable only); residual (device, NCHW, or NULL)
  *   act: 0 none, 1 relu, 2 leaky(0.1); engine: 0 auto, 1 CUDA-core, 2 tcgen05

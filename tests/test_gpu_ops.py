@@ -134,3 +134,29 @@ def test_deformable_layer_matches_oracle(dg, engine):
     ref = ops.deformable_convolution(x, off, wt, 1, 2, 2, dg)
     out = E.conv_layer(x.to(DEV), wt, "deform", 1, 2, 2, offset=off.to(DEV), deform_groups=dg, engine=engine).cpu()
     assert (out - ref).abs().max().item() < _tol(ref)
+
+
+# ----------------------------------------------------------------------------- 7x7/s2 stems (a1, a4, a8, a9)
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("h,w", [(64, 128), (128, 256), (72, 200)])
+def test_stem_matches_torch(h, w, engine):
+    x = _rand(1, 3, h, w, seed=40, scale=60.0)                 # mean-subtracted pixel range
+    wt = _rand(64, 3, 7, 7, seed=41, scale=0.02)
+    scale, shift = torch.rand(64, generator=torch.Generator().manual_seed(42)) + 0.5, _rand(64, seed=43, scale=0.1)
+    ref = F.relu(F.conv2d(x, wt, None, 2, 3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    out = E.conv_layer(x.to(DEV), wt, "stem", 2, 3, 1, scale, shift, act=1, engine=engine).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() < _tol(ref)
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("h,w", [(128, 256), (256, 384)])
+def test_flownet_stem_matches_torch(h, w, engine):
+    a, b = _rand(1, 3, h, w, seed=44, scale=60.0), _rand(1, 3, h, w, seed=45, scale=60.0)
+    wt = _rand(64, 6, 7, 7, seed=46, scale=0.3)
+    shift = _rand(64, seed=47, scale=0.1)
+    x = F.avg_pool2d(torch.cat([a, b], 1) / 255.0, 2, 2)
+    ref = ops.leaky_relu(F.conv2d(x, wt, shift, 2, 3))
+    out = E.conv_layer(a.to(DEV), wt, "flowstem", 2, 3, 1, shift=shift, act=2, offset=b.to(DEV), engine=engine).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() < _tol(ref)
