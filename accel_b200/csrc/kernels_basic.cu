@@ -175,15 +175,19 @@ __global__ void __launch_bounds__(256) dcn_col_kernel(const DcnColParams P) {
 // axis, reads and NCHW writes are coalesced along x), then the tile is transposed through shared
 // memory into the split NHWC copy the task head consumes.
 // ------------------------------------------------------------------------------------------------
-// One thread = one output pixel; its 2x2 neighbourhood and weights are computed once and reused down
-// a run of WP_CH channels.  Loads are issued in batches of 8 channels x 4 taps before any use, so a
-// warp keeps 32 independent 128-byte requests in flight (the kernel is pure HBM streaming:
-// 2 * C*H*W*4 + 2*H*W*4 algorithmic bytes); reads and NCHW writes are coalesced along x.
-constexpr int WP_THREADS = 128, WP_CH = 32, WP_UNROLL = 8;
+// One thread = one output pixel; its four tap pointers and bilinear weights are computed once and reused
+// down the channel axis.  Channels are walked in batches of 8: the 32 gathers of a batch are issued before
+// any use (32 independent 128-byte requests per warp in flight) and, when the plane size is a compile-time
+// constant, every one of them is `[tap pointer + immediate]` -- no per-channel address arithmetic, ~12
+// instructions per output element -- so the kernel is pure HBM streaming: 2*C*H*W*4 + 2*H*W*4 algorithmic
+// bytes.  Reads and NCHW writes are coalesced along x.  The grid is sized to one resident wave: blockIdx.x =
+// block of 128 pixels, blockIdx.y strides over the 8-channel batches.
+constexpr int WP_THREADS = 128, WP_UNROLL = 8;
 
+template <int NPIX>
 __global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restrict__ feat, const float* __restrict__ flow,
                                                           float* __restrict__ out, int C, int H, int W) {
-  const int npix = H * W;
+  const int npix = NPIX > 0 ? NPIX : H * W;
   const int p = blockIdx.x * WP_THREADS + threadIdx.x;
   if (p >= npix) return;
   const int y = p / W, x = p - y * W;
@@ -210,25 +214,40 @@ __global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restric
   const float w10 = (sane && y1ok && x0ok) ? __fmul_rn(wy1, wx0) : 0.f;
   const float w11 = (sane && y1ok && x1ok) ? __fmul_rn(wy1, wx1) : 0.f;
 
-  const int c_begin = blockIdx.y * WP_CH;
-  const int c_end = min(c_begin + WP_CH, C);
-  for (int c0 = c_begin; c0 < c_end; c0 += WP_UNROLL) {
+  const int nbatch = (C + WP_UNROLL - 1) / WP_UNROLL;
+  for (int bt = blockIdx.y; bt < nbatch; bt += gridDim.y) {
+    const int c0 = bt * WP_UNROLL;
+    const size_t base = (size_t)c0 * npix;
+    const float* p00 = feat + base + i00;
+    const float* p01 = feat + base + i01;
+    const float* p10 = feat + base + i10;
+    const float* p11 = feat + base + i11;
+    float* po = out + base + p;
     float a[WP_UNROLL], b[WP_UNROLL], c[WP_UNROLL], d[WP_UNROLL];
+    if (c0 + WP_UNROLL <= C) {
 #pragma unroll
-    for (int k = 0; k < WP_UNROLL; ++k) {
-      const float* f = feat + (size_t)min(c0 + k, C - 1) * npix;
-      a[k] = __ldg(f + i00);
-      b[k] = __ldg(f + i01);
-      c[k] = __ldg(f + i10);
-      d[k] = __ldg(f + i11);
-    }
+      for (int k = 0; k < WP_UNROLL; ++k) {
+        a[k] = __ldg(p00 + (size_t)k * npix);
+        b[k] = __ldg(p01 + (size_t)k * npix);
+        c[k] = __ldg(p10 + (size_t)k * npix);
+        d[k] = __ldg(p11 + (size_t)k * npix);
+      }
 #pragma unroll
-    for (int k = 0; k < WP_UNROLL; ++k) {
-      float v = __fmul_rn(a[k], w00);
-      v = __fadd_rn(v, __fmul_rn(b[k], w01));
-      v = __fadd_rn(v, __fmul_rn(c[k], w10));
-      v = __fadd_rn(v, __fmul_rn(d[k], w11));
-      if (c0 + k < c_end) out[(size_t)(c0 + k) * npix + p] = v;
+      for (int k = 0; k < WP_UNROLL; ++k) {
+        float v = __fmul_rn(a[k], w00);
+        v = __fadd_rn(v, __fmul_rn(b[k], w01));
+        v = __fadd_rn(v, __fmul_rn(c[k], w10));
+        v = __fadd_rn(v, __fmul_rn(d[k], w11));
+        po[(size_t)k * npix] = v;
+      }
+    } else {
+      for (int k = 0; c0 + k < C; ++k) {
+        float v = __fmul_rn(__ldg(p00 + (size_t)k * npix), w00);
+        v = __fadd_rn(v, __fmul_rn(__ldg(p01 + (size_t)k * npix), w01));
+        v = __fadd_rn(v, __fmul_rn(__ldg(p10 + (size_t)k * npix), w10));
+        v = __fadd_rn(v, __fmul_rn(__ldg(p11 + (size_t)k * npix), w11));
+        po[(size_t)k * npix] = v;
+      }
     }
   }
 }
@@ -421,13 +440,34 @@ cudaError_t launch_dcn_col(const DcnColParams& P, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+template <int NPIX>
+static cudaError_t launch_warp_t(const WarpParams& P, cudaStream_t stream) {
+  static int slots = 0;                         // resident CTAs of this instantiation on the whole device
+  if (!slots) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_kernel<NPIX>, WP_THREADS, 0);
+    slots = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const int bx = (P.H * P.W + WP_THREADS - 1) / WP_THREADS;
+  const int nbatch = (P.C + WP_UNROLL - 1) / WP_UNROLL;
+  int by = slots / bx;
+  if (by < 1) by = 1;
+  if (by > nbatch) by = nbatch;
+  warp_kernel<NPIX><<<dim3(bx, by), WP_THREADS, 0, stream>>>(P.feat, P.flow, P.out_nchw, P.C, P.H, P.W);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
   // The warped feature always lands as fp32 NCHW (`warping_feat_output`, or the handle's scratch when the
   // caller does not want it); the split NHWC copy the task head consumes is a second, L2-fed pass.
   if (!P.out_nchw) return cudaErrorInvalidValue;
-  dim3 grid((P.H * P.W + WP_THREADS - 1) / WP_THREADS, (P.C + WP_CH - 1) / WP_CH);
-  warp_kernel<<<grid, WP_THREADS, 0, stream>>>(P.feat, P.flow, P.out_nchw, P.C, P.H, P.W);
-  cudaError_t e = cudaGetLastError();
+  const int npix = P.H * P.W;
+  cudaError_t e;
+  if (npix == 64 * 128) e = launch_warp_t<64 * 128>(P, stream);          // 1024 x 2048 frames
+  else if (npix == 32 * 64) e = launch_warp_t<32 * 64>(P, stream);       // 512 x 1024
+  else e = launch_warp_t<0>(P, stream);
   if (e != cudaSuccess || !P.out_hi) return e;
   return launch_nchw_to_split(P.out_nchw, P.C, P.H, P.W, P.out_hi, P.out_lo, P.out_ld, stream);
 }

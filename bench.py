@@ -235,7 +235,8 @@ def run_native(a):
 
     # per-kernel timing of the warp launch, live, with CUDA events on the launching stream: 30 launches
     # rotating over three (source, destination) feature pairs (6 x 64 MiB > the 126 MB L2, so every read
-    # comes from HBM, as in the real loop where >1 GB of other traffic separates two warps of a stream).
+    # comes from HBM, as in the real loop where >1 GB of other traffic separates two warps of a stream),
+    # driven by the stream's own FlowNet flow field.
     warp_evs = []
     if I > 1:
         from accel_b200 import engine as _E
@@ -244,7 +245,7 @@ def run_native(a):
         bufs = [torch.randn(1, 2048, h, w, generator=g).to(dev) for _ in range(2)] + \
                [torch.empty(1, 2048, h, w, device=dev) for _ in range(4)]
         bufs[2].copy_(bufs[0]); bufs[4].copy_(bufs[1])
-        flow_t = (torch.randn(1, 2, h, w, generator=g) * 2.0).to(dev)
+        flow_t = eng.flownet(frames[1], frames[0]).clone()      # the flow field FlowNet produces on this stream
         pairs = [(bufs[0], bufs[1]), (bufs[2], bufs[3]), (bufs[4], bufs[5])]
         for k in range(6):
             _E.warp(pairs[k % 3][0], flow_t, pairs[k % 3][1])
