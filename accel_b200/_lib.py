@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libaccel_b200.so")
 SYMBOLS = (
     "accel_create", "accel_destroy", "accel_last_error", "accel_param_count", "accel_param_info",
     "accel_set_param", "accel_finalize", "accel_key_forward", "accel_cur_forward", "accel_flownet",
-    "accel_warp", "accel_fuse_argmax", "accel_conv_layer", "accel_last_launch_count",
+    "accel_warp", "accel_fuse_argmax", "accel_preprocess", "accel_confusion", "accel_conv_layer", "accel_last_launch_count",
     "accel_set_profiling", "accel_stage_times", "accel_op_times",
 )
 
@@ -53,6 +53,8 @@ def load():
     lib.accel_flownet.argtypes = [vp, vp, vp, vp, vp]
     lib.accel_warp.argtypes = [vp, vp, vp, ip, ip, ip, vp]
     lib.accel_fuse_argmax.argtypes = [vp, vp, vp, vp, ip, ip, ip, u8p, vp, vp]
+    lib.accel_preprocess.argtypes = [u8p, ip, ip, C.POINTER(C.c_double), vp, vp]
+    lib.accel_confusion.argtypes = [u8p, u8p, C.c_size_t, ip, vp, vp]
     lib.accel_conv_layer.argtypes = [ip, vp, ip, ip, ip, vp, ip, ip, ip, ip, ip, ip, vp, vp, vp, ip, vp, ip, vp, ip,
                                      C.c_char_p, ip]
     lib.accel_last_launch_count.argtypes = [vp]

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaccel_b200.so")
-SOURCES = ["abi.cu", "graph.cu", "nets.cu", "conv_ffma.cu", "conv_tc.cu", "stem_tc.cu", "kernels_basic.cu"]
+SOURCES = ["abi.cu", "graph.cu", "nets.cu", "conv_ffma.cu", "conv_tc.cu", "stem_tc.cu", "kernels_basic.cu", "kernels_io.cu", "warp_staged.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 

@@ -245,6 +245,21 @@ extern "C" int accel_fuse_argmax(const float* score_a, const float* score_b, con
   return e == cudaSuccess ? 0 : 5;
 }
 
+extern "C" int accel_preprocess(const uint8_t* bgr_hwc, int height, int width, const double pixel_means_bgr[3], float* out,
+                                void* stream) {
+  if (!bgr_hwc || !out || !pixel_means_bgr || height <= 0 || width <= 0) return 1;
+  if (no_device(nullptr, 0)) return 6;
+  return launch_preprocess(bgr_hwc, height, width, pixel_means_bgr, out, (cudaStream_t)stream) == cudaSuccess ? 0 : 5;
+}
+
+extern "C" int accel_confusion(const uint8_t* pred, const uint8_t* label, size_t count, int num_classes, int64_t* hist,
+                               void* stream) {
+  if (!pred || !label || !hist || num_classes < 1 || num_classes > 32) return 1;
+  if (no_device(nullptr, 0)) return 6;
+  return launch_confusion(pred, label, count, num_classes, reinterpret_cast<unsigned long long*>(hist),
+                          (cudaStream_t)stream) == cudaSuccess ? 0 : 5;
+}
+
 extern "C" int accel_conv_layer(int kind, const float* in, int cin, int hin, int win, const float* weight, int cout,
                                 int ksize, int stride, int pad, int dilate, int deform_groups, const float* offset,
                                 const float* scale, const float* shift, int act, const float* residual, int engine,

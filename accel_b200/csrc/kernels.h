@@ -90,6 +90,8 @@ struct WarpParams {
   int out_ld;
 };
 cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream);
+// shared-memory staged variant (warp_staged.cu); cudaErrorNotSupported = shape unsuitable, use the gather kernel
+cudaError_t launch_warp_staged(const WarpParams& P, cudaStream_t stream);
 
 // ---- layout conversion --------------------------------------------------------------------------------
 cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,
@@ -128,5 +130,13 @@ struct TailParams {
   float* score_out;          // fp32 planar (K, h*factor, w*factor) or nullptr
 };
 cudaError_t launch_tail(const TailParams& P, cudaStream_t stream);
+
+// ---- frame ingest + metric (kernels_io.cu) ---------------------------------------------------------------
+// lib/utils/image.py:224-235 transform(): uint8 BGR HWC -> fp32 RGB NCHW minus PIXEL_MEANS (B, G, R order)
+cudaError_t launch_preprocess(const uint8_t* bgr_hwc, int H, int W, const double mean_bgr[3], float* out,
+                              cudaStream_t stream);
+// dff_deeplab/demo.py:50-53 fast_hist(): hist[label * K + pred] += 1 where label < K (device int64 K x K)
+cudaError_t launch_confusion(const uint8_t* pred, const uint8_t* label, size_t n, int K, unsigned long long* hist,
+                             cudaStream_t stream);
 
 }  // namespace accel

@@ -1,5 +1,7 @@
 // Bandwidth-side kernels of the Accel hot path: stems, pooling, deformable im2col, flow-guided warp,
 // layout conversion, score fusion + x16 upsampling + argmax.  sm_100a only.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -459,12 +461,24 @@ static cudaError_t launch_warp_t(const WarpParams& P, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+static bool env_gather_only() {
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("ACCEL_WARP_GATHER"); v = (s && atoi(s)) ? 1 : 0; }
+  return v == 1;
+}
+
 cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
   // The warped feature always lands as fp32 NCHW (`warping_feat_output`, or the handle's scratch when the
   // caller does not want it); the split NHWC copy the task head consumes is a second, L2-fed pass.
   if (!P.out_nchw) return cudaErrorInvalidValue;
   const int npix = P.H * P.W;
-  cudaError_t e;
+  cudaError_t e = env_gather_only() ? cudaErrorNotSupported : launch_warp_staged(P, stream);
+  if (e == cudaSuccess) {
+    if (!P.out_hi) return e;
+    return launch_nchw_to_split(P.out_nchw, P.C, P.H, P.W, P.out_hi, P.out_lo, P.out_ld, stream);
+  }
+  if (e != cudaErrorNotSupported) return e;
+  cudaGetLastError();
   if (npix == 64 * 128) e = launch_warp_t<64 * 128>(P, stream);          // 1024 x 2048 frames
   else if (npix == 32 * 64) e = launch_warp_t<32 * 64>(P, stream);       // 512 x 1024
   else e = launch_warp_t<0>(P, stream);

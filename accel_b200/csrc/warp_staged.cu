@@ -1,0 +1,240 @@
+// Flow-guided warp with shared-memory staging of the source rows (sm_100a).
+//
+//   GridGenerator(transform_type='warp') + BilinearSampler  (dff_deeplab/symbols/accel_18.py:174-175)
+//   out[c, y, x] = sum over the 2x2 neighbourhood of  w * feat_key[c, y + dy, x + dx],  zeros outside
+//
+// The plain gather kernel (kernels_basic.cu) fetches each source value ~2.4 times through L2 (four taps, L1 hit
+// rate ~50 %), which makes it L2-fabric bound at ~0.55 of the HBM roofline.  Here a CTA owns TH full output rows
+// and a strided set of 8-channel batches.  The flow field over its rows fixes, once, the band of source rows
+// [r0, r0 + R) that its 2x2 neighbourhoods touch; for every channel that band is ONE contiguous run of R*W floats
+// in NCHW memory, so it is fetched with one `cp.async.bulk` (TMA 1-D bulk copy) into a 3-stage shared-memory ring,
+// each source byte crossing L2->SM once per row band.  The four taps are then gathered from shared memory and the
+// NCHW rows are written coalesced.  Per-pixel tap offsets and bilinear weights are computed once per CTA and kept
+// in registers for all channels.  Arithmetic and operation order are those of the gather kernel (and the oracle):
+// the result is bit-identical.  When the band does not fit (wild flow fields), the CTA gathers from global memory.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace accel {
+
+namespace {
+
+using namespace tc;
+
+constexpr int WS_CB = 8;          // channels per pipeline stage
+constexpr int WS_STAGES = 3;
+constexpr int WS_TILE = 1024;     // output pixels per CTA: TH * W <= WS_THREADS * WS_PPT = 1024
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+struct Tap {
+  int o00;        // offset of the (y0, x0) tap: (yi0 - r0) * W + xi0 when staged, yi0 * W + xi0 otherwise
+  int dx1, dyw;   // xi1 - xi0 (0 / 1), (yi1 - yi0) * W (0 / W)
+  float w00, w01, w10, w11;
+};
+
+template <int WS_THREADS, int WS_PPT>
+__global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __restrict__ feat, const float* __restrict__ flow,
+                                                                 float* __restrict__ out, int C, int H, int W, int TH, int RMAX) {
+  extern __shared__ __align__(128) float ring[];            // [WS_STAGES][WS_CB][RMAX * W]
+  __shared__ __align__(8) uint64_t bars[WS_STAGES];
+  __shared__ int s_min[WS_THREADS / 32], s_max[WS_THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int npix = H * W;
+  const int y0 = blockIdx.x * TH;
+  const int rows = min(TH, H - y0);
+  const int tile = rows * W;
+
+  // ---- per-pixel sampling positions (same fp32 operation sequence as MXNet: normalise to [-1,1], de-normalise)
+  Tap tap[WS_PPT];
+  int ymin = H, ymax = -1;
+  const float sx = (float)(W - 1) / 2.0f, sy = (float)(H - 1) / 2.0f;
+#pragma unroll
+  for (int k = 0; k < WS_PPT; ++k) {
+    const int q = tid + k * WS_THREADS;
+    Tap t;
+    t.o00 = 0; t.dx1 = 0; t.dyw = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+    if (q < tile) {
+      const int y = y0 + q / W, x = q - (q / W) * W;
+      const int p = y * W + x;
+      const float gx = __fsub_rn(__fdiv_rn(__fadd_rn(__ldg(flow + p), (float)x), sx), 1.0f);
+      const float gy = __fsub_rn(__fdiv_rn(__fadd_rn(__ldg(flow + npix + p), (float)y), sy), 1.0f);
+      const float xr = __fmul_rn(__fadd_rn(gx, 1.0f), sx);
+      const float yr = __fmul_rn(__fadd_rn(gy, 1.0f), sy);
+      const float xf = floorf(xr), yf = floorf(yr);
+      const float wx0 = __fsub_rn(1.0f, __fsub_rn(xr, xf)), wy0 = __fsub_rn(1.0f, __fsub_rn(yr, yf));
+      const float wx1 = __fsub_rn(1.0f, wx0), wy1 = __fsub_rn(1.0f, wy0);
+      const bool x0ok = xf >= 0.f && xf <= (float)(W - 1), x1ok = xf + 1.f >= 0.f && xf + 1.f <= (float)(W - 1);
+      const bool y0ok = yf >= 0.f && yf <= (float)(H - 1), y1ok = yf + 1.f >= 0.f && yf + 1.f <= (float)(H - 1);
+      const bool sane = fabsf(xr) < 1e9f && fabsf(yr) < 1e9f;       // keep the int conversion defined for wild flows
+      int xi0 = 0, xi1 = 0, yi0 = y, yi1 = y;                        // dead taps (all weights 0) point at the pixel itself
+      if (sane && (x0ok || x1ok) && (y0ok || y1ok)) {
+        xi0 = min(max((int)xf, 0), W - 1); xi1 = min(max((int)xf + 1, 0), W - 1);
+        yi0 = min(max((int)yf, 0), H - 1); yi1 = min(max((int)yf + 1, 0), H - 1);
+        t.w00 = (y0ok && x0ok) ? __fmul_rn(wy0, wx0) : 0.f;
+        t.w01 = (y0ok && x1ok) ? __fmul_rn(wy0, wx1) : 0.f;
+        t.w10 = (y1ok && x0ok) ? __fmul_rn(wy1, wx0) : 0.f;
+        t.w11 = (y1ok && x1ok) ? __fmul_rn(wy1, wx1) : 0.f;
+      }
+      t.o00 = yi0 * W + xi0; t.dx1 = xi1 - xi0; t.dyw = (yi1 - yi0) * W;
+      ymin = min(ymin, yi0); ymax = max(ymax, yi1);
+    }
+    tap[k] = t;
+  }
+  // ---- band of source rows this CTA touches
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  if (lane == 0) { s_min[wid] = ymin; s_max[wid] = ymax; }
+  if (tid == 0) {
+    for (int s = 0; s < WS_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < WS_THREADS / 32; ++i) { ymin = min(ymin, s_min[i]); ymax = max(ymax, s_max[i]); }
+  const int r0 = ymin, R = ymax - ymin + 1;
+  const int nbatch = (C + WS_CB - 1) / WS_CB;
+
+  if (R <= RMAX) {
+    // ================================ staged path ================================
+    const int band = R * W;                                   // floats per channel in the ring
+    const uint32_t band_bytes = (uint32_t)band * 4u;
+    const int slot = RMAX * W;
+#pragma unroll
+    for (int k = 0; k < WS_PPT; ++k) tap[k].o00 -= r0 * W;
+    const uint32_t ring0 = smem_u32(ring), bar0 = smem_u32(&bars[0]);
+    auto issue = [&](int bt, int s) {                          // one thread: WS_CB bulk copies -> stage s
+      const int c0 = bt * WS_CB;
+      const int nc = min(WS_CB, C - c0);
+      const uint32_t bar = bar0 + 8u * s;
+      mbar_arrive_expect_tx(bar, band_bytes * (uint32_t)nc);
+      for (int c = 0; c < nc; ++c)
+        bulk_load(ring0 + (uint32_t)((s * WS_CB + c) * slot) * 4u, feat + (size_t)(c0 + c) * npix + (size_t)r0 * W, band_bytes, bar);
+    };
+    int issued = 0;                                            // batches issued so far (this CTA's sequence)
+    if (tid == 0)
+      for (int bt = blockIdx.y; bt < nbatch && issued < WS_STAGES - 1; bt += gridDim.y, ++issued) issue(bt, issued);
+    int it = 0;
+    for (int bt = blockIdx.y; bt < nbatch; bt += gridDim.y, ++it) {
+      const int s = it % WS_STAGES;
+      if (tid == 0) {                                          // refill the stage everyone left at the end of iteration it-1
+        const int nb = bt + (WS_STAGES - 1) * gridDim.y;
+        if (nb < nbatch) issue(nb, (it + WS_STAGES - 1) % WS_STAGES);
+      }
+      mbar_wait(bar0 + 8u * s, (uint32_t)((it / WS_STAGES) & 1));
+      const int c0 = bt * WS_CB;
+      const int nc = min(WS_CB, C - c0);
+      const float* st = ring + (size_t)s * WS_CB * slot;
+#pragma unroll
+      for (int k = 0; k < WS_PPT; ++k) {
+        const int q = tid + k * WS_THREADS;
+        if (q < tile) {
+          const Tap t = tap[k];
+          float* po = out + (size_t)c0 * npix + (size_t)y0 * W + q;
+          if (nc == WS_CB) {
+            float a[WS_CB], b[WS_CB], c[WS_CB], d[WS_CB];
+#pragma unroll
+            for (int ch = 0; ch < WS_CB; ++ch) {
+              const float* sp = st + ch * slot + t.o00;
+              a[ch] = sp[0]; b[ch] = sp[t.dx1]; c[ch] = sp[t.dyw]; d[ch] = sp[t.dyw + t.dx1];
+            }
+#pragma unroll
+            for (int ch = 0; ch < WS_CB; ++ch) {
+              float v = __fmul_rn(a[ch], t.w00);
+              v = __fadd_rn(v, __fmul_rn(b[ch], t.w01));
+              v = __fadd_rn(v, __fmul_rn(c[ch], t.w10));
+              v = __fadd_rn(v, __fmul_rn(d[ch], t.w11));
+              po[(size_t)ch * npix] = v;
+            }
+          } else {
+            for (int ch = 0; ch < nc; ++ch) {
+              const float* sp = st + ch * slot + t.o00;
+              float v = __fmul_rn(sp[0], t.w00);
+              v = __fadd_rn(v, __fmul_rn(sp[t.dx1], t.w01));
+              v = __fadd_rn(v, __fmul_rn(sp[t.dyw], t.w10));
+              v = __fadd_rn(v, __fmul_rn(sp[t.dyw + t.dx1], t.w11));
+              po[(size_t)ch * npix] = v;
+            }
+          }
+        }
+      }
+      __syncthreads();                                         // stage s is free for the refill of iteration it+1
+    }
+  } else {
+    // ================================ gather path (band too tall) ================================
+    for (int bt = blockIdx.y; bt < nbatch; bt += gridDim.y) {
+      const int c0 = bt * WS_CB;
+      const int nc = min(WS_CB, C - c0);
+#pragma unroll
+      for (int k = 0; k < WS_PPT; ++k) {
+        const int q = tid + k * WS_THREADS;
+        if (q < tile) {
+          const Tap t = tap[k];
+          float* po = out + (size_t)c0 * npix + (size_t)y0 * W + q;
+          for (int ch = 0; ch < nc; ++ch) {
+            const float* sp = feat + (size_t)(c0 + ch) * npix + t.o00;
+            float v = __fmul_rn(__ldg(sp), t.w00);
+            v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dx1), t.w01));
+            v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dyw), t.w10));
+            v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dyw + t.dx1), t.w11));
+            po[(size_t)ch * npix] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// Returns cudaErrorNotSupported when the shape does not suit the staged kernel (caller falls back to the gather kernel).
+cudaError_t launch_warp_staged(const WarpParams& P, cudaStream_t stream) {
+  const int W = P.W, H = P.H;
+  if (W < 8 || (W & 3) || W > WS_TILE) return cudaErrorNotSupported;
+  if (((uintptr_t)P.feat & 15) != 0) return cudaErrorNotSupported;
+  int th = WS_TILE / W;
+  if (th > H) th = H;
+  static int max_smem = 0, sms = 0, variant = 512, stage_cap = 0;
+  if (!max_smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(warp_kernel_staged<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048) != cudaSuccess ||
+        cudaFuncSetAttribute(warp_kernel_staged<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048) != cudaSuccess) {
+      max_smem = 0;
+      return cudaErrorNotSupported;
+    }
+    variant = env_int("ACCEL_WARP_THREADS", 512);
+    stage_cap = env_int("ACCEL_WARP_RMAX", 0);
+  }
+  const int budget = max_smem - 4096;
+  int rmax = budget / (WS_STAGES * WS_CB * W * 4);
+  if (rmax > H) rmax = H;
+  if (stage_cap > 0 && rmax > stage_cap) rmax = stage_cap;      // tuning aid: smaller ring -> two CTAs per SM
+  if (rmax < th + 2 && rmax < H) return cudaErrorNotSupported;
+  const size_t smem = (size_t)WS_STAGES * WS_CB * rmax * W * 4;
+  const int bx = (H + th - 1) / th;
+  const int nbatch = (P.C + WS_CB - 1) / WS_CB;
+  const int per_sm = smem * 2 + 4096 <= (size_t)max_smem ? 2 : 1;
+  int by = (sms * per_sm) / bx;
+  if (by < 1) by = 1;
+  if (by > nbatch) by = nbatch;
+  if (variant == 256)
+    warp_kernel_staged<256, 4><<<dim3(bx, by), 256, smem, stream>>>(P.feat, P.flow, P.out_nchw, P.C, H, W, th, rmax);
+  else
+    warp_kernel_staged<512, 2><<<dim3(bx, by), 512, smem, stream>>>(P.feat, P.flow, P.out_nchw, P.C, H, W, th, rmax);
+  return cudaGetLastError();
+}
+
+}  // namespace accel

@@ -186,6 +186,50 @@ def fuse_argmax(score_a, score_b=None, corr_weight=None, corr_bias=None, want_sc
     return (label, full) if want_scores else label
 
 
+def preprocess(frame_bgr_u8, out=None, pixel_means_bgr=None):
+    """lib/utils/image.py:224-235 transform() on the device: (H,W,3) uint8 BGR CUDA tensor -> (1,3,H,W) fp32
+    RGB minus PIXEL_MEANS (float64 subtraction rounded once to fp32, as numpy + mx.nd.array)."""
+    lib = _lib.load()
+    if not (frame_bgr_u8.is_cuda and frame_bgr_u8.dtype == torch.uint8 and frame_bgr_u8.is_contiguous()
+            and frame_bgr_u8.dim() == 3 and frame_bgr_u8.shape[2] == 3):
+        raise TypeError("frame must be a contiguous CUDA uint8 tensor of shape (H, W, 3)")
+    h, w = int(frame_bgr_u8.shape[0]), int(frame_bgr_u8.shape[1])
+    if out is None:
+        out = torch.empty(1, 3, h, w, device=frame_bgr_u8.device)
+    else:
+        _check_f32_cuda("out", out, (1, 3, h, w))
+    if pixel_means_bgr is None:
+        from .synthetic import PIXEL_MEANS_BGR as pixel_means_bgr
+    means = (C.c_double * 3)(*[float(m) for m in pixel_means_bgr])
+    st = C.c_void_p(torch.cuda.current_stream(frame_bgr_u8.device).cuda_stream)
+    with torch.cuda.device(frame_bgr_u8.device):
+        rc = lib.accel_preprocess(_ptr(frame_bgr_u8), h, w, means, _ptr(out), st)
+    if rc != 0:
+        raise RuntimeError("accel_preprocess failed (%d)" % rc)
+    return out
+
+
+def confusion(pred, label, hist=None, num_classes=NUM_CLASSES):
+    """fast_hist(pred, label, n) of dff_deeplab/demo.py:50-53, accumulated into `hist` (n x n int64, CUDA)."""
+    lib = _lib.load()
+    for name, t in (("pred", pred), ("label", label)):
+        if not (t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()):
+            raise TypeError("%s must be a contiguous CUDA uint8 tensor" % name)
+    if pred.numel() != label.numel():
+        raise ValueError("pred and label differ in size")
+    if hist is None:
+        hist = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=pred.device)
+    elif not (hist.is_cuda and hist.dtype == torch.int64 and hist.is_contiguous()
+              and tuple(hist.shape) == (num_classes, num_classes)):
+        raise TypeError("hist must be a contiguous CUDA int64 tensor of shape (n, n)")
+    st = C.c_void_p(torch.cuda.current_stream(pred.device).cuda_stream)
+    with torch.cuda.device(pred.device):
+        rc = lib.accel_confusion(_ptr(pred), _ptr(label), pred.numel(), num_classes, _ptr(hist), st)
+    if rc != 0:
+        raise RuntimeError("accel_confusion failed (%d)" % rc)
+    return hist
+
+
 def conv_layer(x, weight, kind="conv", stride=1, pad=0, dilate=1, scale=None, shift=None, act=0, residual=None,
                offset=None, deform_groups=1, engine=0):
     """One layer through the library's kernels (parity-test hook, accel_conv_layer)."""

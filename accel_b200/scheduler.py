@@ -108,6 +108,96 @@ def segment_frame(engine, state, data, interval, schedule, label_out, score_out=
     return is_key
 
 
+class VideoPipeline:
+    """One video stream from HOST frames to HOST label maps -- the loop body of dff_deeplab/demo.py:228-252
+    with the frame ingest of demo.py:170-175 moved onto the GPU.
+
+    Per frame: the decoded uint8 BGR image (what cv2.imread + resize hand to `transform`, 3 bytes/pixel) is
+    copied from pinned host memory on a copy stream, `accel_preprocess` turns it into the fp32 `data` tensor,
+    the key or cur plan runs, and the uint8 label map is copied back on a third stream.  Copies of frame
+    i+1 / labels of frame i-1 overlap the graphs of frame i; nothing else crosses PCIe.  Optionally the
+    confusion matrix against ground-truth label maps is accumulated on the device (demo.py:270-272)."""
+
+    def __init__(self, engine, interval, schedule="chained", pixel_means_bgr=None, depth=2):
+        if schedule not in SCHEDULES:
+            raise ValueError("schedule must be one of %s" % (SCHEDULES,))
+        if interval < 1:
+            raise ValueError("Invalid interval %d - must be >=1" % interval)
+        from . import engine as _E
+        self._E = _E
+        self.engine, self.interval, self.schedule, self.means = engine, int(interval), schedule, pixel_means_bgr
+        dev = engine.torch_device
+        H, W = engine.height, engine.width
+        self.dev, self.depth = dev, int(depth)
+        self.state = StreamState(engine)
+        self.u8 = [torch.empty(H, W, 3, dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.f32 = [torch.empty(1, 3, H, W, device=dev) for _ in range(3)]       # cur / prev / key never collide
+        self.label = [torch.empty(H, W, dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.copy_in = torch.cuda.Stream(dev)
+        self.copy_out = torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # frame landed in u8[b]
+        self.ev_free = [torch.cuda.Event() for _ in range(depth)]     # u8[b] consumed by preprocess
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]     # label[b] written by the graph
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]      # label[b] copied to the host
+        self.n = 0
+        self.hist = torch.zeros(engine.num_classes, engine.num_classes, dtype=torch.int64, device=dev)
+
+    def reset(self):
+        """Start of a new video: the next frame is a key frame."""
+        self.state.index = 0
+        self.state.key_frame = self.state.prev_frame = None
+
+    def _pick_f32(self):
+        busy = {t.data_ptr() for t in (self.state.prev_frame, self.state.key_frame) if t is not None}
+        for t in self.f32:
+            if t.data_ptr() not in busy:
+                return t
+        raise RuntimeError("no free frame buffer")
+
+    def submit(self, frame_u8_host, label_host, gt_label=None):
+        """Queues one frame.  frame_u8_host: pinned (H,W,3) uint8 BGR; label_host: pinned (H,W) uint8, valid
+        after `sync()` (or once the returned event has completed); gt_label: optional CUDA uint8 (H,W)
+        ground truth to accumulate `hist` against.  Returns (is_key, event)."""
+        b = self.n % self.depth
+        main = torch.cuda.current_stream(self.dev)
+        if self.n >= self.depth:
+            self.copy_in.wait_event(self.ev_free[b])
+        with torch.cuda.stream(self.copy_in):
+            self.u8[b].copy_(frame_u8_host, non_blocking=True)
+            self.ev_in[b].record(self.copy_in)
+        main.wait_event(self.ev_in[b])
+        data = self._pick_f32()
+        self._E.preprocess(self.u8[b], data, self.means)
+        self.ev_free[b].record(main)
+        if self.n >= self.depth:
+            main.wait_event(self.ev_out[b])                                  # label[b] has left for the host
+        is_key = segment_frame(self.engine, self.state, data, self.interval, self.schedule, self.label[b])
+        if gt_label is not None:
+            self._E.confusion(self.label[b], gt_label, self.hist, self.engine.num_classes)
+        self.ev_done[b].record(main)
+        self.copy_out.wait_event(self.ev_done[b])
+        with torch.cuda.stream(self.copy_out):
+            label_host.copy_(self.label[b], non_blocking=True)
+            self.ev_out[b].record(self.copy_out)
+        self.n += 1
+        return is_key, self.ev_out[b]
+
+    def sync(self):
+        self.copy_out.synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    def segment_video(self, frames_u8_host, labels_host=None, gt_labels=None):
+        """Whole clip: list of pinned uint8 frames -> list of pinned uint8 label maps (synchronised)."""
+        self.reset()
+        H, W = self.engine.height, self.engine.width
+        if labels_host is None:
+            labels_host = [torch.empty(H, W, dtype=torch.uint8).pin_memory() for _ in frames_u8_host]
+        for i, f in enumerate(frames_u8_host):
+            self.submit(f, labels_host[i], None if gt_labels is None else gt_labels[i])
+        self.sync()
+        return labels_host
+
+
 def confusion_matrix(pred, label, n):
     """fast_hist of demo.py:50-53 on the GPU (int64 n x n; rows = label)."""
     pred = pred.reshape(-1).long()

@@ -120,12 +120,14 @@ def make_frames_u8(num_frames, height, width, stream=0, max_shift=8):
 
 
 def transform(frame_bgr_u8):
-    """lib/utils/image.py:224-235 `transform`: (H,W,3) BGR -> (1,3,H,W) fp32 RGB minus pixel means."""
-    im = frame_bgr_u8.to(torch.float32)
-    out = torch.empty(1, 3, im.shape[0], im.shape[1], dtype=torch.float32)
+    """lib/utils/image.py:224-235 `transform`: (H,W,3) BGR -> (1,3,H,W) fp32 RGB minus pixel means.
+    float64 arithmetic, one rounding to fp32 -- numpy's `im[:, :, 2 - i] - pixel_means[2 - i]` followed by
+    mx.nd.array (demo.py:185); accel_preprocess is the device version of this."""
+    im = frame_bgr_u8.to(torch.float64)
+    out = torch.empty(1, 3, im.shape[0], im.shape[1], dtype=torch.float64)
     for i in range(3):
         out[0, i] = im[:, :, 2 - i] - PIXEL_MEANS_BGR[2 - i]
-    return out
+    return out.to(torch.float32)
 
 
 def make_frames(num_frames, height, width, stream=0):

@@ -103,6 +103,20 @@ int accel_fuse_argmax(const float* score_a, const float* score_b, const float* c
                       const float* corr_bias, int num_classes, int h, int w, uint8_t* label,
                       float* score_full, void* stream);
 
+/* lib/utils/image.py:224-235 transform(im, pixel_means) as demo.py:170-175 applies it to every decoded
+ * frame: `bgr_hwc` is the (H,W,3) uint8 BGR image cv2.imread/resize returns, in DEVICE memory;
+ * pixel_means_bgr = config.network.PIXEL_MEANS (B, G, R; dff_deeplab_vid_demo.yaml:13-16), HOST doubles.
+ * out (1,3,H,W) fp32: out[0,i] = im[:,:,2-i] - pixel_means[2-i], computed in float64 and rounded once to
+ * float32 like numpy + mx.nd.array do (bit-exact).  Lets a frame cross PCIe as 3 bytes per pixel. */
+int accel_preprocess(const uint8_t* bgr_hwc, int height, int width, const double pixel_means_bgr[3], float* out,
+                     void* stream);
+
+/* fast_hist(pred, label, n) of dff_deeplab/demo.py:50-53 on the device: for every pixel with label < n,
+ * hist[label * n + pred] += 1.  pred/label: `count` uint8 values (label 255 = ignore); hist: n*n int64 in
+ * DEVICE memory, ACCUMULATED into (`hist += curr_hist`, demo.py:272) -- zero it before the first frame. */
+int accel_confusion(const uint8_t* pred, const uint8_t* label, size_t count, int num_classes, int64_t* hist,
+                    void* stream);
+
 /* One convolution-like layer through the same kernels the graphs use; parity-test hook.
  *   kind: 0 Convolution, 1 Deconvolution(k4,s2,p1 after crop), 2 DeformableConvolution(3x3,s1),
  *         3 the 7x7/s2/p3 stem over one fp32 NCHW frame (cin 3), 4 FlowNet's stem over the frame pair

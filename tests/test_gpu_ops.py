@@ -27,6 +27,31 @@ def test_warp_is_bit_exact_vs_oracle(c, h, w):
     assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("c,h,w,scale", [(2048, 64, 128, 0.7), (20, 64, 128, 1.5), (44, 32, 64, 0.5), (24, 24, 120, 1.0),
+                                         (16, 128, 256, 2.0), (8, 4, 1024, 0.5)])
+def test_warp_staged_rows_bit_exact(c, h, w, scale):
+    """Smooth FlowNet-like fields (the shared-memory staged path: narrow source-row band per CTA), channel
+    counts that are not a multiple of the 8-channel stage, widths that are not a power of two."""
+    feat = _rand(1, c, h, w, seed=4)
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    flow = torch.stack([scale * (3.0 * torch.sin(yy / 9.0) + 0.01 * xx - 2.0), scale * 2.0 * torch.cos(xx / 13.0 + yy / 7.0)])[None]
+    flow = (flow + _rand(1, 2, h, w, seed=5, scale=0.05)).contiguous()
+    ref = ops.bilinear_sampler(feat, ops.grid_generator_warp(flow))
+    out = E.warp(feat.to(DEV), flow.to(DEV)).cpu()
+    assert torch.equal(out, ref)
+
+
+def test_warp_mixed_band_heights():
+    """Half of the rows see a smooth field (staged CTAs), the other half a wild one (gather CTAs) in one launch."""
+    c, h, w = 40, 64, 128
+    feat = _rand(1, c, h, w, seed=6)
+    flow = _rand(1, 2, h, w, seed=7, scale=0.8)
+    flow[:, :, 32:] = _rand(1, 2, 32, w, seed=8, scale=25.0)
+    ref = ops.bilinear_sampler(feat, ops.grid_generator_warp(flow))
+    out = E.warp(feat.to(DEV), flow.to(DEV)).cpu()
+    assert torch.equal(out, ref)
+
+
 def test_warp_zero_flow_identity_and_integer_shift():
     feat = _rand(1, 32, 16, 32, seed=3)
     zero = torch.zeros(1, 2, 16, 32)
