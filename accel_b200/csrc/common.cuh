@@ -11,9 +11,39 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace accel {
 
 enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// A plan is a chain of several hundred short kernels on one stream.  Every kernel is launched with the
+// programmatic-stream-serialization attribute (launch_k below; the edges survive CUDA-graph capture), calls
+// pdl_trigger() first thing -- so the next kernel's CTAs may be scheduled, and run their prologue (barrier
+// init, TMEM allocation, descriptor prefetch, index arithmetic), on SMs as they drain -- and calls pdl_wait()
+// before its first global-memory access that is not a constant parameter / weight.  pdl_wait() returns once
+// the preceding kernel has completed and flushed, so the chain's memory ordering is that of a plain stream;
+// because EVERY kernel waits before it reads or writes activations, the guarantee is transitive.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // graph.cu: ACCEL_PDL=1 turns it on (measured neutral on B200 for these plans, so off by default)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 constexpr int kMaxTaps = 25;   // 5x5 is the largest generic kernel (FlowNet conv2/conv3); 7x7 stems are separate
 

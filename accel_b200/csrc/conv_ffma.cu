@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams P) {
   __shared__ __align__(16) float As[BK][LDS];
   __shared__ __align__(16) float Bs[BK][LDS];
 
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int m_load = tid & 63;       // pixel (A) / channel row (B) this thread stages
   const int j_load = tid >> 6;       // which 8-wide k sub-chunk
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams P) {
 // Deterministic split-K tail: sum the partial slabs in split order, then the shared epilogue.
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __restrict__ partial, int splits, int npix,
                                                               int Cout_pad, int Wo, const Epilogue epi) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = (epi.Cout + 3) / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)npix * groups) return;
@@ -145,6 +149,8 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __res
 // partial dot products meet in a shuffle tree.  Output is fp32 planar (and/or split NHWC).
 template <int NOUT>
 __global__ void __launch_bounds__(256) conv_narrow_kernel(const ConvParams P) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int npix = P.Ho * P.Wo;
@@ -215,29 +221,28 @@ size_t ffma_partial_bytes(const ConvParams& P, int splits) {
 cudaError_t launch_conv_ffma(const ConvParams& P, cudaStream_t stream) {
   const int npix = P.Ho * P.Wo;
   dim3 grid((npix + BM - 1) / BM, P.Cout_pad / BN, P.splits);
-  conv_ffma_kernel<<<grid, 256, 0, stream>>>(P);
-  if (P.splits > 1) {
+  cudaError_t e = launch_k(conv_ffma_kernel, grid, dim3(256), 0, stream, P);
+  if (e == cudaSuccess && P.splits > 1) {
     const long long work = (long long)npix * ((P.epi.Cout + 3) / 4);
-    splitk_epilogue_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P.partial, P.splits, npix, P.Cout_pad,
-                                                                                P.Wo, P.epi);
+    e = launch_k(splitk_epilogue_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, stream, (const float*)P.partial,
+                 P.splits, npix, P.Cout_pad, P.Wo, P.epi);
   }
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_splitk_epilogue(const float* partial, int splits, int npix, int Cout_pad, int Wo, const Epilogue& epi,
                                    cudaStream_t stream) {
   const long long work = (long long)npix * ((epi.Cout + 3) / 4);
-  splitk_epilogue_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(partial, splits, npix, Cout_pad, Wo, epi);
-  return cudaGetLastError();
+  return launch_k(splitk_epilogue_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, stream, partial, splits, npix,
+                  Cout_pad, Wo, epi);
 }
 
 cudaError_t launch_conv_narrow(const ConvParams& P, cudaStream_t stream) {
   const int npix = P.Ho * P.Wo;
   const unsigned blocks = (unsigned)(((long long)npix * 32 + 255) / 256);
-  if (P.epi.Cout <= 2) conv_narrow_kernel<2><<<blocks, 256, 0, stream>>>(P);
-  else if (P.epi.Cout <= 4) conv_narrow_kernel<4><<<blocks, 256, 0, stream>>>(P);
-  else conv_narrow_kernel<8><<<blocks, 256, 0, stream>>>(P);
-  return cudaGetLastError();
+  if (P.epi.Cout <= 2) return launch_k(conv_narrow_kernel<2>, dim3(blocks), dim3(256), 0, stream, P);
+  if (P.epi.Cout <= 4) return launch_k(conv_narrow_kernel<4>, dim3(blocks), dim3(256), 0, stream, P);
+  return launch_k(conv_narrow_kernel<8>, dim3(blocks), dim3(256), 0, stream, P);
 }
 
 }  // namespace accel

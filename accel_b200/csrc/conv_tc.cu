@@ -36,17 +36,22 @@ constexpr int BK = 64;           // channels per stage: 128 bytes of fp16 = one 
 constexpr int kEpiWarps = 8;      // two warps per TMEM lane quarter; they interleave the 32-column chunks of a tile
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
-constexpr int kSmemMaxDynamic = 227 * 1024 - 1024;   // 227 KB per CTA minus the static barriers/slots
+constexpr int kSmemMaxDynamic = 227 * 1024 - 6 * 1024;   // 227 KB per CTA minus the static barriers/slots/scale-shift stage
+// epilogue staging for TMA stores: per chunk set (2) x double buffer (2) x [hi | lo] x 128 pixel rows x 64 bytes
+constexpr int kStageOut = 2 * 2 * 2 * 8192;
 constexpr int kSmemBudget = kSmemMaxDynamic - 1024;      // minus the 1024-byte alignment slack
 
 struct alignas(64) TcParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap o_hi, o_lo;      // main split output, box = 32 channels x the tile's pixel box (TMA store), when tma_out
   Epilogue epi;
   float* partial;
   int BW, BH, BN, stages;
   int tiles_x, tiles_y, n_tiles, splits, kiters, chunks, ntaps;
   int stride2, Cin_pad, Ho, Wo, Cout_pad, tmem_cols;
   int krot;
+  int tma_out;     // 1: the main output leaves through shared memory + TMA tensor stores (3-D map), 2: 5-D map (transposed-conv phase)
+  int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = no TMA stores
   int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
   int8_t dy[kMaxTaps];
   int8_t dx[kMaxTaps];
@@ -57,11 +62,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float epi_sc[2][2][256];          // [accumulator][scale | shift][channel of the tile]
 
   // operand ring: [stage][A_hi | A_lo | B_hi | B_lo]
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = BM * 128u, b_bytes = (uint32_t)P.BN * 128u;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t stg0 = smem0 + (uint32_t)P.stages * stage_bytes;   // epilogue staging (1024-byte aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
@@ -85,9 +92,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();                                              // the prologue above touched no global memory
   const uint32_t tmem_base = tmem_base_slot;
 
   const int tiles = P.tiles_x * P.tiles_y * P.n_tiles;
@@ -164,15 +173,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else {
     // ===================================== epilogue ==========================================
     // Lane = pixel (TMEM lane), 32 consecutive output channels per chunk: 64 contiguous bytes per
-    // plane per thread, moved as 256-bit accesses; the residual of the next chunk is in flight
-    // while the current one is converted.
+    // plane per thread, moved as 256-bit accesses.  Everything the chunk loop would otherwise wait
+    // for is fetched while the mainloop of the tile still runs: the tile's per-channel scale/shift go
+    // to shared memory, and the residual is kept two chunks ahead in registers (2 x 128 B per thread
+    // in flight = 64 KB per SM, what one SM's share of the HBM stream needs).
     const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
     const int cset = (warp - 2) >> 2;                      // which interleaved chunk set (0 / 1)
     const int r = quarter * 32 + lane;                     // tile row = pixel inside the box
     const int by = r / P.BW, bx = r - by * P.BW;
     const int npix = P.Ho * P.Wo;
+    const int et = threadIdx.x - 64;                       // 0 .. 255 among the epilogue threads
     const Epilogue& E = P.epi;
-    int acc = 0;
+    int acc = 0, sbuf = 0;
     uint32_t accph = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = item % P.splits, tile = item / P.splits;
@@ -181,10 +193,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool valid = x < P.Wo && y < P.Ho;
       const int pix = (y * E.osy + E.ooy) * E.OWf + x * E.osx + E.oox;
       const int nbase = nt * P.BN;
-      const bool use_res = P.splits == 1 && E.res_hi != nullptr && P.vec32;
-      ResChunk rc{};
-      if (use_res && valid && nbase + cset * 32 + 32 <= E.Cout)
-        load_res(E, pix, nbase + cset * 32, rc);
+      const bool use_res = P.splits == 1 && E.res_hi != nullptr && P.vec32 && !(P.debug & 2);
+      if (P.splits == 1 && et < P.BN) {                    // this tile's scale / shift -> shared memory
+        const int c = nbase + et;
+        const bool in = c < E.Cout;
+        epi_sc[acc][0][et] = (in && P.epi.scale) ? __ldg(P.epi.scale + c) : 1.f;
+        epi_sc[acc][1][et] = (in && P.epi.shift) ? __ldg(P.epi.shift + c) : 0.f;
+      }
+      ResChunk rc{}, rc1{};
+      if (use_res && valid) {
+        if (nbase + cset * 32 + 32 <= E.Cout) load_res(E, pix, nbase + cset * 32, rc);
+        if (cset * 32 + 64 < P.BN && nbase + cset * 32 + 96 <= E.Cout) load_res(E, pix, nbase + cset * 32 + 64, rc1);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // scale/shift visible to all epilogue warps
       mbar_wait(tfull0 + 8 * acc, accph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN);
@@ -192,30 +213,66 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int n0 = nbase + cc;
         if (n0 >= P.Cout_pad) break;
         float v[32];
-        tmem_ld32(taddr + cc, v);
+        if (P.debug & 4) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 1.f;
+        } else {
+          tmem_ld32(taddr + cc, v);
+        }
         ResChunk rn{};
-        const int nn = n0 + 64;
-        if (use_res && valid && cc + 64 < P.BN && nn + 32 <= E.Cout) load_res(E, pix, nn, rn);
-        if (valid) {
+        const int nn = n0 + 128;
+        if (use_res && valid && cc + 128 < P.BN && nn + 32 <= E.Cout) load_res(E, pix, nn, rn);
+        if (P.tma_out && P.splits == 1) {
+          // Main output through shared memory: the chunk set's 4 warps stage 128 pixel rows x 32 channels of both
+          // planes (SWIZZLE_64B) and one thread hands the two tiles to the TMA unit -- full-line writes that bypass
+          // the LSU (a lane-per-pixel store is 32 separate 32-byte requests).  Two staging buffers per chunk set:
+          // the stores of chunk i drain while chunk i+1 is converted.  Out-of-range pixels / channels are clipped
+          // by the tensor map.
+          if (valid) epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[acc][0][cc], &epi_sc[acc][1][cc], false);
+          uint32_t wh[16], wl[16];
+          split32_words(v, wh, wl);
+          const uint32_t stg = stg0 + (uint32_t)(cset * 2 + sbuf) * 16384u;
+          const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
+          const bool leader = (quarter == 0 && lane == 0);
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer `sbuf` was read out
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + cset) : "memory");
+          stage_row64(stg, r, wh);
+          stage_row64(stg + 8192u, r, wl);
+          fence_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + cset) : "memory");
+          if (leader && !(P.debug & 1)) {
+            if (P.tma_out == 2) {
+              tma_store_5d(&P.o_hi, stg, n0, E.oox, x0, E.ooy, y0);
+              tma_store_5d(&P.o_lo, stg + 8192u, n0, E.oox, x0, E.ooy, y0);
+            } else {
+              tma_store_3d(&P.o_hi, stg, n0, x0, y0);
+              tma_store_3d(&P.o_lo, stg + 8192u, n0, x0, y0);
+            }
+            bulk_commit();
+          }
+          sbuf ^= 1;
+        } else if (valid && !(P.debug & 1)) {
           if (P.splits > 1) {
             float4* dst = reinterpret_cast<float4*>(P.partial + ((size_t)split * npix + (size_t)y * P.Wo + x) * P.Cout_pad + n0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           } else if (P.vec32 && n0 + 32 <= E.Cout) {
-            epilogue_chunk32(E, pix, n0, v, rc);
+            epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[acc][0][cc], &epi_sc[acc][1][cc]);
           } else {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               if (n0 + g * 8 < E.Cout) epilogue_store<8>(E, pix, n0 + g * 8, v + g * 8);
           }
         }
-        rc = rn;
+        rc = rc1;
+        rc1 = rn;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
+    if (P.tma_out && quarter == 0 && lane == 0) bulk_wait0();     // every tensor store of this CTA has landed
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -296,19 +353,25 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   if (bn != 64 && bn != 128 && bn != 256) bn = best_bn;
   P.BN = bn;
   P.n_tiles = (C.Cout_pad + bn - 1) / bn;
+  int splits = env_int("ACCEL_TC_SPLITS", bn == best_bn ? best_splits : 1);
+  if (splits > P.kiters) splits = P.kiters;
+  if (splits < 1) splits = 1;
   const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)bn * 128;
-  int stages = (int)(kSmemBudget / stage_bytes);
+  // Optional TMA-store epilogue (ACCEL_TC_TMA_OUT=1): needs kStageOut bytes of staging next to the operand ring,
+  // so only when at least two ring stages still fit (BN <= 128).  Measured on B200 (profiles/r01_layer_sweeps.txt)
+  // it does not beat the direct 256-bit stores -- the layers it targets are bound by SM<->L2 traffic, not by the
+  // LSU -- so it is off by default.
+  const bool want_stage = env_int("ACCEL_TC_TMA_OUT", 0) != 0 && splits == 1 && C.epi.out_hi != nullptr &&
+                          (kSmemBudget - kStageOut) / stage_bytes >= 2;
+  int stages = (int)((kSmemBudget - (want_stage ? kStageOut : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   P.stages = stages;
-  plan->smem = stages * stage_bytes + 1024;
+  plan->smem = stages * stage_bytes + 1024 + (want_stage ? kStageOut : 0);
   int cols = 32;
   while (cols < 2 * bn) cols *= 2;
   P.tmem_cols = cols;
 
   const int tiles = tiles_m * P.n_tiles;
-  int splits = env_int("ACCEL_TC_SPLITS", bn == best_bn ? best_splits : 1);
-  if (splits > P.kiters) splits = P.kiters;
-  if (splits < 1) splits = 1;
   P.splits = splits;
   plan->partial_bytes = splits > 1 ? (size_t)splits * C.Ho * C.Wo * C.Cout_pad * sizeof(float) : 0;
   const int items = tiles * splits;
@@ -323,6 +386,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     if (E.out2_hi) v = v && al32(E.out2_hi) && al32(E.out2_lo) && E.out2_ld % 16 == 0;
     P.vec32 = v ? 1 : 0;
     P.krot = env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
+    P.debug = env_int("ACCEL_TC_DEBUG", 0);
   }
 
   // tensor maps ------------------------------------------------------------------------------------
@@ -349,6 +413,29 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     ok = ok && encode(&P.b_hi, C.w_hi, 2, dims, str, box, err, errlen);
     ok = ok && encode(&P.b_lo, C.w_lo, 2, dims, str, box, err, errlen);
   }
+  {
+    // main output as TMA stores: channel chunks of 32 (64 bytes), the tile's BW x BH pixel box
+    const Epilogue& E = C.epi;
+    const bool can = want_stage && !(P.debug & 8) && P.splits == 1 && P.vec32 && E.out_hi && E.Cout % 8 == 0 && E.out_ld % 8 == 0 &&
+                     (E.Cout % 32 == 0 || (!E.res_hi && !E.out_nchw && !E.out2_hi));
+    P.tma_out = 0;
+    if (can && E.osy == 1 && E.osx == 1 && E.ooy == 0 && E.oox == 0) {
+      cuuint64_t dims[3] = {(cuuint64_t)E.Cout, (cuuint64_t)E.OWf, (cuuint64_t)E.OHf};
+      cuuint64_t str[2] = {(cuuint64_t)E.out_ld * e, (cuuint64_t)E.out_ld * E.OWf * e};
+      cuuint32_t box[3] = {32, (cuuint32_t)P.BW, (cuuint32_t)P.BH};
+      ok = ok && encode(&P.o_hi, E.out_hi, 3, dims, str, box, err, errlen, CU_TENSOR_MAP_SWIZZLE_64B);
+      ok = ok && encode(&P.o_lo, E.out_lo, 3, dims, str, box, err, errlen, CU_TENSOR_MAP_SWIZZLE_64B);
+      P.tma_out = 1;
+    } else if (can && E.osy == 2 && E.osx == 2 && E.OWf % 2 == 0 && E.OHf % 2 == 0) {
+      cuuint64_t dims[5] = {(cuuint64_t)E.Cout, 2, (cuuint64_t)E.OWf / 2, 2, (cuuint64_t)E.OHf / 2};
+      cuuint64_t str[4] = {(cuuint64_t)E.out_ld * e, 2 * (cuuint64_t)E.out_ld * e, (cuuint64_t)E.out_ld * E.OWf * e,
+                           2 * (cuuint64_t)E.out_ld * E.OWf * e};
+      cuuint32_t box[5] = {32, 1, (cuuint32_t)P.BW, 1, (cuuint32_t)P.BH};
+      ok = ok && encode(&P.o_hi, E.out_hi, 5, dims, str, box, err, errlen, CU_TENSOR_MAP_SWIZZLE_64B);
+      ok = ok && encode(&P.o_lo, E.out_lo, 5, dims, str, box, err, errlen, CU_TENSOR_MAP_SWIZZLE_64B);
+      P.tma_out = 2;
+    }
+  }
   if (!ok) {
     delete plan;
     return nullptr;
@@ -374,8 +461,7 @@ int tc_plan_launches(const TcPlan* plan) { return plan->launches; }
 cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, cudaStream_t stream) {
   TcParams P = plan->p;
   if (ext_nchw) P.epi.out_nchw = ext_nchw;
-  conv_tc_kernel<<<plan->grid, kThreads, plan->smem, stream>>>(P);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(conv_tc_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
   if (e != cudaSuccess) return e;
   if (P.splits > 1) return launch_splitk_epilogue(P.partial, P.splits, P.Ho * P.Wo, P.Cout_pad, P.Wo, P.epi, stream);
   return cudaSuccess;

@@ -1,4 +1,5 @@
 // Plan builder / executor.  See graph.h.
+#include <stdlib.h>
 #include "graph.h"
 
 #include <math.h>
@@ -7,6 +8,16 @@
 #include <algorithm>
 
 namespace accel {
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACCEL_PDL");
+    v = (e && *e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 

@@ -26,10 +26,12 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams P) {
   const int tid = threadIdx.x;
   const int Hp = P.pool ? P.Hs / 2 : P.Hs, Wp = P.pool ? P.Ws / 2 : P.Ws;   // size the conv sees
 
+  pdl_trigger();
   for (int i = tid; i < P.Cin * 49 * 64; i += 256) {
     const int n = i & 63, k = i >> 6;            // weight (n, c, ky, kx) -> ws[k][n], k = c*49 + ky*7 + kx
     ws[i] = P.weight[(size_t)n * P.Cin * 49 + k];
   }
+  pdl_wait();
   const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
   const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
   for (int i = tid; i < P.Cin * ST_PH * ST_PW; i += 256) {
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams P) {
 // Pooling over the split format: one thread per (output pixel, 8 channels).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pool_kernel(const PoolParams P) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = (P.C + 7) / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)P.Ho * P.Wo * groups) return;
@@ -130,6 +134,8 @@ __global__ void __launch_bounds__(256) pool_kernel(const PoolParams P) {
 // One thread per (pixel, tap, 8 channels); the four neighbours are 16-byte NHWC loads.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dcn_col_kernel(const DcnColParams P) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = P.C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)P.H * P.W * 9 * groups) return;
@@ -189,6 +195,8 @@ constexpr int WP_THREADS = 128, WP_UNROLL = 8;
 template <int NPIX>
 __global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restrict__ feat, const float* __restrict__ flow,
                                                           float* __restrict__ out, int C, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const int npix = NPIX > 0 ? NPIX : H * W;
   const int p = blockIdx.x * WP_THREADS + threadIdx.x;
   if (p >= npix) return;
@@ -262,6 +270,8 @@ __global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restric
 __global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ src, int C, int npix,
                                                             __half* hi, __half* lo, int ld) {
   __shared__ float tile[64][33];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
   float v[8];
@@ -287,6 +297,8 @@ __global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restr
 __global__ void __launch_bounds__(256) split_to_nchw_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
                                                             int ld, int C, int npix, float* dst) {
   __shared__ float tile[32][33];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   if (threadIdx.x < 128) {
@@ -312,6 +324,8 @@ __global__ void __launch_bounds__(256) split_to_nchw_kernel(const __half* __rest
 // FlowNet `upsample_flow*`: Deconvolution(2 -> 2, k4, s2, p0) + Crop(1,1) == transposed conv pad 1.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) upflow_kernel(const UpflowParams P) {
+  pdl_trigger();
+  pdl_wait();
   const int OW = 2 * P.W, OH = 2 * P.H;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= OW * OH) return;
@@ -351,8 +365,10 @@ __global__ void __launch_bounds__(256) upflow_kernel(const UpflowParams P) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) fuse_lowres_kernel(const FuseParams P) {
   extern __shared__ float wsm[];
+  pdl_trigger();
   for (int i = threadIdx.x; i < P.K * 2 * P.K; i += blockDim.x) wsm[i] = P.w[i];
   __syncthreads();
+  pdl_wait();
   const int npix = P.h * P.w_;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
@@ -376,6 +392,8 @@ __global__ void __launch_bounds__(128) fuse_lowres_kernel(const FuseParams P) {
 // The fp32 score volume is written only when the caller asks for it (parity mode).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tail_kernel(const TailParams P) {
+  pdl_trigger();
+  pdl_wait();
   const int OW = P.w * P.factor, OH = P.h * P.factor;
   const int qw = OW / 4;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -426,20 +444,17 @@ cudaError_t launch_stem(const StemParams& P, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((P.Wo + ST_TW - 1) / ST_TW, (P.Ho + ST_TH - 1) / ST_TH);
-  stem_kernel<<<grid, 256, smem, stream>>>(P);
-  return cudaGetLastError();
+  return launch_k(stem_kernel, grid, dim3(256), smem, stream, P);
 }
 
 cudaError_t launch_pool(const PoolParams& P, cudaStream_t stream) {
   const long long work = (long long)P.Ho * P.Wo * ((P.C + 7) / 8);
-  pool_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
-  return cudaGetLastError();
+  return launch_k(pool_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, stream, P);
 }
 
 cudaError_t launch_dcn_col(const DcnColParams& P, cudaStream_t stream) {
   const long long work = (long long)P.H * P.W * 9 * (P.C / 8);
-  dcn_col_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(P);
-  return cudaGetLastError();
+  return launch_k(dcn_col_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, stream, P);
 }
 
 template <int NPIX>
@@ -457,8 +472,7 @@ static cudaError_t launch_warp_t(const WarpParams& P, cudaStream_t stream) {
   int by = slots / bx;
   if (by < 1) by = 1;
   if (by > nbatch) by = nbatch;
-  warp_kernel<NPIX><<<dim3(bx, by), WP_THREADS, 0, stream>>>(P.feat, P.flow, P.out_nchw, P.C, P.H, P.W);
-  return cudaGetLastError();
+  return launch_k(warp_kernel<NPIX>, dim3(bx, by), dim3(WP_THREADS), 0, stream, P.feat, P.flow, P.out_nchw, P.C, P.H, P.W);
 }
 
 static bool env_gather_only() {
@@ -489,34 +503,29 @@ cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
 cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,
                                  cudaStream_t stream) {
   dim3 grid((H * W + 31) / 32, (ld + 63) / 64);
-  nchw_to_split_kernel<<<grid, 256, 0, stream>>>(src, C, H * W, hi, lo, ld);
-  return cudaGetLastError();
+  return launch_k(nchw_to_split_kernel, grid, dim3(256), 0, stream, src, C, H * W, hi, lo, ld);
 }
 
 cudaError_t launch_split_to_nchw(const __half* hi, const __half* lo, int ld, int C, int H, int W, float* dst,
                                  cudaStream_t stream) {
   dim3 grid((H * W + 31) / 32, (C + 31) / 32);
-  split_to_nchw_kernel<<<grid, 256, 0, stream>>>(hi, lo, ld, C, H * W, dst);
-  return cudaGetLastError();
+  return launch_k(split_to_nchw_kernel, grid, dim3(256), 0, stream, hi, lo, ld, C, H * W, dst);
 }
 
 cudaError_t launch_upflow(const UpflowParams& P, cudaStream_t stream) {
   const int work = 4 * P.H * P.W;
-  upflow_kernel<<<(work + 255) / 256, 256, 0, stream>>>(P);
-  return cudaGetLastError();
+  return launch_k(upflow_kernel, dim3((work + 255) / 256), dim3(256), 0, stream, P);
 }
 
 cudaError_t launch_fuse_lowres(const FuseParams& P, cudaStream_t stream) {
   if (P.K > 32) return cudaErrorInvalidValue;
   const int npix = P.h * P.w_;
-  fuse_lowres_kernel<<<(npix + 127) / 128, 128, (size_t)P.K * 2 * P.K * sizeof(float), stream>>>(P);
-  return cudaGetLastError();
+  return launch_k(fuse_lowres_kernel, dim3((npix + 127) / 128), dim3(128), (size_t)P.K * 2 * P.K * sizeof(float), stream, P);
 }
 
 cudaError_t launch_tail(const TailParams& P, cudaStream_t stream) {
   const int work = (P.w * P.factor / 4) * (P.h * P.factor);
-  tail_kernel<<<(work + 255) / 256, 256, 0, stream>>>(P);
-  return cudaGetLastError();
+  return launch_k(tail_kernel, dim3((work + 255) / 256), dim3(256), 0, stream, P);
 }
 
 }  // namespace accel

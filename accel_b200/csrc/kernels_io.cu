@@ -18,6 +18,8 @@ namespace {
 __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ src, int npix4, size_t plane,
                                                          double mean_b, double mean_g, double mean_r,
                                                          float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix4) return;
   const uint32_t* s = reinterpret_cast<const uint32_t*>(src) + (size_t)i * 3;
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
 __global__ void __launch_bounds__(256) preprocess_scalar_kernel(const uint8_t* __restrict__ src, size_t npix,
                                                                 double mean_b, double mean_g, double mean_r,
                                                                 float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   out[i] = (float)((double)src[3 * i + 2] - mean_r);
@@ -58,8 +62,10 @@ constexpr int CM_MAX = 32;
 __global__ void __launch_bounds__(256) confusion_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ label,
                                                         size_t n16, size_t n, int K, unsigned long long* __restrict__ hist) {
   __shared__ unsigned int sh[CM_MAX * CM_MAX];
+  pdl_trigger();
   for (int i = threadIdx.x; i < K * K; i += blockDim.x) sh[i] = 0u;
   __syncthreads();
+  pdl_wait();
   const uint4* p4 = reinterpret_cast<const uint4*>(pred);
   const uint4* l4 = reinterpret_cast<const uint4*>(label);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
@@ -93,11 +99,11 @@ cudaError_t launch_preprocess(const uint8_t* bgr_hwc, int H, int W, const double
   const bool vec = (npix % 4 == 0) && (((uintptr_t)bgr_hwc & 3) == 0) && (((uintptr_t)out & 15) == 0);
   if (vec) {
     const int npix4 = (int)(npix / 4);
-    preprocess_kernel<<<(npix4 + 255) / 256, 256, 0, stream>>>(bgr_hwc, npix4, npix, mean_bgr[0], mean_bgr[1], mean_bgr[2],
-                                                               out);
+    return launch_k(preprocess_kernel, dim3((npix4 + 255) / 256), dim3(256), 0, stream, bgr_hwc, npix4, npix, mean_bgr[0],
+                    mean_bgr[1], mean_bgr[2], out);
   } else {
-    preprocess_scalar_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(bgr_hwc, npix, mean_bgr[0], mean_bgr[1],
-                                                                                  mean_bgr[2], out);
+    return launch_k(preprocess_scalar_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, stream, bgr_hwc, npix,
+                    mean_bgr[0], mean_bgr[1], mean_bgr[2], out);
   }
   return cudaGetLastError();
 }
@@ -111,8 +117,7 @@ cudaError_t launch_confusion(const uint8_t* pred, const uint8_t* label, size_t n
   size_t blocks = (n16 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 2 * 148) blocks = 2 * 148;          // two CTAs per SM; each flushes K*K atomics once
-  confusion_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pred, label, n16, n, K, hist);
-  return cudaGetLastError();
+  return launch_k(confusion_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, pred, label, n16, n, K, hist);
 }
 
 }  // namespace accel

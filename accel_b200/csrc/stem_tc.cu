@@ -84,9 +84,11 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();                                                       // everything above touched no global memory
   const uint32_t tmem_base = tmem_base_slot;
   const int ntiles = P.tiles_x * P.tiles_y;
 
@@ -357,7 +359,7 @@ cudaError_t launch_stem_tc(const StemTcPlan* plan, const float* src0, const floa
   StemTcParams P = plan->p;
   P.src0 = src0;
   P.src1 = src1;
-  stem_tc_kernel<<<plan->grid, kThreads, plan->smem, stream>>>(P);
+  return launch_k(stem_tc_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
   return cudaGetLastError();
 }
 

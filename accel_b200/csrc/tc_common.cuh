@@ -104,6 +104,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- TMA tensor stores (shared -> global), bulk-group completion -----------------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One pixel row of a 32-channel fp16 chunk (64 bytes = four 16-byte pieces) into a SWIZZLE_64B staging tile:
+// piece j of row r lives at chunk j ^ ((r >> 1) & 3) -- address bits [4,5] xor bits [7,8] -- which also spreads
+// the 32 lanes of a warp over all banks.  `tile` is 512-byte aligned, rows are 64 bytes apart.
+__device__ __forceinline__ void stage_row64(uint32_t tile, int r, const uint32_t w[16]) {
+  const uint32_t row = tile + (uint32_t)r * 64u;
+  const uint32_t sw = ((uint32_t)r >> 1) & 3u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)j ^ sw) << 4)), "r"(w[4 * j]),
+                 "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                 : "memory");
+}
+
+// 32 activated fp32 values -> packed hi / lo fp16 pairs (16 words each)
+__device__ __forceinline__ void split32_words(const float v[32], uint32_t hi[16], uint32_t lo[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __half h0, l0, h1, l1;
+    split_f32(v[2 * i], h0, l0);
+    split_f32(v[2 * i + 1], h1, l1);
+    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+    hi[i] = *reinterpret_cast<uint32_t*>(&hh);
+    lo[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+}
+
 // ---- 256-bit global accesses (one full 32-byte sector per thread) ----------------------------------
 struct alignas(32) U8 {
   uint32_t v[8];
@@ -162,11 +204,23 @@ __device__ __forceinline__ void store_split32(__half* hi, __half* lo, const floa
 }
 
 // Epilogue of 32 consecutive channels [c0, c0+32) (all < Cout) of full-map pixel `pix`.
-__device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int c0, float v[32], const ResChunk& rc) {
+// sc32 / sh32: when non-null, the chunk's 32 scale / shift values staged in shared memory by the caller
+// (they replace e.scale / e.shift).
+// store_main = false: the caller writes the main split output itself (TMA store from shared memory); `v`
+// holds the activated values on return either way.
+__device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int c0, float v[32], const ResChunk& rc,
+                                                 const float* sc32 = nullptr, const float* sh32 = nullptr,
+                                                 bool store_main = true) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 s = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-    const float4 b = e.shift ? __ldg(reinterpret_cast<const float4*>(e.shift + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s, b;
+    if (sc32) {
+      s = *(reinterpret_cast<const float4*>(sc32) + q);
+      b = *(reinterpret_cast<const float4*>(sh32) + q);
+    } else {
+      s = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+      b = e.shift ? __ldg(reinterpret_cast<const float4*>(e.shift + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, b.x);
     v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, b.y);
     v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, b.z);
@@ -183,23 +237,24 @@ __device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
-  if (e.out_hi) store_split32(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
+  if (e.out_hi && store_main) store_split32(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
   if (e.out_nchw) {
     const size_t plane = (size_t)e.OHf * e.OWf;
 #pragma unroll
     for (int i = 0; i < 32; ++i) e.out_nchw[(size_t)(c0 + i) * plane + pix] = v[i];
   }
   if (e.out2_hi) {
+    float v2[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 s = __ldg(reinterpret_cast<const float4*>(e.scale2 + c0) + q);
       const float4 b = __ldg(reinterpret_cast<const float4*>(e.shift2 + c0) + q);
-      v[4 * q + 0] = apply_act(fmaf(v[4 * q + 0], s.x, b.x), e.act2);
-      v[4 * q + 1] = apply_act(fmaf(v[4 * q + 1], s.y, b.y), e.act2);
-      v[4 * q + 2] = apply_act(fmaf(v[4 * q + 2], s.z, b.z), e.act2);
-      v[4 * q + 3] = apply_act(fmaf(v[4 * q + 3], s.w, b.w), e.act2);
+      v2[4 * q + 0] = apply_act(fmaf(v[4 * q + 0], s.x, b.x), e.act2);
+      v2[4 * q + 1] = apply_act(fmaf(v[4 * q + 1], s.y, b.y), e.act2);
+      v2[4 * q + 2] = apply_act(fmaf(v[4 * q + 2], s.z, b.z), e.act2);
+      v2[4 * q + 3] = apply_act(fmaf(v[4 * q + 3], s.w, b.w), e.act2);
     }
-    store_split32(e.out2_hi + (size_t)pix * e.out2_ld + c0, e.out2_lo + (size_t)pix * e.out2_ld + c0, v);
+    store_split32(e.out2_hi + (size_t)pix * e.out2_ld + c0, e.out2_lo + (size_t)pix * e.out2_ld + c0, v2);
   }
 }
 
@@ -221,7 +276,7 @@ inline EncodeTiledFn encode_fn() {
 }
 
 inline bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-            const cuuint32_t* box, char* err, int errlen) {
+            const cuuint32_t* box, char* err, int errlen, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled is unavailable");
@@ -229,7 +284,7 @@ inline bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu] box [%u %u %u]", (int)r, rank,

@@ -22,7 +22,6 @@ namespace {
 
 using namespace tc;
 
-constexpr int WS_CB = 8;          // channels per pipeline stage
 constexpr int WS_STAGES = 3;
 constexpr int WS_TILE = 1024;     // output pixels per CTA: TH * W <= WS_THREADS * WS_PPT = 1024
 
@@ -38,13 +37,16 @@ struct Tap {
   float w00, w01, w10, w11;
 };
 
-template <int WS_THREADS, int WS_PPT>
+// WS_CB = channels per pipeline stage
+template <int WS_THREADS, int WS_PPT, int WS_CB>
 __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __restrict__ feat, const float* __restrict__ flow,
                                                                  float* __restrict__ out, int C, int H, int W, int TH, int RMAX) {
   extern __shared__ __align__(128) float ring[];            // [WS_STAGES][WS_CB][RMAX * W]
   __shared__ __align__(8) uint64_t bars[WS_STAGES];
   __shared__ int s_min[WS_THREADS / 32], s_max[WS_THREADS / 32];
 
+  pdl_trigger();
+  pdl_wait();                                               // the flow field is the previous kernel's output
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int npix = H * W;
   const int y0 = blockIdx.x * TH;
@@ -181,13 +183,31 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
         if (q < tile) {
           const Tap t = tap[k];
           float* po = out + (size_t)c0 * npix + (size_t)y0 * W + q;
-          for (int ch = 0; ch < nc; ++ch) {
-            const float* sp = feat + (size_t)(c0 + ch) * npix + t.o00;
-            float v = __fmul_rn(__ldg(sp), t.w00);
-            v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dx1), t.w01));
-            v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dyw), t.w10));
-            v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dyw + t.dx1), t.w11));
-            po[(size_t)ch * npix] = v;
+          const float* sp0 = feat + (size_t)c0 * npix + t.o00;
+          if (nc == WS_CB) {
+            float a[WS_CB], b[WS_CB], c[WS_CB], d[WS_CB];
+#pragma unroll
+            for (int ch = 0; ch < WS_CB; ++ch) {
+              const float* sp = sp0 + (size_t)ch * npix;
+              a[ch] = __ldg(sp); b[ch] = __ldg(sp + t.dx1); c[ch] = __ldg(sp + t.dyw); d[ch] = __ldg(sp + t.dyw + t.dx1);
+            }
+#pragma unroll
+            for (int ch = 0; ch < WS_CB; ++ch) {
+              float v = __fmul_rn(a[ch], t.w00);
+              v = __fadd_rn(v, __fmul_rn(b[ch], t.w01));
+              v = __fadd_rn(v, __fmul_rn(c[ch], t.w10));
+              v = __fadd_rn(v, __fmul_rn(d[ch], t.w11));
+              po[(size_t)ch * npix] = v;
+            }
+          } else {
+            for (int ch = 0; ch < nc; ++ch) {
+              const float* sp = sp0 + (size_t)ch * npix;
+              float v = __fmul_rn(__ldg(sp), t.w00);
+              v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dx1), t.w01));
+              v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dyw), t.w10));
+              v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dyw + t.dx1), t.w11));
+              po[(size_t)ch * npix] = v;
+            }
           }
         }
       }
@@ -197,44 +217,58 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
 
 }  // namespace
 
+template <int THREADS, int PPT, int CB>
+static cudaError_t launch_variant(const WarpParams& P, int th, int max_smem, int sms, int stage_cap, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(warp_kernel_staged<THREADS, PPT, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             max_smem - 2048) != cudaSuccess)
+      return cudaErrorNotSupported;
+    configured = true;
+  }
+  const int W = P.W, H = P.H;
+  // ring sized for `per_sm` resident CTAs: CB = 4 -> two CTAs per SM (one CTA's barrier bubbles hide behind the other)
+  const int per_sm = CB <= 4 ? 2 : 1;
+  const int budget = max_smem / per_sm - 4096;
+  int rmax = budget / (WS_STAGES * CB * W * 4);
+  if (rmax > H) rmax = H;
+  if (stage_cap > 0 && rmax > stage_cap) rmax = stage_cap;
+  if (rmax < th + 2 && rmax < H) return cudaErrorNotSupported;
+  const size_t smem = (size_t)WS_STAGES * CB * rmax * W * 4;
+  const int bx = (H + th - 1) / th;
+  const int nbatch = (P.C + CB - 1) / CB;
+  int by = (sms * per_sm) / bx;
+  if (by < 1) by = 1;
+  if (by > nbatch) by = nbatch;
+  return launch_k(warp_kernel_staged<THREADS, PPT, CB>, dim3(bx, by), dim3(THREADS), smem, stream, P.feat, P.flow, P.out_nchw, P.C,
+                  H, W, th, rmax);
+}
+
 // Returns cudaErrorNotSupported when the shape does not suit the staged kernel (caller falls back to the gather kernel).
 cudaError_t launch_warp_staged(const WarpParams& P, cudaStream_t stream) {
   const int W = P.W, H = P.H;
   if (W < 8 || (W & 3) || W > WS_TILE) return cudaErrorNotSupported;
   if (((uintptr_t)P.feat & 15) != 0) return cudaErrorNotSupported;
-  int th = WS_TILE / W;
-  if (th > H) th = H;
-  static int max_smem = 0, sms = 0, variant = 512, stage_cap = 0;
+  static int max_smem = 0, sms = 0, threads = 512, cb = 4, stage_cap = 0, th_cap = 0;
   if (!max_smem) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(warp_kernel_staged<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048) != cudaSuccess ||
-        cudaFuncSetAttribute(warp_kernel_staged<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048) != cudaSuccess) {
-      max_smem = 0;
-      return cudaErrorNotSupported;
-    }
-    variant = env_int("ACCEL_WARP_THREADS", 512);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    threads = env_int("ACCEL_WARP_THREADS", 512);          // tuning aids (tools/bench_warp.py)
+    cb = env_int("ACCEL_WARP_CB", 4);
     stage_cap = env_int("ACCEL_WARP_RMAX", 0);
+    th_cap = env_int("ACCEL_WARP_TH", 0);
   }
-  const int budget = max_smem - 4096;
-  int rmax = budget / (WS_STAGES * WS_CB * W * 4);
-  if (rmax > H) rmax = H;
-  if (stage_cap > 0 && rmax > stage_cap) rmax = stage_cap;      // tuning aid: smaller ring -> two CTAs per SM
-  if (rmax < th + 2 && rmax < H) return cudaErrorNotSupported;
-  const size_t smem = (size_t)WS_STAGES * WS_CB * rmax * W * 4;
-  const int bx = (H + th - 1) / th;
-  const int nbatch = (P.C + WS_CB - 1) / WS_CB;
-  const int per_sm = smem * 2 + 4096 <= (size_t)max_smem ? 2 : 1;
-  int by = (sms * per_sm) / bx;
-  if (by < 1) by = 1;
-  if (by > nbatch) by = nbatch;
-  if (variant == 256)
-    warp_kernel_staged<256, 4><<<dim3(bx, by), 256, smem, stream>>>(P.feat, P.flow, P.out_nchw, P.C, H, W, th, rmax);
-  else
-    warp_kernel_staged<512, 2><<<dim3(bx, by), 512, smem, stream>>>(P.feat, P.flow, P.out_nchw, P.C, H, W, th, rmax);
-  return cudaGetLastError();
+  int th = WS_TILE / W;
+  if (th > H) th = H;
+  if (th_cap > 0 && th > th_cap) th = th_cap;
+  if (threads == 256) {
+    if (cb == 8) return launch_variant<256, 4, 8>(P, th, max_smem, sms, stage_cap, stream);
+    return launch_variant<256, 4, 4>(P, th, max_smem, sms, stage_cap, stream);
+  }
+  if (cb == 8) return launch_variant<512, 2, 8>(P, th, max_smem, sms, stage_cap, stream);
+  return launch_variant<512, 2, 4>(P, th, max_smem, sms, stage_cap, stream);
 }
 
 }  // namespace accel

@@ -97,8 +97,11 @@ class Predictor:
 
     def __init__(self, symbol, data_names, label_names, context=None, max_data_shapes=None, provide_data=None,
                  provide_label=None, arg_params=None, aux_params=None, engine=None, emit_scores=True, flags=0):
-        if list(data_names)[:3] != ["data", "data_key", "feat_key"]:
-            raise ValueError("data_names must be ['data', 'data_key', 'feat_key'] (demo.py:184)")
+        names = list(data_names)
+        if not all(k in names for k in ("data", "data_key", "feat_key")):
+            raise ValueError("data_names must contain 'data', 'data_key', 'feat_key' (demo.py:184; TestLoader adds "
+                             "'im_info', core/loader.py:214)")
+        self._slots = tuple(names.index(k) for k in ("data", "data_key", "feat_key"))
         self.symbol = symbol
         self.output_names = symbol.list_outputs()
         ctx = context[0] if isinstance(context, (list, tuple)) else context
@@ -117,7 +120,7 @@ class Predictor:
 
     def predict(self, data_batch):
         """Returns [ {output_name: tensor} ] for the single device, like tester.py:32-35."""
-        data, data_key, feat_key = data_batch.data[0][:3]
+        data, data_key, feat_key = (data_batch.data[0][i] for i in self._slots)
         eng = self.engine
         feat_out = self._feat[self._flip]
         if self.symbol.kind == "cur" and feat_key.data_ptr() == feat_out.data_ptr():

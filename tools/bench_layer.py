@@ -43,10 +43,27 @@ SWEEP = [
 ]
 
 
+DEBUG_SWEEP = [
+    {},
+    {"ACCEL_TC_TMA_OUT": "0"},
+    {"ACCEL_TC_BN": "128", "ACCEL_TC_TMA_OUT": "0"},
+    {"ACCEL_TC_BN": "64"},
+    {"ACCEL_TC_BN": "64", "ACCEL_TC_TMA_OUT": "0"},
+    {"ACCEL_TC_DEBUG": "1"},
+    {"ACCEL_TC_DEBUG": "2"},
+    {"ACCEL_TC_DEBUG": "3"},
+    {"ACCEL_TC_DEBUG": "7"},
+    {"ACCEL_TC_BN": "128"},
+    {"ACCEL_TC_BN": "128", "ACCEL_TC_DEBUG": "3"},
+    {"ACCEL_TC_BN": "128", "ACCEL_TC_DEBUG": "7"},
+]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--set", default="")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--sweep", default="default")
     a = ap.parse_args()
     os.environ["ACCEL_LAYER_REPS"] = str(a.reps)
     names = [n for n in LAYERS if not a.set or n in a.set.split(",")]
@@ -59,8 +76,8 @@ def main():
         ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
         wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
         r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
-        for knobs in SWEEP:
-            for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES"):
+        for knobs in (DEBUG_SWEEP if a.sweep == "debug" else SWEEP):
+            for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT"):
                 os.environ.pop(kk, None)
             os.environ.update(knobs)
             sys.stderr.write("%-14s %-44s " % (name, knobs))

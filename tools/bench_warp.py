@@ -34,10 +34,13 @@ def main():
         "zero": torch.zeros(1, 2, h, w),
         "const(3.3,-1.7)": torch.stack([torch.full((h, w), 3.3), torch.full((h, w), -1.7)])[None],
         "smooth": torch.stack([3.0 * torch.sin(yy / 9.0) + 0.01 * xx, 2.0 * torch.cos(xx / 13.0)])[None],
+        "smooth+noise": torch.stack([3.0 * torch.sin(yy / 9.0) + 0.01 * xx, 2.0 * torch.cos(xx / 13.0)])[None]
+        + torch.randn(1, 2, h, w, generator=g) * 0.3,
         "random(2px)": torch.randn(1, 2, h, w, generator=g) * 2.0,
     }
     nbytes = 2 * C * h * w * 4 + 2 * h * w * 4
     us = timeit(lambda k: dst[k % 3].copy_(src[k % 3]))
+    print("env:", {k: v for k, v in os.environ.items() if k.startswith("ACCEL_WARP")})
     print("torch copy_            %7.2f us  %7.1f GB/s" % (us, 2 * C * h * w * 4 / us / 1e3))
     for name, fl in flows.items():
         fl = fl.contiguous().to(dev)
