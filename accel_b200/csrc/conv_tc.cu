@@ -50,6 +50,7 @@ struct alignas(64) TcParams {
   int tiles_x, tiles_y, n_tiles, splits, kiters, chunks, ntaps;
   int stride2, Cin_pad, Ho, Wo, Cout_pad, tmem_cols;
   int krot;
+  int pair;        // 1: conv_tc2_kernel (cta_group::2 pairs)
   int tma_out;     // 1: the main output leaves through shared memory + TMA tensor stores (3-D map), 2: 5-D map (transposed-conv phase)
   int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = no TMA stores
   int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
@@ -283,6 +284,271 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 }
 
+
+// ================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster -- two SMs of one TPC -- share one
+// 256-pixel x BN tile.  Each CTA stages its own 128 pixel rows of A and HALF of the BN weight rows;
+// the pair's tensor cores read both halves, so per SM the weight traffic (L2 -> shared memory and
+// shared memory -> tensor core) is halved, which is what bounds the single-CTA kernel on these
+// hi/lo-plane operands.  The leader CTA (cluster rank 0) issues every MMA; TMA loads of both CTAs
+// signal the LEADER's `full` barrier, MMA completion is multicast to both CTAs' `empty` / `tfull`
+// barriers, and the peer's epilogue warps release the accumulator on the leader's `tempty` barrier.
+// ================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_idx() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float epi_sc[2][2][256];
+
+  // operand ring per CTA: [stage][A_hi | A_lo | B_hi half | B_lo half]
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = BM * 128u, b_bytes = (uint32_t)(P.BN / 2) * 128u;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * kMaxStages]), tempty0 = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(full0 + 8 * s, 2);                  // (leader's copy is the live one) one arrival per CTA's producer
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 2 * kEpiWarps);    // (leader's copy) the epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {                                  // one warp of EACH CTA takes part in the pair allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  pdl_trigger();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                               // barriers of both CTAs are initialised before anyone signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tiles_m = P.tiles_x * P.tiles_y;
+  const int tiles_m2 = (tiles_m + 1) / 2;
+  const int items = tiles_m2 * P.n_tiles * P.splits;
+  const int cid = (int)cluster_idx(), ncl = (int)cluster_count();
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = cid; item < items; item += ncl) {
+        const int split = item % P.splits, tile = item / P.splits;
+        const int nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * 2 + (int)rank;     // phantom tile past the end: all OOB
+        const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
+        const int kb = (int)(((long long)P.kiters * split) / P.splits);
+        const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
+        const int rot = P.krot ? (int)(((unsigned)item * 5u) % (unsigned)(ke - kb)) : 0;
+        for (int i = kb; i < ke; ++i) {
+          int it = i + rot;
+          if (it >= ke) it -= ke - kb;
+          const int t = it / P.chunks, kc = it - t * P.chunks;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t fb = mapa_u32(full0 + 8 * s, 0);                // the LEADER's full barrier
+          const uint32_t sa = smem0 + s * stage_bytes;
+          const int dy = P.dy[t], dx = P.dx[t];
+          if (P.stride2) {
+            tma2_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+            tma2_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+          } else {
+            tma2_load_3d(sa, &P.a_hi, fb, kc * BK, x0 + dx, y0 + dy);
+            tma2_load_3d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, y0 + dy);
+          }
+          const int kcol = t * P.Cin_pad + kc * BK;
+          const int nrow = nt * P.BN + (int)rank * (P.BN / 2);
+          tma2_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nrow);
+          tma2_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nrow);
+          if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * stage_bytes);   // bytes of BOTH CTAs' loads
+          else mbar_arrive_cluster(fb);
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) ==================================
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, accph = 0;
+      for (int item = cid; item < items; item += ncl) {
+        const int split = item % P.splits;
+        const int kb = (int)(((long long)P.kiters * split) / P.splits);
+        const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
+        mbar_wait(tempty0 + 8 * acc, accph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_base + (uint32_t)(acc * P.BN);
+        for (int it = kb; it < ke; ++it) {
+          mbar_wait(full0 + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem0 + s * stage_bytes;
+          const uint64_t ah = umma_desc(sa), al = umma_desc(sa + a_bytes);
+          const uint64_t bh = umma_desc(sa + 2 * a_bytes), bl = umma_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma2_f16(d, ah + adv, bh + adv, idesc, (it > kb || k > 0) ? 1u : 0u);
+            umma2_f16(d, ah + adv, bl + adv, idesc, 1u);
+            umma2_f16(d, al + adv, bh + adv, idesc, 1u);
+          }
+          umma2_commit(empty0 + 8 * s);                   // frees the stage in both CTAs
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
+        umma2_commit(tfull0 + 8 * acc);                   // accumulator complete -> both CTAs' epilogues
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue (each CTA: its own 128 pixel rows) =====================
+    const int quarter = warp & 3;
+    const int cset = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const int by = r / P.BW, bx = r - by * P.BW;
+    const int npix = P.Ho * P.Wo;
+    const int et = threadIdx.x - 64;
+    const Epilogue& E = P.epi;
+    const uint32_t tempty_leader0 = mapa_u32(tempty0, 0);
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int item = cid; item < items; item += ncl) {
+      const int split = item % P.splits, tile = item / P.splits;
+      const int nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * 2 + (int)rank;
+      const int x = (mt % P.tiles_x) * P.BW + bx, y = (mt / P.tiles_x) * P.BH + by;
+      const bool valid = mt < tiles_m && x < P.Wo && y < P.Ho;
+      const int pix = (y * E.osy + E.ooy) * E.OWf + x * E.osx + E.oox;
+      const int nbase = nt * P.BN;
+      const bool use_res = P.splits == 1 && E.res_hi != nullptr && P.vec32;
+      if (P.splits == 1 && et < P.BN) {
+        const int c = nbase + et;
+        const bool in = c < E.Cout;
+        epi_sc[acc][0][et] = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
+        epi_sc[acc][1][et] = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
+      }
+      ResChunk rc{}, rc1{};
+      if (use_res && valid) {
+        if (nbase + cset * 32 + 32 <= E.Cout) load_res(E, pix, nbase + cset * 32, rc);
+        if (cset * 32 + 64 < P.BN && nbase + cset * 32 + 96 <= E.Cout) load_res(E, pix, nbase + cset * 32 + 64, rc1);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(tfull0 + 8 * acc, accph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN);
+      for (int cc = cset * 32; cc < P.BN; cc += 64) {
+        const int n0 = nbase + cc;
+        if (n0 >= P.Cout_pad) break;
+        float v[32];
+        tmem_ld32(taddr + cc, v);
+        ResChunk rn{};
+        const int nn = n0 + 128;
+        if (use_res && valid && cc + 128 < P.BN && nn + 32 <= E.Cout) load_res(E, pix, nn, rn);
+        if (valid) {
+          if (P.splits > 1) {
+            float4* dst = reinterpret_cast<float4*>(P.partial + ((size_t)split * npix + (size_t)y * P.Wo + x) * P.Cout_pad + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else if (P.vec32 && n0 + 32 <= E.Cout) {
+            epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[acc][0][cc], &epi_sc[acc][1][cc]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (n0 + g * 8 < E.Cout) epilogue_store<8>(E, pix, n0 + g * 8, v + g * 8);
+          }
+        }
+        rc = rc1;
+        rc1 = rn;
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * acc);     // the leader's MMA thread owns this wait
+      if (++acc == 2) { acc = 0; accph ^= 1; }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                               // nobody leaves while its partner may still signal or read it
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
+  }
+}
+
 }  // namespace
 
 struct TcPlan {
@@ -351,17 +617,19 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   }
   int bn = env_int("ACCEL_TC_BN", best_bn);
   if (bn != 64 && bn != 128 && bn != 256) bn = best_bn;
+  P.pair = env_int("ACCEL_TC_PAIR", 0) != 0 ? 1 : 0;
+  if (P.pair && bn > C.Cout_pad && bn != 64) P.pair = 0;
   P.BN = bn;
   P.n_tiles = (C.Cout_pad + bn - 1) / bn;
   int splits = env_int("ACCEL_TC_SPLITS", bn == best_bn ? best_splits : 1);
   if (splits > P.kiters) splits = P.kiters;
   if (splits < 1) splits = 1;
-  const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)bn * 128;
+  const size_t stage_bytes = 2 * (size_t)BM * 128 + (P.pair ? 1 : 2) * (size_t)bn * 128;   // pair: half the weight rows per CTA
   // Optional TMA-store epilogue (ACCEL_TC_TMA_OUT=1): needs kStageOut bytes of staging next to the operand ring,
   // so only when at least two ring stages still fit (BN <= 128).  Measured on B200 (profiles/r01_layer_sweeps.txt)
   // it does not beat the direct 256-bit stores -- the layers it targets are bound by SM<->L2 traffic, not by the
   // LSU -- so it is off by default.
-  const bool want_stage = env_int("ACCEL_TC_TMA_OUT", 0) != 0 && splits == 1 && C.epi.out_hi != nullptr &&
+  const bool want_stage = !P.pair && env_int("ACCEL_TC_TMA_OUT", 0) != 0 && splits == 1 && C.epi.out_hi != nullptr &&
                           (kSmemBudget - kStageOut) / stage_bytes >= 2;
   int stages = (int)((kSmemBudget - (want_stage ? kStageOut : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -374,8 +642,13 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   const int tiles = tiles_m * P.n_tiles;
   P.splits = splits;
   plan->partial_bytes = splits > 1 ? (size_t)splits * C.Ho * C.Wo * C.Cout_pad * sizeof(float) : 0;
-  const int items = tiles * splits;
+  int items = tiles * splits;
   plan->grid = items < num_sms ? items : num_sms;
+  if (P.pair) {
+    items = ((tiles_m + 1) / 2) * P.n_tiles * splits;
+    const int ncl = items < num_sms / 2 ? items : num_sms / 2;
+    plan->grid = 2 * ncl;
+  }
   plan->launches = splits > 1 ? 2 : 1;
   {
     auto al32 = [](const void* p) { return ((uintptr_t)p & 31) == 0; };
@@ -409,7 +682,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   {
     cuuint64_t dims[2] = {(cuuint64_t)C.Kpad, (cuuint64_t)C.Cout_pad};
     cuuint64_t str[1] = {(cuuint64_t)C.Kpad * e};
-    cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {BK, (cuuint32_t)(P.pair ? bn / 2 : bn)};
     ok = ok && encode(&P.b_hi, C.w_hi, 2, dims, str, box, err, errlen);
     ok = ok && encode(&P.b_lo, C.w_lo, 2, dims, str, box, err, errlen);
   }
@@ -443,6 +716,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   static bool configured = false;
   if (!configured) {
     cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
       delete plan;
@@ -461,7 +735,8 @@ int tc_plan_launches(const TcPlan* plan) { return plan->launches; }
 cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, cudaStream_t stream) {
   TcParams P = plan->p;
   if (ext_nchw) P.epi.out_nchw = ext_nchw;
-  cudaError_t e = launch_k(conv_tc_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
+  cudaError_t e = P.pair ? launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, 2u, P)
+                         : launch_k(conv_tc_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
   if (e != cudaSuccess) return e;
   if (P.splits > 1) return launch_splitk_epilogue(P.partial, P.splits, P.Ho * P.Wo, P.Cout_pad, P.Wo, P.epi, stream);
   return cudaSuccess;

@@ -43,6 +43,16 @@ SWEEP = [
 ]
 
 
+PAIR_SWEEP = [
+    {},
+    {"ACCEL_TC_PAIR": "1"},
+    {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "256"},
+    {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "128"},
+    {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "256", "ACCEL_TC_SPLITS": "2"},
+    {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "256", "ACCEL_TC_SPLITS": "3"},
+    {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "128", "ACCEL_TC_SPLITS": "2"},
+]
+
 DEBUG_SWEEP = [
     {},
     {"ACCEL_TC_TMA_OUT": "0"},
@@ -76,8 +86,8 @@ def main():
         ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
         wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
         r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
-        for knobs in (DEBUG_SWEEP if a.sweep == "debug" else SWEEP):
-            for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT"):
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP}.get(a.sweep, SWEEP):
+            for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR"):
                 os.environ.pop(kk, None)
             os.environ.update(knobs)
             sys.stderr.write("%-14s %-44s " % (name, knobs))
