@@ -30,6 +30,11 @@ Graph::~Graph() {
       if (op.stem_tc) stem_tc_plan_destroy(op.stem_tc);
   for (auto& c : graph_cache_) cudaGraphExecDestroy(c.exec);
   if (capture_stream_) cudaStreamDestroy(capture_stream_);
+  for (int i = 0; i < kMaxBranches; ++i) {
+    if (side_[i]) cudaStreamDestroy(side_[i]);
+    if (join_ev_[i]) cudaEventDestroy(join_ev_[i]);
+  }
+  if (fork_ev_) cudaEventDestroy(fork_ev_);
   for (void* p : allocs_) cudaFree(p);
   for (auto e : events_) cudaEventDestroy(e);
 }
@@ -549,7 +554,8 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
   }
   if (eng == ENG_TC) {
     char msg[256] = {0};
-    op.tc = tc_plan_create(P, num_sms_, msg, sizeof(msg));
+    const int sm_budget = (op.par_group && op.par_width > 1 && branches_enabled()) ? std::max(8, num_sms_ / op.par_width) : num_sms_;
+    op.tc = tc_plan_create(P, sm_budget, msg, sizeof(msg));
     if (!op.tc) { *err = std::string("tcgen05 plan failed for ") + op.name + ": " + msg; return false; }
     const size_t pb = tc_plan_partial_bytes(op.tc);
     if (pb) {
@@ -813,7 +819,16 @@ bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t
   return true;
 }
 
-bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err) {
+bool Graph::branches_enabled() const {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACCEL_BRANCHES");
+    v = (e && *e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaStream_t main_stream, std::string* err) {
   auto it = seqs_.find(which);
   if (it == seqs_.end()) { *err = "no such graph: " + which; return false; }
   if (!finalized_ && !finalize(err)) return false;
@@ -828,10 +843,50 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
       cudaEventCreate(&e);
       events_.push_back(e);
     }
-    cudaEventRecord(events_[ev++], stream);
+    cudaEventRecord(events_[ev++], main_stream);
   }
   cudaError_t ce = cudaSuccess;
+  // fork / join of parallel sections (see Op::par_group).  Works the same on a real stream and under capture,
+  // where it turns the branches into parallel kernel nodes of the graph.
+  const bool use_branches = branches_enabled() && !profiling_;
+  int cur_group = 0;
+  unsigned used = 0;                                       // bit b: side stream b received work in this section
+  auto join_all = [&]() -> cudaError_t {
+    for (int b = 0; b < kMaxBranches; ++b)
+      if (used & (1u << b)) {
+        cudaError_t e = cudaEventRecord(join_ev_[b], side_[b]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, join_ev_[b], 0);
+        if (e != cudaSuccess) return e;
+      }
+    used = 0;
+    return cudaSuccess;
+  };
   for (auto& op : ops) {
+    cudaStream_t stream = main_stream;
+    if (use_branches) {
+      if (op.par_group != cur_group) {
+        if (cur_group && (ce = join_all()) != cudaSuccess) { *err = std::string("join failed: ") + cudaGetErrorString(ce); return false; }
+        cur_group = op.par_group;
+        if (cur_group) {
+          if (!fork_ev_) cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming);
+          ce = cudaEventRecord(fork_ev_, main_stream);
+          if (ce != cudaSuccess) { *err = std::string("fork failed: ") + cudaGetErrorString(ce); return false; }
+        }
+      }
+      if (cur_group && op.par_branch > 0 && op.par_branch <= kMaxBranches) {
+        const int b = op.par_branch - 1;
+        if (!side_[b]) {
+          cudaStreamCreateWithFlags(&side_[b], cudaStreamNonBlocking);
+          cudaEventCreateWithFlags(&join_ev_[b], cudaEventDisableTiming);
+        }
+        if (!(used & (1u << b))) {
+          ce = cudaStreamWaitEvent(side_[b], fork_ev_, 0);
+          if (ce != cudaSuccess) { *err = std::string("fork failed: ") + cudaGetErrorString(ce); return false; }
+          used |= 1u << b;
+        }
+        stream = side_[b];
+      }
+    }
     switch (op.type) {
       case OP_STEM: {
         StemParams S = op.stem;
@@ -934,6 +989,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
       event_op_.push_back(&op);
     }
   }
+  if (cur_group && (ce = join_all()) != cudaSuccess) { *err = std::string("join failed: ") + cudaGetErrorString(ce); return false; }
   last_launches_ = launches;
   return true;
 }

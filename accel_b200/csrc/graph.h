@@ -87,6 +87,10 @@ struct Op {
   StemTcPlan* stem_tc = nullptr;
   int partial_buf = -1;
   double flops = 0.0;
+  // Parallel section: ops that share `par_group` (> 0) are mutually independent across `par_branch` values and are
+  // issued on forked streams (parallel kernel nodes once captured); ops of one branch keep their order.
+  // `par_width` = number of branches that run tensor-core convs at once: the planner gives each 1/par_width of the SMs.
+  int par_group = 0, par_branch = 0, par_width = 1;
 };
 
 struct OpTime {
@@ -184,6 +188,14 @@ class Graph {
   std::vector<CachedGraph> graph_cache_;
   std::set<std::string> warmed_;
   cudaStream_t capture_stream_ = nullptr;
+  static constexpr int kMaxBranches = 5;
+  cudaStream_t side_[kMaxBranches] = {nullptr};
+  cudaEvent_t fork_ev_ = nullptr, join_ev_[kMaxBranches] = {nullptr};
+  int next_group_ = 0;
+ public:
+  int new_par_group() { return ++next_group_; }
+  bool branches_enabled() const;
+ private:
   unsigned long long graph_clock_ = 0;   // fp32 NCHW warped feature when the caller passes no feat_out
 
  public:

@@ -391,6 +391,9 @@ __global__ void __launch_bounds__(128) fuse_lowres_kernel(const FuseParams P) {
 // four horizontally adjacent pixels (they share the same source columns); labels leave as uchar4.
 // The fp32 score volume is written only when the caller asks for it (parity mode).
 // ------------------------------------------------------------------------------------------------
+// KC > 0: class count known at compile time (19 for Cityscapes): the class loop is fully unrolled, so the 4 x KC
+// low-resolution loads of a thread are all in flight before the first use.
+template <int KC>
 __global__ void __launch_bounds__(256) tail_kernel(const TailParams P) {
   pdl_trigger();
   pdl_wait();
@@ -416,7 +419,9 @@ __global__ void __launch_bounds__(256) tail_kernel(const TailParams P) {
   const size_t plane = (size_t)P.h * P.w, oplane = (size_t)OH * OW;
   float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   int arg[4] = {0, 0, 0, 0};
-  for (int c = 0; c < P.K; ++c) {
+  const int K = KC > 0 ? KC : P.K;
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
     const float* s = P.score + c * plane;
     const float s00 = s[r0 * P.w + q0], s01 = s[r0 * P.w + q1], s10 = s[r1 * P.w + q0], s11 = s[r1 * P.w + q1];
     const float b = P.bias ? P.bias[c] : 0.f;
@@ -525,7 +530,8 @@ cudaError_t launch_fuse_lowres(const FuseParams& P, cudaStream_t stream) {
 
 cudaError_t launch_tail(const TailParams& P, cudaStream_t stream) {
   const int work = (P.w * P.factor / 4) * (P.h * P.factor);
-  return launch_k(tail_kernel, dim3((work + 255) / 256), dim3(256), 0, stream, P);
+  if (P.K == 19) return launch_k(tail_kernel<19>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
+  return launch_k(tail_kernel<0>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
 }
 
 }  // namespace accel

@@ -59,9 +59,23 @@ int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out) {
     EpiSpec fe = bias_epi(flow_name, ACT_NONE);
     fe.out_f32 = f;
     fe.no_split_out = true;
+    // One refinement level = five independent chains over the same input: the 2-channel flow head followed by its
+    // x2 upsampling, and the four output phases of the feature deconvolution.  They write disjoint channel ranges
+    // of the next concat buffer, so they run as parallel branches (forked streams -> parallel graph nodes), each
+    // deconv phase planned for a quarter of the SMs.
+    const int grp = g.new_par_group();
+    const size_t i0 = s.size();
     g.conv(s, st, feat, flow_name, 2, 3, 1, 1, 1, fe);
+    const size_t i1 = s.size();
     g.deconv4(s, st, feat, deconv_name, deconv_c, bias_epi(deconv_name, ACT_LEAKY), g.new_view(cat, skip_c, deconv_c));
+    const size_t i2 = s.size();
     g.upflow(s, f, up_name, std::string(up_name) + "_bias", g.new_view(cat, skip_c + deconv_c, 2));
+    for (size_t i = i0; i < s.size(); ++i) {
+      s[i].par_group = grp;
+      s[i].par_width = 4;
+      if (i >= i1 && i < i2) s[i].par_branch = 1 + s[i].phase_y * 2 + s[i].phase_x;     // branches 1..4: deconv phases
+      else s[i].par_branch = (i < i1) ? 5 : 5;                                          // branch 5: flow head -> upflow
+    }
   };
   refine(r10, c2, 512, 512, "Convolution1", "deconv5", "upsample_flow6to5");
   refine(c2, c3, 512, 256, "Convolution2", "deconv4", "upsample_flow5to4");

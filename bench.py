@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--multi-stream", type=int, default=0,
+                    help="also time S independent video streams interleaved on each GPU (S engines on S CUDA streams); "
+                         "reported as an extra `multi_stream` object, the headline stays one stream per GPU")
     return ap.parse_args()
 
 
@@ -311,6 +314,42 @@ def run_native(a):
         barrier()
         e2e32_ms = e0.elapsed_time(e1)
 
+    # optional: S independent streams per GPU, each with its own handle and CUDA stream (fills the SMs that one
+    # stream's small layers leave idle).  Extra information; `value` stays one stream per GPU.
+    multi = None
+    if a.multi_stream > 1:
+        S = a.multi_stream
+        engines = [eng] + [Engine(a.version, H, W, params=synthetic.make_params(a.version), device=local, flags=a.flags)
+                           for _ in range(S - 1)]
+        cstreams = [torch.cuda.Stream(dev) for _ in range(S)]
+        states = [scheduler.StreamState(e) for e in engines]
+        labels = [torch.empty(H, W, dtype=torch.uint8, device=dev) for _ in range(S)]
+
+        def ms_step(s):
+            for i in range(I):
+                for k in range(S):
+                    with torch.cuda.stream(cstreams[k]):
+                        scheduler.segment_frame(engines[k], states[k], frames[(s * I + i + k) % n_frames], I, a.schedule, labels[k])
+
+        for s in range(max(a.warmup, 3)):
+            ms_step(s)
+        barrier()
+        for st in states:
+            st.index = 0
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for c in cstreams:
+            c.wait_event(m0)
+        for s in range(a.steps):
+            ms_step(s)
+        for c in cstreams:
+            torch.cuda.current_stream().wait_stream(c)
+        m1.record()
+        barrier()
+        multi = {"streams_per_gpu": S, "ms_per_step": m0.elapsed_time(m1) / a.steps,
+                 "value": S * I * a.steps / (m0.elapsed_time(m1) / 1000.0) * world, "unit": "frames/s",
+                 "note": "S independent video streams interleaved per GPU (own handle + CUDA stream each); not the headline"}
+
     # ---- reduce: max time over ranks, total frames --------------------------------------------------
     rows = multigpu.gather_rows([a.steps * I, ms, e2e_ms or 0.0, e2e32_ms or 0.0], dev)   # the single metric collective
     fps, ms_max = multigpu.aggregate_throughput(rows[:, 0].tolist(), rows[:, 1].tolist())
@@ -331,10 +370,15 @@ def run_native(a):
             wb = 2048 * (H // 16) * (W // 16) * 4 + 2 * (H // 16) * (W // 16) * 4
         warp_avg_ms = sum(warp_evs) / len(warp_evs) if warp_evs else None
         roofline = None
+        traffic = None
+        try:                                            # dram__bytes_read+write per launch from the committed ncu capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "warp_traffic.json")))["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         if warp_avg_ms:
             ach = wb / (warp_avg_ms * 1e-3) / 1e9
             roofline = {"kernel": "warp_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                        "frac": ach / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                         "algorithmic_bytes_per_launch": wb, "avg_launch_ms": warp_avg_ms,
                         "frac_of_8TBps_nominal": ach / 8000.0}
         scale = (H * W) / float(1024 * 2048)
@@ -363,6 +407,8 @@ def run_native(a):
                                 "h2d_bytes_per_step": I * 3 * H * W * 4, "d2h_bytes_per_step": I * H * W,
                                 "note": "same loop fed the reference's upload format (pinned fp32 NCHW `data`), single stream"}
             line["gpu_launches_e2e_per_step"] = launches_per_step + I
+        if multi is not None:
+            line["multi_stream"] = multi
         if world == 1 and not a.no_cpu_baseline:
             budget = 25.0
             v, d = cpu_oracle_fps(a, steps=2 * I, warmup=0, budget_s=budget)
