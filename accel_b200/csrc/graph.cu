@@ -35,6 +35,9 @@ Graph::~Graph() {
     if (join_ev_[i]) cudaEventDestroy(join_ev_[i]);
   }
   if (fork_ev_) cudaEventDestroy(fork_ev_);
+  if (lane_stream_) cudaStreamDestroy(lane_stream_);
+  if (lane_fork_ev_) cudaEventDestroy(lane_fork_ev_);
+  if (lane_join_ev_) cudaEventDestroy(lane_join_ev_);
   for (void* p : allocs_) cudaFree(p);
   for (auto e : events_) cudaEventDestroy(e);
 }
@@ -861,9 +864,33 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
     used = 0;
     return cudaSuccess;
   };
+  bool lane_open = false;
+  if (use_branches) {
+    for (auto& op : ops) lane_open = lane_open || op.lane == 1;
+    if (lane_open) {
+      if (!lane_stream_) {
+        cudaStreamCreateWithFlags(&lane_stream_, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&lane_fork_ev_, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&lane_join_ev_, cudaEventDisableTiming);
+      }
+      ce = cudaEventRecord(lane_fork_ev_, main_stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(lane_stream_, lane_fork_ev_, 0);
+      if (ce != cudaSuccess) { *err = std::string("lane fork failed: ") + cudaGetErrorString(ce); return false; }
+    }
+  }
+  auto join_lane = [&]() -> cudaError_t {
+    if (!lane_open) return cudaSuccess;
+    lane_open = false;
+    cudaError_t e = cudaEventRecord(lane_join_ev_, lane_stream_);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, lane_join_ev_, 0);
+    return e;
+  };
   for (auto& op : ops) {
     cudaStream_t stream = main_stream;
-    if (use_branches) {
+    if (use_branches && op.lane == 1 && lane_open) {
+      stream = lane_stream_;
+    } else if (use_branches) {
+      if (op.join_lane && (ce = join_lane()) != cudaSuccess) { *err = std::string("lane join failed: ") + cudaGetErrorString(ce); return false; }
       if (op.par_group != cur_group) {
         if (cur_group && (ce = join_all()) != cudaSuccess) { *err = std::string("join failed: ") + cudaGetErrorString(ce); return false; }
         cur_group = op.par_group;
@@ -990,6 +1017,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
     }
   }
   if (cur_group && (ce = join_all()) != cudaSuccess) { *err = std::string("join failed: ") + cudaGetErrorString(ce); return false; }
+  if ((ce = join_lane()) != cudaSuccess) { *err = std::string("lane join failed: ") + cudaGetErrorString(ce); return false; }
   last_launches_ = launches;
   return true;
 }

@@ -91,6 +91,9 @@ struct Op {
   // issued on forked streams (parallel kernel nodes once captured); ops of one branch keep their order.
   // `par_width` = number of branches that run tensor-core convs at once: the planner gives each 1/par_width of the SMs.
   int par_group = 0, par_branch = 0, par_width = 1;
+  // Lane 1 = a long chain independent of lane 0 (the correction branch next to FlowNet + warp + L head): issued on its
+  // own stream from the start of the plan; the first op with `join_lane` waits for it.
+  int lane = 0, join_lane = 0;
 };
 
 struct OpTime {
@@ -191,6 +194,8 @@ class Graph {
   static constexpr int kMaxBranches = 5;
   cudaStream_t side_[kMaxBranches] = {nullptr};
   cudaEvent_t fork_ev_ = nullptr, join_ev_[kMaxBranches] = {nullptr};
+  cudaStream_t lane_stream_ = nullptr;
+  cudaEvent_t lane_fork_ev_ = nullptr, lane_join_ev_ = nullptr;
   int next_group_ = 0;
  public:
   int new_par_group() { return ++next_group_; }

@@ -264,8 +264,13 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
     if (version == 101) {
       const int cat = g.new_tensor(4096, h, w);
       g.warp(s, X_FEAT_KEY, flow, g.new_view(cat, 0, 2048), X_FEAT_OUT);
+      // the correction net only reads the current frame: it runs as its own lane next to FlowNet + warp
+      const size_t r0 = s.size();
       bottleneck_net(g, s, "rbranch", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_NONE, g.new_view(cat, 2048, 2048));
+      for (size_t i = r0; i < s.size(); ++i) s[i].lane = 1;
+      const size_t j0 = s.size();
       int fused = g.conv(s, "fusion", cat, "corr", 2048, 1, 1, 0, 1, bias_epi("corr", ACT_NONE));
+      s[j0].join_lane = 1;
       int sc = head(g, s, "head", fused, "fc6", "score", "upsampling", K);
       g.tail(s, sc, "", X_LABEL_OUT, X_SCORE_OUT);
     } else {
@@ -276,6 +281,7 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
         g.tail(s, sl, "", X_LABEL_OUT, X_SCORE_OUT);
       } else {
         int sr;
+        const size_t r0 = s.size();                       // R branch + R head: a lane of its own (reads only `data`)
         if (version == 50) {
           int f = bottleneck_net(g, s, "rbranch", H, W, "50_", units_50(), DeformCfg{72, 2, 2, 4}, X_NONE, -1);
           sr = head(g, s, "rhead", f, "curr_fc6", "curr_score", "curr_upsampling", K);
@@ -286,8 +292,11 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
                                 version == 18 ? "ab" : "abc");
           sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K);
         }
+        for (size_t i = r0; i < s.size(); ++i) s[i].lane = 1;
         const int fused = g.new_tensor(K, h, w, true);
+        const size_t j0 = s.size();
         g.fuse(s, sl, sr, "corr", fused);
+        s[j0].join_lane = 1;
         g.tail(s, fused, "corr_bias", X_LABEL_OUT, X_SCORE_OUT);
       }
     }
