@@ -79,7 +79,8 @@ def run_reference_loop(key_predictor, cur_predictor, frames, interval, version, 
 
 
 class StreamState:
-    """Per-video state the schedule carries between frames: {feat, data_key}."""
+    """Per-video state the schedule carries between frames: {feat, data_key}, plus the
+    buffers of the optional key-frame lookahead (see segment_frame)."""
 
     def __init__(self, engine):
         dev = engine.torch_device
@@ -88,21 +89,70 @@ class StreamState:
         self.key_frame = None
         self.prev_frame = None
         self.index = 0
+        self.feat_in = self.feat[0]          # the feature the next cur frame reads
+        # lookahead (allocated on first use)
+        self.key_stream = None
+        self.key_feat = None                 # two key-feature buffers, alternating per interval
+        self.key_label = None
+        self.key_slot = 0
+        self.pending = None                  # {"data": tensor, "slot": int, "event": cuda event}
 
 
-def segment_frame(engine, state, data, interval, schedule, label_out, score_out=None):
-    """Production step (no score volume unless asked): one frame of one stream through the
-    key/cur plans with double-buffered features.  Returns True when it was a key frame."""
+def _launch_lookahead(engine, state, next_key_data):
+    """Starts the key plan of the NEXT interval's key frame on the state's key stream, after everything issued so
+    far on the current stream (so the buffers it overwrites are no longer read)."""
+    dev = engine.torch_device
+    if state.key_stream is None:
+        state.key_stream = torch.cuda.Stream(dev)
+        state.key_feat = [torch.empty(engine.feat_shape, device=dev) for _ in range(2)]
+        state.key_label = [torch.empty(engine.height, engine.width, dtype=torch.uint8, device=dev) for _ in range(2)]
+    slot = state.key_slot
+    state.key_slot ^= 1
+    main = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(main)
+    state.key_stream.wait_event(ready)
+    with torch.cuda.stream(state.key_stream):
+        engine.key_forward(next_key_data, state.key_feat[slot], None, state.key_label[slot])
+        done = torch.cuda.Event()
+        done.record(state.key_stream)
+    state.pending = {"data": next_key_data, "slot": slot, "event": done}
+
+
+def segment_frame(engine, state, data, interval, schedule, label_out, score_out=None, next_key_data=None):
+    """Production step (no score volume unless asked): one frame of one stream through the key/cur plans with
+    double-buffered features.  Returns True when it was a key frame.
+
+    Key-frame lookahead: a key frame depends on no earlier frame, so when the caller already holds the NEXT
+    interval's key frame (a video file, a decode queue) it passes it as `next_key_data` with the current key
+    frame; its key plan then runs on a second CUDA stream underneath this interval's cur frames (which are many
+    small kernels) and is merely waited for when its turn comes.  Same plans, same inputs, same outputs as the
+    sequential loop of demo.py:228-250 -- only the issue order on the GPU changes."""
     is_key = state.index % interval == 0
+    dev = engine.torch_device
     if is_key:
-        engine.key_forward(data, state.feat[state.cur], score_out, label_out)
+        p = state.pending
+        if p is not None and p["data"] is data and score_out is None:
+            main = torch.cuda.current_stream(dev)
+            main.wait_event(p["event"])
+            label_out.copy_(state.key_label[p["slot"]], non_blocking=True)
+            state.feat_in = state.key_feat[p["slot"]]
+        else:
+            if p is not None:                                   # a stale lookahead: let it drain before reusing buffers
+                torch.cuda.current_stream(dev).wait_event(p["event"])
+            engine.key_forward(data, state.feat[state.cur], score_out, label_out)
+            state.feat_in = state.feat[state.cur]
+        state.pending = None
         state.key_frame = data
+        if next_key_data is not None:
+            _launch_lookahead(engine, state, next_key_data)
     elif schedule == "chained":
         nxt = state.cur ^ 1
-        engine.cur_forward(data, state.prev_frame, state.feat[state.cur], state.feat[nxt], score_out, label_out)
+        engine.cur_forward(data, state.prev_frame, state.feat_in, state.feat[nxt], score_out, label_out)
         state.cur = nxt
+        state.feat_in = state.feat[nxt]
     else:
-        engine.cur_forward(data, state.key_frame, state.feat[state.cur], None, score_out, label_out)
+        engine.cur_forward(data, state.key_frame, state.feat_in, None, score_out, label_out)
     state.prev_frame = data
     state.index += 1
     return is_key
@@ -118,7 +168,7 @@ class VideoPipeline:
     i+1 / labels of frame i-1 overlap the graphs of frame i; nothing else crosses PCIe.  Optionally the
     confusion matrix against ground-truth label maps is accumulated on the device (demo.py:270-272)."""
 
-    def __init__(self, engine, interval, schedule="chained", pixel_means_bgr=None, depth=2):
+    def __init__(self, engine, interval, schedule="chained", pixel_means_bgr=None, depth=2, lookahead=True):
         if schedule not in SCHEDULES:
             raise ValueError("schedule must be one of %s" % (SCHEDULES,))
         if interval < 1:
@@ -126,26 +176,33 @@ class VideoPipeline:
         from . import engine as _E
         self._E = _E
         self.engine, self.interval, self.schedule, self.means = engine, int(interval), schedule, pixel_means_bgr
+        self.lookahead = bool(lookahead)
         dev = engine.torch_device
         H, W = engine.height, engine.width
         self.dev, self.depth = dev, int(depth)
         self.state = StreamState(engine)
-        self.u8 = [torch.empty(H, W, 3, dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.nu8 = depth + 1                                                      # a key turn uploads two frames
+        self.u8 = [torch.empty(H, W, 3, dtype=torch.uint8, device=dev) for _ in range(self.nu8)]
         self.f32 = [torch.empty(1, 3, H, W, device=dev) for _ in range(3)]       # cur / prev / key never collide
+        self.keybuf = [torch.empty(1, 3, H, W, device=dev) for _ in range(2)] if self.lookahead else []
         self.label = [torch.empty(H, W, dtype=torch.uint8, device=dev) for _ in range(depth)]
         self.copy_in = torch.cuda.Stream(dev)
         self.copy_out = torch.cuda.Stream(dev)
-        self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # frame landed in u8[b]
-        self.ev_free = [torch.cuda.Event() for _ in range(depth)]     # u8[b] consumed by preprocess
+        self.ev_in = [torch.cuda.Event() for _ in range(self.nu8)]    # frame landed in u8[b]
+        self.ev_free = [torch.cuda.Event() for _ in range(self.nu8)]  # u8[b] consumed by preprocess
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]     # label[b] written by the graph
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]      # label[b] copied to the host
-        self.n = 0
+        self.n = 0                                                    # frames submitted (label ring position)
+        self.nu = 0                                                   # uploads issued (u8 ring position)
+        self.kslot = 0
+        self.pre_key = None                                           # {"host": pinned frame, "data": fp32 tensor}
         self.hist = torch.zeros(engine.num_classes, engine.num_classes, dtype=torch.int64, device=dev)
 
     def reset(self):
         """Start of a new video: the next frame is a key frame."""
         self.state.index = 0
         self.state.key_frame = self.state.prev_frame = None
+        self.pre_key = None
 
     def _pick_f32(self):
         busy = {t.data_ptr() for t in (self.state.prev_frame, self.state.key_frame) if t is not None}
@@ -154,24 +211,44 @@ class VideoPipeline:
                 return t
         raise RuntimeError("no free frame buffer")
 
-    def submit(self, frame_u8_host, label_host, gt_label=None):
-        """Queues one frame.  frame_u8_host: pinned (H,W,3) uint8 BGR; label_host: pinned (H,W) uint8, valid
-        after `sync()` (or once the returned event has completed); gt_label: optional CUDA uint8 (H,W)
-        ground truth to accumulate `hist` against.  Returns (is_key, event)."""
-        b = self.n % self.depth
+    def _upload(self, frame_u8_host, into):
+        """H2D of one uint8 frame on the copy stream + accel_preprocess on the current stream -> `into`."""
+        b = self.nu % self.nu8
         main = torch.cuda.current_stream(self.dev)
-        if self.n >= self.depth:
+        if self.nu >= self.nu8:
             self.copy_in.wait_event(self.ev_free[b])
         with torch.cuda.stream(self.copy_in):
             self.u8[b].copy_(frame_u8_host, non_blocking=True)
             self.ev_in[b].record(self.copy_in)
         main.wait_event(self.ev_in[b])
-        data = self._pick_f32()
-        self._E.preprocess(self.u8[b], data, self.means)
+        self._E.preprocess(self.u8[b], into, self.means)
         self.ev_free[b].record(main)
+        self.nu += 1
+        return into
+
+    def submit(self, frame_u8_host, label_host, gt_label=None, next_key_host=None):
+        """Queues one frame.  frame_u8_host: pinned (H,W,3) uint8 BGR; label_host: pinned (H,W) uint8, valid
+        after `sync()` (or once the returned event has completed); gt_label: optional CUDA uint8 (H,W)
+        ground truth to accumulate `hist` against; next_key_host: with a key frame, the NEXT interval's key
+        frame if the caller already has it (enables the key-frame lookahead of segment_frame).
+        Returns (is_key, event)."""
+        b = self.n % self.depth
+        main = torch.cuda.current_stream(self.dev)
+        key_turn = self.state.index % self.interval == 0
+        if key_turn and self.pre_key is not None and self.pre_key["host"] is frame_u8_host:
+            data = self.pre_key["data"]                                      # uploaded + preprocessed an interval ago
+        else:
+            data = self._upload(frame_u8_host, self._pick_f32())
+        self.pre_key = None if key_turn else self.pre_key
+        nk = None
+        if key_turn and self.lookahead and next_key_host is not None:
+            nk = self._upload(next_key_host, self.keybuf[self.kslot])
+            self.kslot ^= 1
+            self.pre_key = {"host": next_key_host, "data": nk}
         if self.n >= self.depth:
             main.wait_event(self.ev_out[b])                                  # label[b] has left for the host
-        is_key = segment_frame(self.engine, self.state, data, self.interval, self.schedule, self.label[b])
+        is_key = segment_frame(self.engine, self.state, data, self.interval, self.schedule, self.label[b],
+                               next_key_data=nk)
         if gt_label is not None:
             self._E.confusion(self.label[b], gt_label, self.hist, self.engine.num_classes)
         self.ev_done[b].record(main)
@@ -185,15 +262,19 @@ class VideoPipeline:
     def sync(self):
         self.copy_out.synchronize()
         torch.cuda.current_stream(self.dev).synchronize()
+        if self.state.key_stream is not None:
+            self.state.key_stream.synchronize()
 
     def segment_video(self, frames_u8_host, labels_host=None, gt_labels=None):
         """Whole clip: list of pinned uint8 frames -> list of pinned uint8 label maps (synchronised)."""
         self.reset()
         H, W = self.engine.height, self.engine.width
+        T, I = len(frames_u8_host), self.interval
         if labels_host is None:
             labels_host = [torch.empty(H, W, dtype=torch.uint8).pin_memory() for _ in frames_u8_host]
         for i, f in enumerate(frames_u8_host):
-            self.submit(f, labels_host[i], None if gt_labels is None else gt_labels[i])
+            nxt = frames_u8_host[i + I] if (self.lookahead and i % I == 0 and i + I < T) else None
+            self.submit(f, labels_host[i], None if gt_labels is None else gt_labels[i], next_key_host=nxt)
         self.sync()
         return labels_host
 

@@ -60,6 +60,6 @@ def test_cuda_path_matches_golden(version):
         if i % interval:
             flow = eng.flownet(f, frames[i - 1])[0].cpu().numpy()
         scheduler.segment_frame(eng, state, f, interval, "chained", label, score)
-        feat = state.feat[state.cur]
+        feat = state.feat_in
         _check_frame(g, i, sub, label.cpu().numpy(), score.cpu().numpy(), feat.cpu().numpy(), SCORE_TOL, flow)
     eng.close()

@@ -99,3 +99,29 @@ def test_video_pipeline_equals_plain_loop(schedule):
     assert np.array_equal(labels2[0].numpy(), labels[0].numpy())
     assert np.array_equal(labels2[1].numpy(), labels[1].numpy())
     eng.close()
+
+
+@pytest.mark.parametrize("schedule", ["chained", "unchained"])
+@pytest.mark.parametrize("interval", [1, 2, 4])
+def test_key_lookahead_equals_sequential_loop(schedule, interval):
+    """segment_frame with the next key frame handed in advance (key plan on a second stream) produces the same
+    label maps and features as the strictly sequential loop."""
+    from accel_b200.engine import Engine
+    H, W, T = 128, 256, 9
+    eng = Engine("dff", H, W, params=synthetic.make_params("dff"))
+    dev = eng.torch_device
+    frames = [f.to(dev) for f in synthetic.make_frames(T, H, W, stream=6)]
+    lab = torch.empty(H, W, dtype=torch.uint8, device=dev)
+    ref_labels, ref_feats = [], []
+    st = scheduler.StreamState(eng)
+    for f in frames:
+        scheduler.segment_frame(eng, st, f, interval, schedule, lab)
+        ref_labels.append(lab.cpu().numpy().copy())
+        ref_feats.append(st.feat_in.cpu().numpy().copy())
+    st = scheduler.StreamState(eng)
+    for i, f in enumerate(frames):
+        nk = frames[i + interval] if (i % interval == 0 and i + interval < T) else None
+        scheduler.segment_frame(eng, st, f, interval, schedule, lab, next_key_data=nk)
+        assert np.array_equal(lab.cpu().numpy(), ref_labels[i]), "frame %d" % i
+        assert np.array_equal(st.feat_in.cpu().numpy(), ref_feats[i]), "frame %d" % i
+    eng.close()
