@@ -182,6 +182,7 @@ def run_native(a):
         raise SystemExit("bench.py: no CUDA device -- the native arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
     multigpu.init("nccl", dev)
 
     H, W, I = a.height, a.width, a.interval
@@ -293,16 +294,23 @@ def run_native(a):
     e2e_ms = e2e32_ms = None
     if not a.no_e2e:
         host_u8 = [f.contiguous().pin_memory() for f in frames_u8]
-        labels_host = [torch.empty(H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        n_lab = 4
+        labels_host = [torch.empty(H, W, dtype=torch.uint8).pin_memory() for _ in range(n_lab)]
+        lab_ev = [None] * n_lab
         pipe = scheduler.VideoPipeline(eng, I, a.schedule, lookahead=look)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def e2e_step(s, last=False):
+            # the consumer takes label map k (its copy event has completed) before host buffer k % 4 is reused:
+            # at most 4 frames are in flight, every label map reaches the host inside the timed region
             for i in range(I):
                 k = s * I + i
+                if lab_ev[k % n_lab] is not None:
+                    lab_ev[k % n_lab].synchronize()
                 nk = host_u8[(k + I) % n_frames] if (look and i == 0 and not last) else None
-                pipe.submit(host_u8[k % n_frames], labels_host[k & 1], next_key_host=nk)
-            pipe.sync()                                                        # the caller holds the label maps
+                _, lab_ev[k % n_lab] = pipe.submit(host_u8[k % n_frames], labels_host[k % n_lab], next_key_host=nk)
+            if last:
+                pipe.sync()
 
         pipe.reset()
         n_prime = max(a.warmup, 8)                     # the pipeline's buffer rings repeat after a few intervals
