@@ -161,6 +161,19 @@ def test_deformable_layer_matches_oracle(dg, engine):
     assert (out - ref).abs().max().item() < _tol(ref)
 
 
+@pytest.mark.parametrize("dg,cin,h,w,scale", [(1, 512, 64, 128, 1.0), (4, 512, 32, 64, 1.5), (4, 128, 19, 45, 6.0), (1, 64, 8, 16, 0.0)])
+def test_deformable_layer_staged_shapes(dg, cin, h, w, scale):
+    """Shapes of the real res5 layers (TMA-staged im2col: tile + halo in shared memory), a map that is not a
+    multiple of the 8x16 tile with offsets large enough to leave the staged halo, and zero offsets."""
+    cout = 64
+    x = _rand(1, cin, h, w, seed=33)
+    wt = _rand(cout, cin, 3, 3, seed=34, scale=(2.0 / (cin * 9)) ** 0.5)
+    off = _rand(1, dg * 18, h, w, seed=35, scale=scale)
+    ref = ops.deformable_convolution(x, off, wt, 1, 2, 2, dg)
+    out = E.conv_layer(x.to(DEV), wt, "deform", 1, 2, 2, offset=off.to(DEV), deform_groups=dg, engine=2).cpu()
+    assert (out - ref).abs().max().item() < _tol(ref)
+
+
 # ----------------------------------------------------------------------------- 7x7/s2 stems (a1, a4, a8, a9)
 @pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("h,w", [(64, 128), (128, 256), (72, 200)])
