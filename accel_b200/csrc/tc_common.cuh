@@ -136,14 +136,7 @@ __device__ __forceinline__ void stage_row64(uint32_t tile, int r, const uint32_t
 // 32 activated fp32 values -> packed hi / lo fp16 pairs (16 words each)
 __device__ __forceinline__ void split32_words(const float v[32], uint32_t hi[16], uint32_t lo[16]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    __half h0, l0, h1, l1;
-    split_f32(v[2 * i], h0, l0);
-    split_f32(v[2 * i + 1], h1, l1);
-    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-    hi[i] = *reinterpret_cast<uint32_t*>(&hh);
-    lo[i] = *reinterpret_cast<uint32_t*>(&ll);
-  }
+  for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
 }
 
 // ---- 256-bit global accesses (one full 32-byte sector per thread) ----------------------------------
@@ -189,14 +182,7 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 __device__ __forceinline__ void store_split32(__half* hi, __half* lo, const float v[32]) {
   U8 a[2], b[2];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    __half h0, l0, h1, l1;
-    split_f32(v[2 * i], h0, l0);
-    split_f32(v[2 * i + 1], h1, l1);
-    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-    a[i >> 3].v[i & 7] = *reinterpret_cast<uint32_t*>(&hh);
-    b[i >> 3].v[i & 7] = *reinterpret_cast<uint32_t*>(&ll);
-  }
+  for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], a[i >> 3].v[i & 7], b[i >> 3].v[i & 7]);
   st256(hi, a[0]);
   st256(hi + 16, a[1]);
   st256(lo, b[0]);
