@@ -44,6 +44,7 @@ constexpr int kSmemBudget = kSmemMaxDynamic - 1024;      // minus the 1024-byte 
 struct alignas(64) TcParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   CUtensorMap o_hi, o_lo;      // main split output, box = 32 channels x the tile's pixel box (TMA store), when tma_out
+  CUtensorMap r_hi, r_lo;      // residual, same box (TMA load into the same staging tile), when tma_out and a residual exists
   Epilogue epi;
   float* partial;
   int BW, BH, BN, stages;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float epi_sc[2][2][256];          // [accumulator][scale | shift][channel of the tile]
+  __shared__ __align__(8) uint64_t res_bars[4];              // TMA epilogue: residual landed in staging buffer [chunk set][buffer]
 
   // operand ring: [stage][A_hi | A_lo | B_hi | B_lo]
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, kEpiWarps);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&res_bars[a]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -172,6 +175,102 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else {
+    if (P.tma_out && P.splits == 1) {
+      // ===================================== epilogue, TMA both ways ===========================
+      // The lane-per-pixel global accesses of the direct epilogue are 32 separate lines per warp instruction and
+      // saturate the L1TEX pipe (profiles/r01_ncu_dcn_col.txt shows the same pattern).  Here global memory is only
+      // touched by the TMA unit: per chunk set (4 warps = the tile's 128 pixel rows) and 32-channel chunk, the
+      // residual tile lands in a SWIZZLE_64B staging buffer (hi | lo, 16 KB) one chunk ahead, every thread folds
+      // its own 64+64 bytes into its accumulator row and writes the result back IN PLACE, and the leader hands
+      // the buffer to two tensor stores.  Two buffers per chunk set; one named barrier per chunk.
+      const int quarter = warp & 3, cset = (warp - 2) >> 2;
+      const int r = quarter * 32 + lane;
+      const int by = r / P.BW, bx = r - by * P.BW;
+      const int et = threadIdx.x - 64;
+      const Epilogue& E = P.epi;
+      const bool has_res = E.res_hi != nullptr;
+      const bool leader = quarter == 0 && lane == 0;
+      const uint32_t sb0 = stg0 + (uint32_t)cset * 2u * 16384u;
+      const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]);
+      auto issue_res = [&](int item2, int cc2, int b2) {     // leader: residual of chunk (item2, cc2) -> buffer b2
+        const int tile2 = item2 / P.splits, nt2 = tile2 % P.n_tiles, mt2 = tile2 / P.n_tiles;
+        const int x02 = (mt2 % P.tiles_x) * P.BW, y02 = (mt2 / P.tiles_x) * P.BH;
+        const uint32_t dst = sb0 + (uint32_t)b2 * 16384u, bar = rbar0 + 8u * b2;
+        mbar_arrive_expect_tx(bar, 16384u);
+        tma_load_3d(dst, &P.r_hi, bar, nt2 * P.BN + cc2, x02, y02);
+        tma_load_3d(dst + 8192u, &P.r_lo, bar, nt2 * P.BN + cc2, x02, y02);
+      };
+      int acc = 0, n = 0;
+      uint32_t accph = 0;
+      if (leader && has_res && (int)blockIdx.x < items) issue_res(blockIdx.x, cset * 32, 0);
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int tile = item / P.splits;
+        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
+        const int x = x0 + bx, y = y0 + by;
+        const bool valid = x < P.Wo && y < P.Ho;
+        const int pix = (y * E.osy + E.ooy) * E.OWf + x * E.osx + E.oox;
+        const int nbase = nt * P.BN;
+        if (et < P.BN) {
+          const int c = nbase + et;
+          const bool in = c < E.Cout;
+          epi_sc[acc][0][et] = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
+          epi_sc[acc][1][et] = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(tfull0 + 8 * acc, accph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN);
+        for (int cc = cset * 32; cc < P.BN; cc += 64, ++n) {
+          const int b = n & 1;
+          const uint32_t sb = sb0 + (uint32_t)b * 16384u;
+          if (leader) {
+            bulk_wait_read0();                               // the stores that read buffer b^1 (chunk n-1) are done with it
+            if (has_res) {
+              if (cc + 64 < P.BN) issue_res(item, cc + 64, b ^ 1);
+              else if (item + (int)gridDim.x < items) issue_res(item + gridDim.x, cset * 32, b ^ 1);
+            }
+          }
+          float v[32];
+          tmem_ld32(taddr + cc, v);
+          ResChunk rc{};
+          if (has_res) {
+            mbar_wait(rbar0 + 8u * b, (uint32_t)((n >> 1) & 1));
+            const uint32_t row = sb + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = row + (((uint32_t)j ^ sw) << 4);
+              uint32_t* dh = &rc.h[j >> 1].v[(j & 1) * 4];
+              uint32_t* dl = &rc.l[j >> 1].v[(j & 1) * 4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dh[0]), "=r"(dh[1]), "=r"(dh[2]), "=r"(dh[3]) : "r"(a));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dl[0]), "=r"(dl[1]), "=r"(dl[2]), "=r"(dl[3]) : "r"(a + 8192u));
+            }
+          }
+          if (valid) epilogue_chunk32(E, pix, nbase + cc, v, rc, &epi_sc[acc][0][cc], &epi_sc[acc][1][cc], false);
+          uint32_t wh[16], wl[16];
+          split32_words(v, wh, wl);
+          stage_row64(sb, r, wh);
+          stage_row64(sb + 8192u, r, wl);
+          fence_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + cset) : "memory");
+          if (leader) {
+            if (P.tma_out == 2) {
+              tma_store_5d(&P.o_hi, sb, nbase + cc, E.oox, x0, E.ooy, y0);
+              tma_store_5d(&P.o_lo, sb + 8192u, nbase + cc, E.oox, x0, E.ooy, y0);
+            } else {
+              tma_store_3d(&P.o_hi, sb, nbase + cc, x0, y0);
+              tma_store_3d(&P.o_lo, sb + 8192u, nbase + cc, x0, y0);
+            }
+            bulk_commit();
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
+      if (leader) bulk_wait0();
+    } else {
     // ===================================== epilogue ==========================================
     // Lane = pixel (TMEM lane), 32 consecutive output channels per chunk: 64 contiguous bytes per
     // plane per thread, moved as 256-bit accesses.  Everything the chunk loop would otherwise wait
@@ -185,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int npix = P.Ho * P.Wo;
     const int et = threadIdx.x - 64;                       // 0 .. 255 among the epilogue threads
     const Epilogue& E = P.epi;
-    int acc = 0, sbuf = 0;
+    int acc = 0;
     uint32_t accph = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = item % P.splits, tile = item / P.splits;
@@ -223,36 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         ResChunk rn{};
         const int nn = n0 + 128;
         if (use_res && valid && cc + 128 < P.BN && nn + 32 <= E.Cout) load_res(E, pix, nn, rn);
-        if (P.tma_out && P.splits == 1) {
-          // Main output through shared memory: the chunk set's 4 warps stage 128 pixel rows x 32 channels of both
-          // planes (SWIZZLE_64B) and one thread hands the two tiles to the TMA unit -- full-line writes that bypass
-          // the LSU (a lane-per-pixel store is 32 separate 32-byte requests).  Two staging buffers per chunk set:
-          // the stores of chunk i drain while chunk i+1 is converted.  Out-of-range pixels / channels are clipped
-          // by the tensor map.
-          if (valid) epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[acc][0][cc], &epi_sc[acc][1][cc], false);
-          uint32_t wh[16], wl[16];
-          split32_words(v, wh, wl);
-          const uint32_t stg = stg0 + (uint32_t)(cset * 2 + sbuf) * 16384u;
-          const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
-          const bool leader = (quarter == 0 && lane == 0);
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer `sbuf` was read out
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + cset) : "memory");
-          stage_row64(stg, r, wh);
-          stage_row64(stg + 8192u, r, wl);
-          fence_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + cset) : "memory");
-          if (leader && !(P.debug & 1)) {
-            if (P.tma_out == 2) {
-              tma_store_5d(&P.o_hi, stg, n0, E.oox, x0, E.ooy, y0);
-              tma_store_5d(&P.o_lo, stg + 8192u, n0, E.oox, x0, E.ooy, y0);
-            } else {
-              tma_store_3d(&P.o_hi, stg, n0, x0, y0);
-              tma_store_3d(&P.o_lo, stg + 8192u, n0, x0, y0);
-            }
-            bulk_commit();
-          }
-          sbuf ^= 1;
-        } else if (valid && !(P.debug & 1)) {
+        if (valid && !(P.debug & 1)) {
           if (P.splits > 1) {
             float4* dst = reinterpret_cast<float4*>(P.partial + ((size_t)split * npix + (size_t)y * P.Wo + x) * P.Cout_pad + n0);
 #pragma unroll
@@ -273,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
-    if (P.tma_out && quarter == 0 && lane == 0) bulk_wait0();     // every tensor store of this CTA has landed
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -615,6 +685,13 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
       if (cost < best_cost) { best_cost = cost; best_bn = bn; best_splits = sp; }
     }
   }
+  // Short-K layers with wide outputs (the 1x1 expand convs of the bottleneck blocks and their shortcut convs) are
+  // bound by the epilogue, not the mainloop: measured (profiles/r01_layer_tma_epilogue.txt) the TMA-both-ways
+  // epilogue at BN = 128 beats the direct epilogue at BN = 256 by 14-28 % there, and loses elsewhere.
+  const int tma_mode = env_int("ACCEL_TC_TMA_OUT", -1);          // -1 auto, 0 never, 1 wherever it fits
+  const bool auto_t = tma_mode < 0 && best_splits == 1 && P.kiters <= 8 && C.epi.Cout >= 256 && C.epi.Cout % 128 == 0 &&
+                      C.epi.out_hi != nullptr && !C.epi.out2_hi;
+  if (auto_t) best_bn = 128;
   int bn = env_int("ACCEL_TC_BN", best_bn);
   if (bn != 64 && bn != 128 && bn != 256) bn = best_bn;
   P.pair = env_int("ACCEL_TC_PAIR", 0) != 0 ? 1 : 0;
@@ -625,11 +702,9 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   if (splits > P.kiters) splits = P.kiters;
   if (splits < 1) splits = 1;
   const size_t stage_bytes = 2 * (size_t)BM * 128 + (P.pair ? 1 : 2) * (size_t)bn * 128;   // pair: half the weight rows per CTA
-  // Optional TMA-store epilogue (ACCEL_TC_TMA_OUT=1): needs kStageOut bytes of staging next to the operand ring,
-  // so only when at least two ring stages still fit (BN <= 128).  Measured on B200 (profiles/r01_layer_sweeps.txt)
-  // it does not beat the direct 256-bit stores -- the layers it targets are bound by SM<->L2 traffic, not by the
-  // LSU -- so it is off by default.
-  const bool want_stage = !P.pair && env_int("ACCEL_TC_TMA_OUT", 0) != 0 && splits == 1 && C.epi.out_hi != nullptr &&
+  // TMA-both-ways epilogue: needs kStageOut bytes of staging next to the operand ring, so only when at least two
+  // ring stages still fit (BN <= 128).
+  const bool want_stage = !P.pair && (tma_mode > 0 || (auto_t && bn == 128)) && splits == 1 && C.epi.out_hi != nullptr &&
                           (kSmemBudget - kStageOut) / stage_bytes >= 2;
   int stages = (int)((kSmemBudget - (want_stage ? kStageOut : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -689,8 +764,8 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   {
     // main output as TMA stores: channel chunks of 32 (64 bytes), the tile's BW x BH pixel box
     const Epilogue& E = C.epi;
-    const bool can = want_stage && !(P.debug & 8) && P.splits == 1 && P.vec32 && E.out_hi && E.Cout % 8 == 0 && E.out_ld % 8 == 0 &&
-                     (E.Cout % 32 == 0 || (!E.res_hi && !E.out_nchw && !E.out2_hi));
+    const bool can = want_stage && !(P.debug & 8) && P.splits == 1 && P.vec32 && E.out_hi && E.out_ld % 8 == 0 &&
+                     E.Cout % P.BN == 0 && (!E.res_hi || (E.osy == 1 && E.res_ld % 8 == 0));
     P.tma_out = 0;
     if (can && E.osy == 1 && E.osx == 1 && E.ooy == 0 && E.oox == 0) {
       cuuint64_t dims[3] = {(cuuint64_t)E.Cout, (cuuint64_t)E.OWf, (cuuint64_t)E.OHf};
@@ -698,8 +773,13 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
       cuuint32_t box[3] = {32, (cuuint32_t)P.BW, (cuuint32_t)P.BH};
       ok = ok && encode(&P.o_hi, E.out_hi, 3, dims, str, box, err, errlen, CU_TENSOR_MAP_SWIZZLE_64B);
       ok = ok && encode(&P.o_lo, E.out_lo, 3, dims, str, box, err, errlen, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (E.res_hi) {
+        cuuint64_t rstr[2] = {(cuuint64_t)E.res_ld * e, (cuuint64_t)E.res_ld * E.OWf * e};
+        ok = ok && encode(&P.r_hi, E.res_hi, 3, dims, rstr, box, err, errlen, CU_TENSOR_MAP_SWIZZLE_64B);
+        ok = ok && encode(&P.r_lo, E.res_lo, 3, dims, rstr, box, err, errlen, CU_TENSOR_MAP_SWIZZLE_64B);
+      }
       P.tma_out = 1;
-    } else if (can && E.osy == 2 && E.osx == 2 && E.OWf % 2 == 0 && E.OHf % 2 == 0) {
+    } else if (can && !E.res_hi && E.osy == 2 && E.osx == 2 && E.OWf % 2 == 0 && E.OHf % 2 == 0) {
       cuuint64_t dims[5] = {(cuuint64_t)E.Cout, 2, (cuuint64_t)E.OWf / 2, 2, (cuuint64_t)E.OHf / 2};
       cuuint64_t str[4] = {(cuuint64_t)E.out_ld * e, 2 * (cuuint64_t)E.out_ld * e, (cuuint64_t)E.out_ld * E.OWf * e,
                            2 * (cuuint64_t)E.out_ld * E.OWf * e};
