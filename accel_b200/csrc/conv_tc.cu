@@ -689,9 +689,10 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   // bound by the epilogue, not the mainloop: measured (profiles/r01_layer_tma_epilogue.txt) the TMA-both-ways
   // epilogue at BN = 128 beats the direct epilogue at BN = 256 by 14-28 % there, and loses elsewhere.
   const int tma_mode = env_int("ACCEL_TC_TMA_OUT", -1);          // -1 auto, 0 never, 1 wherever it fits
-  const bool auto_t = tma_mode < 0 && best_splits == 1 && P.kiters <= 8 && C.epi.Cout >= 256 && C.epi.Cout % 128 == 0 &&
+  const int t_bn = best_bn > 128 ? 128 : best_bn;
+  const bool auto_t = tma_mode < 0 && best_splits == 1 && P.kiters <= env_int("ACCEL_TC_TMA_KMAX", 10) && C.epi.Cout % t_bn == 0 &&
                       C.epi.out_hi != nullptr && !C.epi.out2_hi;
-  if (auto_t) best_bn = 128;
+  if (auto_t) best_bn = t_bn;
   int bn = env_int("ACCEL_TC_BN", best_bn);
   if (bn != 64 && bn != 128 && bn != 256) bn = best_bn;
   P.pair = env_int("ACCEL_TC_PAIR", 0) != 0 ? 1 : 0;
@@ -704,7 +705,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   const size_t stage_bytes = 2 * (size_t)BM * 128 + (P.pair ? 1 : 2) * (size_t)bn * 128;   // pair: half the weight rows per CTA
   // TMA-both-ways epilogue: needs kStageOut bytes of staging next to the operand ring, so only when at least two
   // ring stages still fit (BN <= 128).
-  const bool want_stage = !P.pair && (tma_mode > 0 || (auto_t && bn == 128)) && splits == 1 && C.epi.out_hi != nullptr &&
+  const bool want_stage = !P.pair && (tma_mode > 0 || (auto_t && bn == best_bn)) && splits == 1 && C.epi.out_hi != nullptr &&
                           (kSmemBudget - kStageOut) / stage_bytes >= 2;
   int stages = (int)((kSmemBudget - (want_stage ? kStageOut : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
