@@ -205,7 +205,7 @@ def run_reference(a):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -485,13 +485,27 @@ def run_native(a):
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "%d frames of the same workload on the CPU oracle (%.2fs/key, %.2fs/cur), "
                                               "~%ds budget" % (d["frames_timed"], d["key_s"], d["cur_s"], int(budget))}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else a library prints on fd 1 during the
+    run (NCCL's version banner, for one) has been diverted to stderr by main()."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
+_REAL_STDOUT = sys.stdout
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
