@@ -691,7 +691,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   const int tma_mode = env_int("ACCEL_TC_TMA_OUT", -1);          // -1 auto, 0 never, 1 wherever it fits
   const int t_bn = best_bn > 128 ? 128 : best_bn;
   const bool auto_t = tma_mode < 0 && best_splits == 1 && P.kiters <= env_int("ACCEL_TC_TMA_KMAX", 10) && C.epi.Cout % t_bn == 0 &&
-                      C.epi.out_hi != nullptr && !C.epi.out2_hi;
+                      C.epi.out_hi != nullptr && (!C.epi.out2_hi || env_int("ACCEL_TC_TMA_OUT2", 1) != 0);
   if (auto_t) best_bn = t_bn;
   int bn = env_int("ACCEL_TC_BN", best_bn);
   if (bn != 64 && bn != 128 && bn != 256) bn = best_bn;

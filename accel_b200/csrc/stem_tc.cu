@@ -149,12 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 f = src[e];
-              __half h0, l0, h1, l1;
-              split_f32(f.x, h0, l0);
-              split_f32(f.y, h1, l1);
-              const __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-              hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
-              lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
+              split_pair(f.x, f.y, hw[e], lw[e]);
             }
             hv = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
