@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(128) fuse_lowres_kernel(const FuseParams P) {
 // ------------------------------------------------------------------------------------------------
 // KC > 0: class count known at compile time (19 for Cityscapes): the class loop is fully unrolled, so the 4 x KC
 // low-resolution loads of a thread are all in flight before the first use.
-template <int KC>
-__global__ void __launch_bounds__(256) tail_kernel(const TailParams P) {
+template <int KC, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) tail_kernel(const TailParams P) {
   pdl_trigger();
   pdl_wait();
   const int OW = P.w * P.factor, OH = P.h * P.factor;
@@ -530,6 +530,10 @@ cudaError_t launch_fuse_lowres(const FuseParams& P, cudaStream_t stream) {
 
 cudaError_t launch_tail(const TailParams& P, cudaStream_t stream) {
   const int work = (P.w * P.factor / 4) * (P.h * P.factor);
+  static int minb = -1;
+  if (minb < 0) { const char* e = getenv("ACCEL_TAIL_MINB"); minb = e && *e ? atoi(e) : 4; }
+  if (P.K == 19 && minb == 4) return launch_k(tail_kernel<19, 4>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
+  if (P.K == 19 && minb == 6) return launch_k(tail_kernel<19, 6>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
   if (P.K == 19) return launch_k(tail_kernel<19>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
   return launch_k(tail_kernel<0>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
 }
