@@ -28,6 +28,11 @@ enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// True the first time it is called for (slot, current device): cudaFuncSetAttribute is per device, and one process may
+// drive several GPUs (pred_eval_multiprocess uses one predictor pair per GPU from threads).
+bool first_time_on_device(int slot);
+enum { ONCE_CONV_TC = 0, ONCE_STEM_TC, ONCE_STEM, ONCE_WARP_STAGED_0, ONCE_WARP_STAGED_1, ONCE_WARP_STAGED_2, ONCE_WARP_STAGED_3, ONCE_SLOTS };
+
 bool pdl_enabled();   // graph.cu: ACCEL_PDL=1 turns it on (measured neutral on B200 for these plans, so off by default)
 
 // Same, as thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it).

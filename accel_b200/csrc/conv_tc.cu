@@ -794,8 +794,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     delete plan;
     return nullptr;
   }
-  static bool configured = false;
-  if (!configured) {
+  if (first_time_on_device(ONCE_CONV_TC)) {
     cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
@@ -803,7 +802,6 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
       delete plan;
       return nullptr;
     }
-    configured = true;
   }
   return plan;
 }

@@ -6,8 +6,21 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 namespace accel {
+
+bool first_time_on_device(int slot) {
+  static std::mutex mu;
+  static bool done[ONCE_SLOTS][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || slot < 0 || slot >= ONCE_SLOTS) return true;
+  std::lock_guard<std::mutex> lock(mu);
+  const bool first = !done[slot][dev];
+  done[slot][dev] = true;
+  return first;
+}
 
 bool pdl_enabled() {
   static int v = -1;

@@ -442,11 +442,9 @@ __global__ void __launch_bounds__(256, MINB) tail_kernel(const TailParams P) {
 
 cudaError_t launch_stem(const StemParams& P, cudaStream_t stream) {
   const size_t smem = ((size_t)P.Cin * 49 * 64 + (size_t)P.Cin * ST_PH * ST_PWP) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  if (first_time_on_device(ONCE_STEM)) {
     cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((P.Wo + ST_TW - 1) / ST_TW, (P.Ho + ST_TH - 1) / ST_TH);
   return launch_k(stem_kernel, grid, dim3(256), smem, stream, P);

@@ -335,15 +335,13 @@ StemTcPlan* stem_tc_plan_create(const StemParams& S, const __half* w_hi, const _
     delete plan;
     return nullptr;
   }
-  static bool configured = false;
-  if (!configured) {
+  if (first_time_on_device(ONCE_STEM_TC)) {
     cudaError_t ce = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
       delete plan;
       return nullptr;
     }
-    configured = true;
   }
   return plan;
 }

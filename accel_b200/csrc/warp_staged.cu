@@ -219,12 +219,10 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
 
 template <int THREADS, int PPT, int CB>
 static cudaError_t launch_variant(const WarpParams& P, int th, int max_smem, int sms, int stage_cap, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  if (first_time_on_device(ONCE_WARP_STAGED_0 + (THREADS == 256 ? 0 : 2) + (CB == 8 ? 0 : 1))) {
     if (cudaFuncSetAttribute(warp_kernel_staged<THREADS, PPT, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              max_smem - 2048) != cudaSuccess)
       return cudaErrorNotSupported;
-    configured = true;
   }
   const int W = P.W, H = P.H;
   // ring sized for `per_sm` resident CTAs: CB = 4 -> two CTAs per SM (one CTA's barrier bubbles hide behind the other)

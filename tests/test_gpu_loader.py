@@ -79,3 +79,28 @@ def test_loader_rejects_wrong_scale():
     bad = [{"pattern": None, "frames": torch.zeros(2, 64, 64, 3, dtype=torch.uint8), "frame_seg_len": 2, "frame_id": 0}]
     with pytest.raises(ValueError):
         loader.TestLoader(bad, cfg, device="cuda:0")
+
+
+def test_pred_eval_multiprocess_two_gpus(tmp_path):
+    """One predictor pair + one TestLoader per GPU, driven from one process (tester.py:305-316): needs 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = loader.default_config(key_frame_interval=INTERVAL, scales=(H, W))
+    roidb = _roidb()
+    params = {k: v.numpy() for k, v in synthetic.make_params("dff").items()}
+    arg, aux = params_io.split_arg_aux(params)
+    sym = predictor.dff_deeplab()
+    shapes = [[("data", (1, 3, H, W)), ("data_key", (1, 3, H, W))]]
+    keys, curs, datas = [], [], []
+    for g in range(2):
+        datas.append(loader.TestLoader([roidb[g]], cfg, device="cuda:%d" % g))
+        a, x = dict(arg), dict(aux)                     # distinct dicts -> distinct engines per device
+        keys.append(predictor.Predictor(sym.get_key_test_symbol(cfg), datas[g].data_name, [], context=[predictor.gpu(g)],
+                                        max_data_shapes=shapes, arg_params=a, aux_params=x))
+        curs.append(predictor.Predictor(sym.get_cur_test_symbol(cfg), datas[g].data_name, [], context=[predictor.gpu(g)],
+                                        max_data_shapes=shapes, arg_params=a, aux_params=x, engine=keys[g].engine))
+    merged = loader.pred_eval_multiprocess(2, keys, curs, datas, None, cfg)
+    # the same two videos on one GPU
+    single = loader.pred_eval(0, keys[0], curs[0], loader.TestLoader(roidb, cfg, device="cuda:0"), None, cfg)
+    assert np.array_equal(merged["hist"], single["hist"])
+    assert sorted(merged["frame_ids"]) == sorted(single["frame_ids"])
