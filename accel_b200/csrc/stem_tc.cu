@@ -43,6 +43,7 @@ struct alignas(64) StemTcParams {
   int nblocks;           // K blocks of 64 (8 chunks)
   int nchunks;           // real chunks = Cin * 7
   int stages;            // per producer group (ring)
+  int debug;             // ACCEL_STEM_DEBUG (timing decomposition only): 1 no epilogue stores, 2 no patch loads, 4 no A build
 };
 
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
         const int py = rem / (ST_PW / 4), pv = rem - py * (ST_PW / 4);
         const int iy = iy0 + py, ix = ix0 + pv * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy >= 0 && iy < P.Hp && ix >= 0 && ix < P.Wp) {
+        if (!(P.debug & 2) && iy >= 0 && iy < P.Hp && ix >= 0 && ix < P.Wp) {
           const float* src = (c < 3 ? P.src0 : P.src1) + (size_t)(c < 3 ? c : c - 3) * P.Hs * P.Ws;
           if (P.pool) {
             const float4* q0 = reinterpret_cast<const float4*>(src + (size_t)(2 * iy) * P.Ws + 2 * ix);
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = hv;
-          if (b * 8 + j < P.nchunks) {
+          if (b * 8 + j < P.nchunks && !(P.debug & 4)) {
             const float2* src = reinterpret_cast<const float2*>(patch + (c * ST_PH + ty * 2 + ky) * ST_PW + tx * 2);
             uint32_t hw[4], lw[4];
 #pragma unroll
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
       for (int cc = 0; cc < 64; cc += 32) {
         float v[32];
         tmem_ld32(taddr + cc, v);
-        if (valid) {
+        if (valid && !(P.debug & 1)) {
           if (vec) {
             ResChunk none{};
             epilogue_chunk32(P.epi, pix, cc, v, none);
@@ -325,6 +326,7 @@ StemTcPlan* stem_tc_plan_create(const StemParams& S, const __half* w_hi, const _
     return nullptr;
   }
   P.stages = stages / 2;
+  P.debug = env_int("ACCEL_STEM_DEBUG", 0);
   plan->smem = fixed + 2 * (size_t)P.stages * 32768;
   const int ntiles = P.tiles_x * P.tiles_y;
   plan->grid = ntiles < num_sms ? ntiles : num_sms;
