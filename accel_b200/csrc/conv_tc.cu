@@ -52,6 +52,7 @@ struct alignas(64) TcParams {
   int stride2, Cin_pad, Ho, Wo, Cout_pad, tmem_cols;
   int krot;
   int pair;        // 1: conv_tc2_kernel (cta_group::2 pairs)
+  int ncat;        // 1: hi*hi and hi*lo issued as ONE MMA over [B_hi ; B_lo] (N = 2*BN, two accumulator halves summed in the epilogue)
   int tma_out;     // 1: the main output leaves through shared memory + TMA tensor stores (3-D map), 2: 5-D map (transposed-conv phase)
   int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = no TMA stores
   int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
@@ -60,6 +61,8 @@ struct alignas(64) TcParams {
 };
 
 
+// NCAT: hi*hi and hi*lo issued as ONE MMA over [B_hi ; B_lo] (N = 2*BN <= 256), see the MMA issuer.
+template <bool NCAT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
@@ -145,6 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * P.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const int acc_cols = NCAT ? 2 * P.BN : P.BN;
       int s = 0, acc = 0;
       uint32_t ph = 0, accph = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
         mbar_wait(tempty0 + 8 * acc, accph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(acc * P.BN);
+        const uint32_t d = tmem_base + (uint32_t)(acc * acc_cols);
         for (int it = kb; it < ke; ++it) {
           mbar_wait(full0 + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -163,9 +168,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes along K inside the swizzle atom
-            umma_f16(d, ah + adv, bh + adv, idesc, (it > kb || k > 0) ? 1u : 0u);
-            umma_f16(d, ah + adv, bl + adv, idesc, 1u);
-            umma_f16(d, al + adv, bh + adv, idesc, 1u);
+            const uint32_t first = (it > kb || k > 0) ? 1u : 0u;
+            if (NCAT) {
+              // B_hi and B_lo are adjacent in the stage with one row pitch: a single N = 2*BN operand.  Columns
+              // [0, BN) collect hi*hi (+ lo*hi below), columns [BN, 2BN) collect hi*lo; the tensor core reads the
+              // A_hi slice once instead of twice and issues two instructions instead of three.
+              umma_f16(d, ah + adv, bh + adv, idesc2, first);
+              umma_f16(d, al + adv, bh + adv, idesc, 1u);
+            } else {
+              umma_f16(d, ah + adv, bh + adv, idesc, first);
+              umma_f16(d, ah + adv, bl + adv, idesc, 1u);
+              umma_f16(d, al + adv, bh + adv, idesc, 1u);
+            }
           }
           umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
           if (++s == P.stages) { s = 0; ph ^= 1; }
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(tfull0 + 8 * acc, accph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * (NCAT ? 2 * P.BN : P.BN));
         for (int cc = cset * 32; cc < P.BN; cc += 64, ++n) {
           const int b = n & 1;
           const uint32_t sb = sb0 + (uint32_t)b * 16384u;
@@ -233,6 +247,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           float v[32];
           tmem_ld32(taddr + cc, v);
+          if (NCAT) {
+            float v2[32];
+            tmem_ld32(taddr + P.BN + cc, v2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          }
           ResChunk rc{};
           if (has_res) {
             mbar_wait(rbar0 + 8u * b, (uint32_t)((n >> 1) & 1));
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       asm volatile("bar.sync 1, 256;" ::: "memory");       // scale/shift visible to all epilogue warps
       mbar_wait(tfull0 + 8 * acc, accph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * (NCAT ? 2 * P.BN : P.BN));
       for (int cc = cset * 32; cc < P.BN; cc += 64) {
         const int n0 = nbase + cc;
         if (n0 >= P.Cout_pad) break;
@@ -318,6 +338,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int i = 0; i < 32; ++i) v[i] = 1.f;
         } else {
           tmem_ld32(taddr + cc, v);
+          if (NCAT) {
+            float v2[32];
+            tmem_ld32(taddr + P.BN + cc, v2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          }
         }
         ResChunk rn{};
         const int nn = n0 + 128;
@@ -711,8 +737,14 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   if (stages > kMaxStages) stages = kMaxStages;
   P.stages = stages;
   plan->smem = stages * stage_bytes + 1024 + (want_stage ? kStageOut : 0);
+  // hi*hi and hi*lo as one N = 2*BN MMA (see the MMA issuer): needs 4*BN TMEM columns, i.e. BN <= 128.
+  // ACCEL_TC_NCAT: -1 auto (on whenever it fits), 0 off, 1 on.
+  {
+    const int ncat_mode = env_int("ACCEL_TC_NCAT", -1);
+    P.ncat = (!P.pair && bn <= 128 && ncat_mode != 0) ? 1 : 0;
+  }
   int cols = 32;
-  while (cols < 2 * bn) cols *= 2;
+  while (cols < (P.ncat ? 4 : 2) * bn) cols *= 2;
   P.tmem_cols = cols;
 
   const int tiles = tiles_m * P.n_tiles;
@@ -795,7 +827,8 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     return nullptr;
   }
   if (first_time_on_device(ONCE_CONV_TC)) {
-    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -815,7 +848,8 @@ cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, cudaStream_t
   TcParams P = plan->p;
   if (ext_nchw) P.epi.out_nchw = ext_nchw;
   cudaError_t e = P.pair ? launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, 2u, P)
-                         : launch_k(conv_tc_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
+                         : P.ncat ? launch_k(conv_tc_kernel<true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
+                                  : launch_k(conv_tc_kernel<false>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
   if (e != cudaSuccess) return e;
   if (P.splits > 1) return launch_splitk_epilogue(P.partial, P.splits, P.Ho * P.Wo, P.Cout_pad, P.Wo, P.epi, stream);
   return cudaSuccess;
