@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
           *reinterpret_cast<uint4*>(a_hi + off) = hv;
           *reinterpret_cast<uint4*>(a_lo + off) = lv;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        if (!(P.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive(full0 + 8 * s);
       }

@@ -1,6 +1,7 @@
 """Checks at sizes the small-clip parity tests do not reach (-m gpu).
 
-* 384x640 (not a power of two; partial tiles in every layer): key + cur graphs of Accel-18 against the CPU oracle.
+* 384x640 / 256x384 / 384x256 (not powers of two; partial tiles in every layer): key + cur graphs of Accel-18, -50,
+  -101 and DFF against the CPU oracle.
 * BASELINE.json's full 1024x2048, where the oracle is too slow for the GPU suite: size-independent properties --
   the label map is bit-exactly the lowest-index argmax of the emitted score volume, production mode (no score
   volume) emits the same labels, two runs are bit-identical (deterministic split-K, fixed graphs), interval 1 equals
@@ -19,8 +20,8 @@ pytestmark = pytest.mark.gpu
 SCORE_TOL = 1e-3
 
 
-def test_odd_size_parity_accel18():
-    H, W, version = 384, 640, "18"
+@pytest.mark.parametrize("version,H,W", [("18", 384, 640), ("50", 256, 384), ("101", 256, 384), ("dff", 384, 256)])
+def test_odd_size_parity(version, H, W):
     params = synthetic.make_params(version)
     frames = synthetic.make_frames(2, H, W, stream=7)
     eng = Engine(version, H, W, params=params)
@@ -38,7 +39,7 @@ def test_odd_size_parity_accel18():
     eng.cur_forward(d1, d0, rk["res5c_relu_output"].to(dev), feat2, score, label)
     assert torch.equal(feat2.cpu(), rc["warping_feat_output"]) or \
         (feat2.cpu() - rc["warping_feat_output"]).abs().max().item() < SCORE_TOL
-    ref = rc["correction_output"]
+    ref = rc[nets.output_key(version)]
     assert (score.cpu() - ref).abs().max().item() < SCORE_TOL
     top2 = ref.topk(2, dim=1).values
     margin = (top2[:, 0] - top2[:, 1])[0].numpy()
