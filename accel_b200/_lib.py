@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libaccel_b200.so")
 # every symbol include/accel_b200.h declares
 SYMBOLS = (
     "accel_create", "accel_destroy", "accel_last_error", "accel_param_count", "accel_param_info",
-    "accel_set_param", "accel_finalize", "accel_key_forward", "accel_cur_forward", "accel_flownet",
+    "accel_set_param", "accel_finalize", "accel_key_forward", "accel_cur_forward", "accel_key_forward_lin",
+    "accel_cur_forward_lin", "accel_flownet",
     "accel_warp", "accel_fuse_argmax", "accel_preprocess", "accel_confusion", "accel_conv_layer", "accel_last_launch_count",
     "accel_set_profiling", "accel_stage_times", "accel_op_times",
 )
@@ -50,6 +51,8 @@ def load():
     lib.accel_finalize.argtypes = [vp]
     lib.accel_key_forward.argtypes = [vp, vp, vp, vp, u8p, vp]
     lib.accel_cur_forward.argtypes = [vp, vp, vp, vp, vp, vp, u8p, vp]
+    lib.accel_key_forward_lin.argtypes = [vp, vp, vp, vp, vp, u8p, vp]
+    lib.accel_cur_forward_lin.argtypes = [vp, vp, vp, vp, vp, vp, u8p, vp]
     lib.accel_flownet.argtypes = [vp, vp, vp, vp, vp]
     lib.accel_warp.argtypes = [vp, vp, vp, ip, ip, ip, vp]
     lib.accel_fuse_argmax.argtypes = [vp, vp, vp, vp, ip, ip, ip, u8p, vp, vp]

@@ -144,6 +144,40 @@ extern "C" int accel_cur_forward(AccelHandle* h, const float* data, const float*
   ACCEL_CATCH(h)
 }
 
+extern "C" int accel_key_forward_lin(AccelHandle* h, const float* data, float* feat_out, float* g_out, float* score_out,
+                                     uint8_t* label_out, void* stream) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!data) { h->err = "accel_key_forward_lin: data is NULL"; return 1; }
+  void* ext[X_COUNT] = {nullptr};
+  ext[X_DATA] = (void*)data;
+  ext[X_FEAT_OUT] = feat_out;
+  ext[X_G_OUT] = g_out;
+  ext[X_SCORE_OUT] = score_out;
+  ext[X_LABEL_OUT] = label_out;
+  if (!h->graph->run("key", ext, (cudaStream_t)stream, &h->err)) return 1;
+  return check_stream_error(h);
+  ACCEL_CATCH(h)
+}
+
+extern "C" int accel_cur_forward_lin(AccelHandle* h, const float* data, const float* data_key, const float* g_key, float* g_out,
+                                     float* score_out, uint8_t* label_out, void* stream) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!data || !data_key || !g_key) { h->err = "accel_cur_forward_lin: data, data_key and g_key are required"; return 1; }
+  if (h->cfg.version == ACCEL_VERSION_101) { h->err = "accel_cur_forward_lin: Accel-101 fuses at feature level and needs the warped feature itself"; return 1; }
+  void* ext[X_COUNT] = {nullptr};
+  ext[X_DATA] = (void*)data;
+  ext[X_DATA_KEY] = (void*)data_key;
+  ext[X_G_KEY] = (void*)g_key;
+  ext[X_G_OUT] = g_out;
+  ext[X_SCORE_OUT] = score_out;
+  ext[X_LABEL_OUT] = label_out;
+  if (!h->graph->run("cur_lin", ext, (cudaStream_t)stream, &h->err)) return 1;
+  return check_stream_error(h);
+  ACCEL_CATCH(h)
+}
+
 extern "C" int accel_flownet(AccelHandle* h, const float* data, const float* data_key, float* flow_out, void* stream) {
   if (!h) return 1;
   ACCEL_TRY

@@ -177,6 +177,7 @@ struct Epilogue {
   __half* out2_lo;
   int out2_ld;
   float* out_nchw;
+  float* raw_nchw;           // fp32 NCHW copy of acc * scale (no shift, no residual, no activation), or nullptr
   int osy, osx, ooy, oox;
   int OHf, OWf;
   int Cout;
@@ -197,6 +198,7 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& e, int pix, int c
     if (c < e.Cout) {
       float s = e.scale ? e.scale[c] : 1.f;
       float b = e.shift ? e.shift[c] : 0.f;
+      if (e.raw_nchw) e.raw_nchw[(size_t)c * ((size_t)e.OHf * e.OWf) + pix] = v[i] * s;
       x = fmaf(v[i], s, b);
       if (e.res_hi) x += r[i];
       x = apply_act(x, e.act);

@@ -844,9 +844,10 @@ size_t tc_plan_partial_bytes(const TcPlan* plan) { return plan->partial_bytes; }
 void tc_plan_set_partial(TcPlan* plan, float* partial) { plan->p.partial = partial; }
 int tc_plan_launches(const TcPlan* plan) { return plan->launches; }
 
-cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, cudaStream_t stream) {
+cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_raw, cudaStream_t stream) {
   TcParams P = plan->p;
   if (ext_nchw) P.epi.out_nchw = ext_nchw;
+  P.epi.raw_nchw = ext_raw;
   cudaError_t e = P.pair ? launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, 2u, P)
                          : P.ncat ? launch_k(conv_tc_kernel<true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
                                   : launch_k(conv_tc_kernel<false>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);

@@ -234,7 +234,8 @@ int Graph::pool(std::vector<Op>& s, const std::string& stage, int in, int k, int
   return op.out;
 }
 
-void Graph::warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, int ext_out) {
+void Graph::warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, int ext_out, const std::string& bias,
+                 int act) {
   Op op{};
   op.type = OP_WARP;
   op.stage = "warp";
@@ -252,6 +253,9 @@ void Graph::warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, 
   cv.ext_in0 = ext_out;
   cv.src_warp = 1;
   cv.out = out_split;
+  cv.split_bias = bias;       // commuted L head: relu(warp(W*F) + fc6_bias) while converting
+  cv.split_act = act;
+  if (!bias.empty()) add_param(bias, {tensors_[out_split].C});
   s.push_back(cv);
 }
 
@@ -767,6 +771,12 @@ bool Graph::finalize(std::string* err) {
           break;
         }
         case OP_TO_SPLIT:
+          if (!op.split_bias.empty()) {
+            const std::vector<float>* b = host_param(op.split_bias, err);
+            if (!b) return false;
+            op.split_bias_dev = upload(*b);
+          }
+          break;
         case OP_TO_NCHW:
         case OP_COPY_F32:
           break;
@@ -939,12 +949,14 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
       }
       case OP_CONV: {
         float* ext_nchw = op.epi.ext_out != X_NONE ? (float*)ext[op.epi.ext_out] : nullptr;
+        float* ext_raw = op.epi.ext_raw != X_NONE ? (float*)ext[op.epi.ext_raw] : nullptr;
         if (op.engine == ENG_TC) {
-          ce = launch_conv_tc_ext(op.tc, ext_nchw, stream);
+          ce = launch_conv_tc_ext(op.tc, ext_nchw, ext_raw, stream);
           launches += tc_plan_launches(op.tc);
         } else {
           ConvParams P = op.conv;
           if (ext_nchw) P.epi.out_nchw = ext_nchw;
+          P.epi.raw_nchw = ext_raw;
           if (op.engine == ENG_NARROW) {
             ce = launch_conv_narrow(P, stream);
             ++launches;
@@ -996,7 +1008,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
         if (!src && op.src_warp) src = warp_scratch_;
         if (!src) { *err = "missing input tensor"; return false; }
         ce = launch_nchw_to_split(src, to.C, to.H, to.W, bufs_[to.buf].hi + to.coff, bufs_[to.buf].lo + to.coff, to.ld,
-                                  stream);
+                                  stream, op.split_bias_dev, op.split_act);
         ++launches;
         break;
       }

@@ -13,7 +13,7 @@
 namespace accel {
 
 enum Ext { X_NONE = 0, X_DATA, X_DATA_KEY, X_FEAT_KEY, X_FEAT_OUT, X_SCORE_OUT, X_LABEL_OUT, X_FLOW_OUT, X_AUX_IN,
-           X_AUX_OUT, X_COUNT };
+           X_AUX_OUT, X_G_KEY, X_G_OUT, X_COUNT };   // X_G_*: fc6's linear part W*F (1,1024,h,w) of the commuted L head
 
 struct Tensor {
   int C = 0, H = 0, W = 0;
@@ -49,6 +49,7 @@ struct EpiSpec {
   int out2 = -1;
   int out_f32 = -1;          // also/only write fp32 planar tensor
   int ext_out = X_NONE;      // also write an external fp32 NCHW output when the caller passed one
+  int ext_raw = X_NONE;      // external fp32 NCHW copy of the LINEAR part (acc * scale: no bias, no activation)
   bool no_split_out = false;
 };
 
@@ -73,6 +74,9 @@ struct Op {
   std::string bn_in;         // stem: input BatchNorm (bn_data)
   int stem_pool = 0;
   int src_warp = 0;          // OP_TO_SPLIT: read the warp op's fp32 output (caller's feat_out or the scratch)
+  std::string split_bias;    // OP_TO_SPLIT: per-channel bias added + `split_act` applied during the conversion
+  int split_act = 0;
+  const float* split_bias_dev = nullptr;
   float stem_in_mul = 1.f;
   // resolved
   ConvParams conv{};
@@ -124,7 +128,8 @@ class Graph {
   int pool(std::vector<Op>& s, const std::string& stage, int in, int k, int stride, int pad, bool is_max, bool full,
            EpiSpec post = EpiSpec());
   void require_bilinear(const std::string& name, int num_classes);
-  void warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, int ext_out);
+  void warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, int ext_out, const std::string& bias = "",
+            int act = 0);
   void upflow(std::vector<Op>& s, int flow_f32, const std::string& wname, const std::string& bname, int out_view);
   void fuse(std::vector<Op>& s, int a_f32, int b_f32, const std::string& wname, int out_f32);
   void tail(std::vector<Op>& s, int score_f32, const std::string& bias_name, int ext_label, int ext_score);

@@ -21,7 +21,8 @@ void tc_plan_destroy(TcPlan* plan);
 size_t tc_plan_partial_bytes(const TcPlan* plan);
 void tc_plan_set_partial(TcPlan* plan, float* partial);
 // ext_nchw: optional fp32 NCHW destination that replaces the plan's epilogue out_nchw for this launch
-cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, cudaStream_t stream);
+// ext_raw: optional fp32 NCHW destination of acc * scale (Epilogue::raw_nchw) for this launch
+cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_raw, cudaStream_t stream);
 int tc_plan_launches(const TcPlan* plan);
 
 // ---- stems (7x7 / stride 2 / pad 3, 64 output channels, fp32 NCHW source) ------------------------
@@ -94,8 +95,9 @@ cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream);
 cudaError_t launch_warp_staged(const WarpParams& P, cudaStream_t stream);
 
 // ---- layout conversion --------------------------------------------------------------------------------
+// bias / act: optional per-channel bias added and activation applied on the way (nullptr / ACT_NONE = plain copy)
 cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, const float* bias = nullptr, int act = 0);
 cudaError_t launch_split_to_nchw(const __half* hi, const __half* lo, int ld, int C, int H, int W, float* dst,
                                  cudaStream_t stream);
 

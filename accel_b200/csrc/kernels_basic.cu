@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restric
 // pixel and plane.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restrict__ src, int C, int npix,
-                                                            __half* hi, __half* lo, int ld) {
+                                                            __half* hi, __half* lo, int ld, const float* __restrict__ bias,
+                                                            int act) {
   __shared__ float tile[64][33];
   pdl_trigger();
   pdl_wait();
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restr
   for (int k = 0; k < 8; ++k) {
     const int c = c0 + wid * 8 + k, p = p0 + lane;
     v[k] = (c < C && p < npix) ? __ldg(src + (size_t)c * npix + p) : 0.f;
+    if (bias && c < C) v[k] = apply_act(v[k] + __ldg(bias + c), act);
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) tile[wid * 8 + k][lane] = v[k];
@@ -504,9 +506,9 @@ cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
 }
 
 cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, const float* bias, int act) {
   dim3 grid((H * W + 31) / 32, (ld + 63) / 64);
-  return launch_k(nchw_to_split_kernel, grid, dim3(256), 0, stream, src, C, H * W, hi, lo, ld);
+  return launch_k(nchw_to_split_kernel, grid, dim3(256), 0, stream, src, C, H * W, hi, lo, ld, bias, act);
 }
 
 cudaError_t launch_split_to_nchw(const __half* hi, const __half* lo, int ld, int C, int H, int W, float* dst,

@@ -218,9 +218,17 @@ int preact_branch(Graph& g, Seq& s, const std::string& st, int H, int W, const s
 }
 
 // ---- DeepLab head: fc6 1x1 + ReLU -> score 1x1; returns the low-res fp32 score map ----------------------
+// ext_raw: external slot that receives fc6's LINEAR part W*F (no bias, no ReLU) as fp32 NCHW when the caller passes
+// a pointer -- the quantity the commuted L head of the cur frames warps instead of the 2048-channel feature.
+// fc6_done >= 0: `feat` already IS relu(fc6(.)) (commuted head): only the score conv runs.
 int head(Graph& g, Seq& s, const std::string& st, int feat, const std::string& fc6, const std::string& score,
-         const std::string& upsampling, int K) {
-  int x = g.conv(s, st, feat, fc6, 1024, 1, 1, 0, 1, bias_epi(fc6, ACT_RELU));
+         const std::string& upsampling, int K, int ext_raw = X_NONE, bool fc6_done = false) {
+  int x = feat;
+  if (!fc6_done) {
+    EpiSpec fe = bias_epi(fc6, ACT_RELU);
+    fe.ext_raw = ext_raw;
+    x = g.conv(s, st, feat, fc6, 1024, 1, 1, 0, 1, fe);
+  }
   const Tensor tx = g.tensor(x);
   const int sc = g.new_tensor(K, tx.H, tx.W, true);
   EpiSpec e = bias_epi(score, ACT_NONE);
@@ -249,7 +257,7 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
   {
     Seq& s = g.seq("key");
     int feat = bottleneck_net(g, s, "backbone", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_FEAT_OUT, -1);
-    int sc = head(g, s, "head", feat, "fc6", "score", "upsampling", K);
+    int sc = head(g, s, "head", feat, "fc6", "score", "upsampling", K, X_G_OUT);
     g.tail(s, sc, "", X_LABEL_OUT, X_SCORE_OUT);
   }
   // FlowNet alone (accel_flownet)
@@ -299,6 +307,41 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
         s[j0].join_lane = 1;
         g.tail(s, fused, "corr_bias", X_LABEL_OUT, X_SCORE_OUT);
       }
+    }
+  }
+  // cur frame with the L head commuted through the warp (DFF, Accel-18/34/50): fc6 is a per-pixel linear map and the
+  // bilinear warp a per-channel linear one, so fc6(warp(F)) = warp(W*F) + b.  The key frame hands out G = W*F_key
+  // (X_G_OUT above); every cur frame warps the 1024-channel G instead of the 2048-channel feature (half the bytes),
+  // adds the bias and the ReLU while converting to the split layout, and never runs the 34 GFLOP fc6 GEMM or the
+  // 2048-channel layout conversion.  Chained: G_t = warp_t(G_{t-1}); un-chained: G_key is reused.  Accel-101 needs
+  // the warped feature itself for its feature-level fusion and keeps the plan above.
+  if (version != 101) {
+    Seq& s = g.seq("cur_lin");
+    const int flow = flownet(g, s, H, W, X_NONE);
+    const int gw = g.new_tensor(1024, h, w);
+    g.warp(s, X_G_KEY, flow, gw, X_G_OUT, "fc6_bias", ACT_RELU);
+    const int sl = head(g, s, "head", gw, "fc6", "score", "upsampling", K, X_NONE, true);
+    if (version == 0) {
+      g.tail(s, sl, "", X_LABEL_OUT, X_SCORE_OUT);
+    } else {
+      int sr;
+      const size_t r0 = s.size();
+      if (version == 50) {
+        int f = bottleneck_net(g, s, "rbranch", H, W, "50_", units_50(), DeformCfg{72, 2, 2, 4}, X_NONE, -1);
+        sr = head(g, s, "rhead", f, "curr_fc6", "curr_score", "curr_upsampling", K);
+      } else {
+        const std::string pre = std::to_string(version) + "_";
+        int f = preact_branch(g, s, "rbranch", H, W, pre,
+                              version == 18 ? std::vector<int>{2, 2, 2} : std::vector<int>{3, 4, 6},
+                              version == 18 ? "ab" : "abc");
+        sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K);
+      }
+      for (size_t i = r0; i < s.size(); ++i) s[i].lane = 1;
+      const int fused = g.new_tensor(K, h, w, true);
+      const size_t j0 = s.size();
+      g.fuse(s, sl, sr, "corr", fused);
+      s[j0].join_lane = 1;
+      g.tail(s, fused, "corr_bias", X_LABEL_OUT, X_SCORE_OUT);
     }
   }
   return true;

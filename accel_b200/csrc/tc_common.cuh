@@ -207,6 +207,11 @@ __device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int
       s = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
       b = e.shift ? __ldg(reinterpret_cast<const float4*>(e.shift + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (e.raw_nchw) {                       // the linear part alone (key frame `fc6`: W*F for the commuted L head)
+      const size_t plane = (size_t)e.OHf * e.OWf;
+      float* rp = e.raw_nchw + (size_t)(c0 + 4 * q) * plane + pix;
+      rp[0] = v[4 * q + 0] * s.x; rp[plane] = v[4 * q + 1] * s.y; rp[2 * plane] = v[4 * q + 2] * s.z; rp[3 * plane] = v[4 * q + 3] * s.w;
+    }
     v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, b.x);
     v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, b.y);
     v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, b.z);

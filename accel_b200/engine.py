@@ -42,6 +42,7 @@ class Engine:
         if self.lib.accel_create(C.byref(cfg), C.byref(h)) != 0:
             raise RuntimeError("accel_create failed: %s" % self.lib.accel_last_error(None).decode())
         self._h = h
+        self.flags = int(flags)
         self.torch_device = torch.device("cuda", self.device)
         if params is not None:
             self.set_params(params)
@@ -81,18 +82,34 @@ class Engine:
     def feat_shape(self):
         return (1, FEAT_DIM, self.height // 16, self.width // 16)
 
+    @property
+    def g_shape(self):
+        """fc6's linear part W*F that the commuted L head warps: (1, 1024, H/16, W/16)."""
+        return (1, 1024, self.height // 16, self.width // 16)
+
+    @property
+    def supports_linear_head(self):
+        return self.version != "101"
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.torch_device).cuda_stream)
 
-    def key_forward(self, data, feat_out=None, score_out=None, label_out=None):
+    def key_forward(self, data, feat_out=None, score_out=None, label_out=None, g_out=None):
+        """g_out: optional (1,1024,H/16,W/16) output of fc6's linear part (accel_key_forward_lin)."""
         _check_f32_cuda("data", data, (1, 3, self.height, self.width))
         if feat_out is not None:
             _check_f32_cuda("feat_out", feat_out, self.feat_shape)
         if score_out is not None:
             _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width))
+        if g_out is not None:
+            _check_f32_cuda("g_out", g_out, self.g_shape)
         with torch.cuda.device(self.torch_device):
-            rc = self.lib.accel_key_forward(self._h, _ptr(data), _ptr(feat_out), _ptr(score_out), _ptr(label_out),
-                                            self._stream())
+            if g_out is not None:
+                rc = self.lib.accel_key_forward_lin(self._h, _ptr(data), _ptr(feat_out), _ptr(g_out), _ptr(score_out),
+                                                    _ptr(label_out), self._stream())
+            else:
+                rc = self.lib.accel_key_forward(self._h, _ptr(data), _ptr(feat_out), _ptr(score_out), _ptr(label_out),
+                                                self._stream())
         if rc != 0:
             raise RuntimeError("accel_key_forward failed: %s" % self._err())
 
@@ -109,6 +126,22 @@ class Engine:
                                             _ptr(score_out), _ptr(label_out), self._stream())
         if rc != 0:
             raise RuntimeError("accel_cur_forward failed: %s" % self._err())
+
+    def cur_forward_lin(self, data, data_key, g_key, g_out=None, score_out=None, label_out=None):
+        """Cur-frame graph with the L head commuted through the warp (accel_cur_forward_lin): warps g_key = W_fc6 * F
+        instead of the 2048-channel feature; DFF / Accel-18/34/50 only."""
+        _check_f32_cuda("data", data, (1, 3, self.height, self.width))
+        _check_f32_cuda("data_key", data_key, (1, 3, self.height, self.width))
+        _check_f32_cuda("g_key", g_key, self.g_shape)
+        if g_out is not None:
+            _check_f32_cuda("g_out", g_out, self.g_shape)
+        if score_out is not None:
+            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width))
+        with torch.cuda.device(self.torch_device):
+            rc = self.lib.accel_cur_forward_lin(self._h, _ptr(data), _ptr(data_key), _ptr(g_key), _ptr(g_out),
+                                                _ptr(score_out), _ptr(label_out), self._stream())
+        if rc != 0:
+            raise RuntimeError("accel_cur_forward_lin failed: %s" % self._err())
 
     def flownet(self, data, data_key, flow_out=None):
         if flow_out is None:

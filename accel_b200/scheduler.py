@@ -82,9 +82,15 @@ class StreamState:
     """Per-video state the schedule carries between frames: {feat, data_key}, plus the
     buffers of the optional key-frame lookahead (see segment_frame)."""
 
-    def __init__(self, engine):
+    def __init__(self, engine, linear_head=False):
+        """linear_head: carry G = W_fc6 * F (1024 channels) from frame to frame instead of the 2048-channel feature
+        (the commuted L head, accel_cur_forward_lin).  Off by default: the graphs then are the reference's as
+        written; bench.py and production pipelines turn it on."""
         dev = engine.torch_device
-        self.feat = [torch.empty(engine.feat_shape, device=dev) for _ in range(2)]
+        self.linear_head = bool(linear_head) and engine.supports_linear_head
+        shape = engine.g_shape if self.linear_head else engine.feat_shape
+        self.carry_shape = shape
+        self.feat = [torch.empty(shape, device=dev) for _ in range(2)]
         self.cur = 0
         self.key_frame = None
         self.prev_frame = None
@@ -104,7 +110,7 @@ def _launch_lookahead(engine, state, next_key_data):
     dev = engine.torch_device
     if state.key_stream is None:
         state.key_stream = torch.cuda.Stream(dev)
-        state.key_feat = [torch.empty(engine.feat_shape, device=dev) for _ in range(2)]
+        state.key_feat = [torch.empty(state.carry_shape, device=dev) for _ in range(2)]
         state.key_label = [torch.empty(engine.height, engine.width, dtype=torch.uint8, device=dev) for _ in range(2)]
     slot = state.key_slot
     state.key_slot ^= 1
@@ -113,7 +119,10 @@ def _launch_lookahead(engine, state, next_key_data):
     ready.record(main)
     state.key_stream.wait_event(ready)
     with torch.cuda.stream(state.key_stream):
-        engine.key_forward(next_key_data, state.key_feat[slot], None, state.key_label[slot])
+        if state.linear_head:
+            engine.key_forward(next_key_data, None, None, state.key_label[slot], g_out=state.key_feat[slot])
+        else:
+            engine.key_forward(next_key_data, state.key_feat[slot], None, state.key_label[slot])
         done = torch.cuda.Event()
         done.record(state.key_stream)
     state.pending = {"data": next_key_data, "slot": slot, "event": done}
@@ -140,7 +149,10 @@ def segment_frame(engine, state, data, interval, schedule, label_out, score_out=
         else:
             if p is not None:                                   # a stale lookahead: let it drain before reusing buffers
                 torch.cuda.current_stream(dev).wait_event(p["event"])
-            engine.key_forward(data, state.feat[state.cur], score_out, label_out)
+            if state.linear_head:
+                engine.key_forward(data, None, score_out, label_out, g_out=state.feat[state.cur])
+            else:
+                engine.key_forward(data, state.feat[state.cur], score_out, label_out)
             state.feat_in = state.feat[state.cur]
         state.pending = None
         state.key_frame = data
@@ -148,11 +160,13 @@ def segment_frame(engine, state, data, interval, schedule, label_out, score_out=
             _launch_lookahead(engine, state, next_key_data)
     elif schedule == "chained":
         nxt = state.cur ^ 1
-        engine.cur_forward(data, state.prev_frame, state.feat_in, state.feat[nxt], score_out, label_out)
+        fwd = engine.cur_forward_lin if state.linear_head else engine.cur_forward
+        fwd(data, state.prev_frame, state.feat_in, state.feat[nxt], score_out, label_out)
         state.cur = nxt
         state.feat_in = state.feat[nxt]
     else:
-        engine.cur_forward(data, state.key_frame, state.feat_in, None, score_out, label_out)
+        fwd = engine.cur_forward_lin if state.linear_head else engine.cur_forward
+        fwd(data, state.key_frame, state.feat_in, None, score_out, label_out)
     state.prev_frame = data
     state.index += 1
     return is_key
@@ -168,7 +182,8 @@ class VideoPipeline:
     i+1 / labels of frame i-1 overlap the graphs of frame i; nothing else crosses PCIe.  Optionally the
     confusion matrix against ground-truth label maps is accumulated on the device (demo.py:270-272)."""
 
-    def __init__(self, engine, interval, schedule="chained", pixel_means_bgr=None, depth=2, lookahead=True):
+    def __init__(self, engine, interval, schedule="chained", pixel_means_bgr=None, depth=2, lookahead=True,
+                 linear_head=False):
         if schedule not in SCHEDULES:
             raise ValueError("schedule must be one of %s" % (SCHEDULES,))
         if interval < 1:
@@ -180,7 +195,7 @@ class VideoPipeline:
         dev = engine.torch_device
         H, W = engine.height, engine.width
         self.dev, self.depth = dev, int(depth)
-        self.state = StreamState(engine)
+        self.state = StreamState(engine, linear_head=linear_head)
         self.nu8 = depth + 1                                                      # a key turn uploads two frames
         self.u8 = [torch.empty(H, W, 3, dtype=torch.uint8, device=dev) for _ in range(self.nu8)]
         self.f32 = [torch.empty(1, 3, H, W, device=dev) for _ in range(3)]       # cur / prev / key never collide

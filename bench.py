@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--linear-head", action="store_true",
+                    help="headline run uses the commuted L head (accel_cur_forward_lin: warp W_fc6*F, 1024 channels); "
+                         "without the flag the reference's graphs run as written and the commuted variant is reported "
+                         "as the extra object `linear_head`")
     ap.add_argument("--no-lookahead", action="store_true",
                     help="strictly sequential issue order (no key-frame lookahead on a second CUDA stream)")
     ap.add_argument("--multi-stream", type=int, default=0,
@@ -234,11 +238,12 @@ def run_native(a):
     frames = [h.to(dev) for h in host]
     label = torch.empty(H, W, dtype=torch.uint8, device=dev)
     label_host = torch.empty(H, W, dtype=torch.uint8).pin_memory()
-    state = scheduler.StreamState(eng)
+    lin_main = bool(a.linear_head) and eng.supports_linear_head
+    state = scheduler.StreamState(eng, linear_head=lin_main)
 
     look = not a.no_lookahead and I > 1
 
-    def step(s, last=False):
+    def step(s, last=False, state=state):
         # key-frame lookahead: the next interval's key frame (already resident, like the reference's preloaded
         # `data` list, demo.py:165-185) runs its key plan on a second stream under this interval's cur frames
         for i in range(I):
@@ -295,8 +300,30 @@ def run_native(a):
     if sampler:
         sampler.stop_flag = True
 
+    # the same loop with the L head commuted through the warp (fc6(warp(F)) = warp(W*F) + b): extra object, same K steps
+    lin_ms = None
+    if eng.supports_linear_head and I > 1 and not lin_main:
+        st_lin = scheduler.StreamState(eng, linear_head=True)
+        for s in range(4):
+            step(s, last=(s == 3), state=st_lin)
+        reset_state(st_lin)
+        for s in range(a.warmup):
+            step(s, last=(s == a.warmup - 1), state=st_lin)
+        reset_state(st_lin)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0.record()
+        for s in range(a.steps):
+            step(s, last=(s == a.steps - 1), state=st_lin)
+        if st_lin.key_stream is not None:
+            torch.cuda.current_stream().wait_stream(st_lin.key_stream)
+        l1.record()
+        barrier()
+        lin_ms = l0.elapsed_time(l1)
+        del st_lin
+
     # per-kernel timing of the warp launch, live, with CUDA events on the launching stream: 30 launches
-    # rotating over three (source, destination) feature pairs (6 x 64 MiB > the 126 MB L2, so every read
+    # rotating over three (source, destination) feature pairs (6 x 64 MiB -- 6 x 32 MiB with --linear-head -- > the 126 MB L2, so every read
     # comes from HBM, as in the real loop where >1 GB of other traffic separates two warps of a stream),
     # driven by the stream's own FlowNet flow field.
     warp_evs = []
@@ -304,8 +331,9 @@ def run_native(a):
         from accel_b200 import engine as _E
         h, w = H // 16, W // 16
         g = torch.Generator(device="cpu").manual_seed(7)
-        bufs = [torch.randn(1, 2048, h, w, generator=g).to(dev) for _ in range(2)] + \
-               [torch.empty(1, 2048, h, w, device=dev) for _ in range(4)]
+        warp_c = 1024 if lin_main else 2048
+        bufs = [torch.randn(1, warp_c, h, w, generator=g).to(dev) for _ in range(2)] + \
+               [torch.empty(1, warp_c, h, w, device=dev) for _ in range(4)]
         bufs[2].copy_(bufs[0]); bufs[4].copy_(bufs[1])
         flow_t = eng.flownet(frames[1], frames[0]).clone()      # the flow field FlowNet produces on this stream
         pairs = [(bufs[0], bufs[1]), (bufs[2], bufs[3]), (bufs[4], bufs[5])]
@@ -335,7 +363,7 @@ def run_native(a):
         n_lab = 4
         labels_host = [torch.empty(H, W, dtype=torch.uint8).pin_memory() for _ in range(n_lab)]
         lab_ev = [None] * n_lab
-        pipe = scheduler.VideoPipeline(eng, I, a.schedule, lookahead=look)
+        pipe = scheduler.VideoPipeline(eng, I, a.schedule, lookahead=look, linear_head=lin_main)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def e2e_step(s, last=False):
@@ -364,7 +392,7 @@ def run_native(a):
         e2e_ms = e0.elapsed_time(e1)
 
         stage_in = [torch.empty(1, 3, H, W, device=dev) for _ in range(2)]
-        state = scheduler.StreamState(eng)
+        state = scheduler.StreamState(eng, linear_head=lin_main)
 
         def e2e32_step(s):
             for i in range(I):
@@ -421,11 +449,12 @@ def run_native(a):
                  "note": "S independent video streams interleaved per GPU (own handle + CUDA stream each); not the headline"}
 
     # ---- reduce: max time over ranks, total frames --------------------------------------------------
-    rows = multigpu.gather_rows([a.steps * I, ms, e2e_ms or 0.0, e2e32_ms or 0.0], dev)   # the single metric collective
+    rows = multigpu.gather_rows([a.steps * I, ms, e2e_ms or 0.0, e2e32_ms or 0.0, lin_ms or 0.0], dev)   # the single metric collective
     fps, ms_max = multigpu.aggregate_throughput(rows[:, 0].tolist(), rows[:, 1].tolist())
     e2e_max = float(rows[:, 2].max())
     e2e32_max = float(rows[:, 3].max())
     frames_total = float(rows[:, 0].sum())
+    lin_max = float(rows[:, 4].max())
 
     if rank == 0:
         peaks = {}
@@ -435,7 +464,7 @@ def run_native(a):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_kind = "measured" if "hbm_gbs" in peaks else "fallback"
-        wb = WARP_BYTES(2048, H // 16, W // 16)
+        wb = WARP_BYTES(1024 if lin_main else 2048, H // 16, W // 16)
         # (the un-chained schedule has no consumer for `warping_feat_output`, but this kernel still writes the fp32
         # NCHW feature -- to the handle's scratch -- so the same bytes are counted)
         warp_avg_ms = sum(warp_evs) / len(warp_evs) if warp_evs else None
@@ -464,7 +493,7 @@ def run_native(a):
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "fp16x3 split (fp32-equivalent operands, fp32 accumulate)", "data": "synthetic",
                 "config": {"workload": workload_name(a), "schedule": a.schedule, "frames_per_step": I,
-                           "streams": world, "key_lookahead": bool(look), "l2": "working set per step exceeds the 126 MB L2 (frames 24 MiB each, "
+                           "streams": world, "key_lookahead": bool(look), "linear_head": bool(lin_main), "l2": "working set per step exceeds the 126 MB L2 (frames 24 MiB each, "
                            "features 64 MiB, activations > 1 GiB); no explicit flush"},
                 "gpu_launches": launches_per_step * a.steps, "launches_per_step": launches_per_step,
                 "roofline": roofline, "roofline_conv": conv,
@@ -482,6 +511,13 @@ def run_native(a):
                                 "h2d_bytes_per_step": I * 3 * H * W * 4, "d2h_bytes_per_step": I * H * W,
                                 "note": "same loop fed the reference's upload format (pinned fp32 NCHW `data`), single stream"}
             line["gpu_launches_e2e_per_step"] = launches_per_step + I
+        if lin_ms is not None:
+            line["linear_head"] = {"value": frames_total / (lin_max / 1000.0), "unit": "frames/s",
+                                   "ms_per_step": lin_max / a.steps,
+                                   "note": "same loop, same K steps, L head commuted through the warp (accel_*_forward_lin: "
+                                           "fc6(warp(F)) = warp(W_fc6*F) + b; the cur frames warp 1024 channels and skip the "
+                                           "fc6 GEMM); scores within the same 1e-3 (tests/test_gpu_linear_head.py); not the "
+                                           "headline -- `value` runs the reference's graphs as written"}
         if multi is not None:
             line["multi_stream"] = multi
         if world == 1 and not a.no_cpu_baseline:

@@ -83,6 +83,18 @@ int accel_key_forward(AccelHandle* h, const float* data, float* feat_out, float*
 int accel_cur_forward(AccelHandle* h, const float* data, const float* data_key, const float* feat_key,
                       float* feat_out, float* score_out, uint8_t* label_out, void* stream);
 
+/* The same two graphs with the L head commuted through the warp (DFF, Accel-18/34/50 only).  `fc6` is a per-pixel
+ * linear map and GridGenerator(warp)+BilinearSampler a per-channel linear one (accel_18.py:174-183), so
+ *     fc6(warp(F)) = warp(W_fc6 * F) + b_fc6
+ * accel_key_forward_lin additionally emits g_out = W_fc6 * res5c_relu (1,1024,H/16,W/16; no bias, no ReLU);
+ * accel_cur_forward_lin warps g_key instead of the 2048-channel feature (half the bytes, no fc6 GEMM) and returns
+ * the warped g_out for the next frame of the chained schedule (may be NULL; must not alias g_key).  Same score
+ * volume / label map as accel_cur_forward up to fp32 re-association (parity tests hold both to the same 1e-3). */
+int accel_key_forward_lin(AccelHandle* h, const float* data, float* feat_out, float* g_out, float* score_out,
+                          uint8_t* label_out, void* stream);
+int accel_cur_forward_lin(AccelHandle* h, const float* data, const float* data_key, const float* g_key, float* g_out,
+                          float* score_out, uint8_t* label_out, void* stream);
+
 /* FlowNet-S alone, get_flownet (resnet_v1_101_flownet_deeplab.py:1751-1808): flow_out (1,2,H/16,W/16),
  * channel 0 = dx, 1 = dy in feature-grid pixels, already multiplied by 2.5. */
 int accel_flownet(AccelHandle* h, const float* data, const float* data_key, float* flow_out, void* stream);
