@@ -151,10 +151,21 @@ int Graph::conv(std::vector<Op>& s, const std::string& stage, int in, const std:
   return out;
 }
 
-int Graph::deconv4(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname, int cout,
-                   EpiSpec e, int out) {
+int Graph::deconv4(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname_in, int cout,
+                   EpiSpec e, int out, const std::string& fold_1x1, int mid) {
   const Tensor ti = tensors_[in];
-  add_param(wname + "_weight", {ti.C, cout, 4, 4});
+  std::string wname = wname_in;
+  if (fold_1x1.empty()) {
+    add_param(wname + "_weight", {ti.C, cout, 4, 4});
+  } else {
+    // the caller's two parameters stay the public ones; the composed weight is private to the handle
+    add_param(wname_in + "_weight", {ti.C, mid, 4, 4});
+    add_param(fold_1x1 + "_weight", {cout, mid, 1, 1});
+    wname = fold_1x1 + "*" + wname_in;
+    bool seen = false;
+    for (const FoldSpec& f : folds_) seen = seen || f.out == wname + "_weight";
+    if (!seen) folds_.push_back({wname + "_weight", wname_in + "_weight", fold_1x1 + "_weight", ti.C, mid, cout});
+  }
   register_epi_params(*this, e, cout);
   if (out < 0) out = new_tensor(cout, 2 * ti.H, 2 * ti.W);
   for (int py = 0; py < 2; ++py)
@@ -643,6 +654,26 @@ bool Graph::finalize(std::string* err) {
             return false;
           }
         }
+  }
+  // derived parameters: (1x1 conv) o (4x4/s2 transposed conv) composed into one transposed conv, on the device in
+  // fp32 products with fp64 accumulation
+  for (const FoldSpec& f : folds_) {
+    const std::vector<float>* wd = host_param(f.deconv, err);
+    const std::vector<float>* wc = wd ? host_param(f.conv1x1, err) : nullptr;
+    if (!wd || !wc) return false;
+    float *dd = nullptr, *dc = nullptr, *dout = nullptr;
+    const size_t nout = (size_t)f.cin * f.cout * 16;
+    bool ok = cudaMalloc(&dd, wd->size() * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&dc, wc->size() * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&dout, nout * sizeof(float)) == cudaSuccess;
+    std::vector<float>& composed = host_[f.out];
+    composed.resize(nout);
+    ok = ok && cudaMemcpy(dd, wd->data(), wd->size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(dc, wc->data(), wc->size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+         launch_fold_deconv_1x1(dd, dc, dout, f.cin, f.mid, f.cout, nullptr) == cudaSuccess &&
+         cudaMemcpy(composed.data(), dout, nout * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(dd); cudaFree(dc); cudaFree(dout);
+    if (!ok) { *err = "composing '" + f.out + "' failed: " + cudaGetErrorString(cudaGetLastError()); return false; }
   }
   for (auto& kv : seqs_) {
     for (auto& op : kv.second) {

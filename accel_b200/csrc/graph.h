@@ -121,8 +121,11 @@ class Graph {
            float in_mul, const std::string& bn_in, const std::string& wname, int cin, EpiSpec e);
   int conv(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname, int cout, int k, int stride,
            int pad, int dil, EpiSpec e, int out = -1);
+  // fold_1x1: name of a 1x1 convolution (weight (cout, mid, 1, 1)) that follows the transposed conv (weight
+  // (Cin, mid, 4, 4)) with nothing in between: the two linear maps are composed once at finalize into one
+  // (Cin, cout, 4, 4) transposed conv (shortcut iii: 18_fc6 o 18_feat_upsampling).
   int deconv4(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname, int cout, EpiSpec e,
-              int out = -1);
+              int out = -1, const std::string& fold_1x1 = "", int mid = 0);
   int dcn(std::vector<Op>& s, const std::string& stage, int in, int offset_f32, const std::string& wname, int cout,
           int dg, EpiSpec e);
   int pool(std::vector<Op>& s, const std::string& stage, int in, int k, int stride, int pad, bool is_max, bool full,
@@ -182,6 +185,8 @@ class Graph {
   std::vector<const Op*> event_op_;
   std::vector<std::pair<std::string, float>> times_;
   std::vector<std::string> bilinear_checks_;
+  struct FoldSpec { std::string out, deconv, conv1x1; int cin, mid, cout; };
+  std::vector<FoldSpec> folds_;          // derived parameters: out = conv1x1 o deconv, computed at finalize
   int label_scratch_ = -1;
   uint8_t* label_scratch_ptr_ = nullptr;
   size_t label_scratch_bytes_ = 0;

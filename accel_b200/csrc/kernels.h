@@ -94,6 +94,12 @@ cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream);
 // shared-memory staged variant (warp_staged.cu); cudaErrorNotSupported = shape unsuitable, use the gather kernel
 cudaError_t launch_warp_staged(const WarpParams& P, cudaStream_t stream);
 
+// ---- weight preparation (finalize time) --------------------------------------------------------------------
+// out[c][n][t] = sum_m conv1x1[n][m] * deconv[c][m][t]  (t = ky*4+kx; deconv (Cin, mid, 4, 4), conv1x1 (cout, mid),
+// out (Cin, cout, 4, 4)); fp32 operands, fp64 accumulation.
+cudaError_t launch_fold_deconv_1x1(const float* deconv, const float* conv1x1, float* out, int cin, int mid, int cout,
+                                   cudaStream_t stream);
+
 // ---- layout conversion --------------------------------------------------------------------------------
 // bias / act: optional per-channel bias added and activation applied on the way (nullptr / ACT_NONE = plain copy)
 cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,

@@ -440,6 +440,98 @@ __global__ void __launch_bounds__(256, MINB) tail_kernel(const TailParams P) {
       make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
 }
 
+// Band version of the tail for the shape that matters (factor 16, KC classes): every 16 x 16 output cell
+// {Y+8 in [16 i0, 16 i0 + 16)} x {X+8 in [16 j0, 16 j0 + 16)} interpolates the SAME 2 x 2 low-resolution neighbourhood,
+// so the interpolation is evaluated separably -- per class and quad column once `top = wx0 s[i0][j0] + wx1 s[i0][j0-1]`
+// and `bot` (row i0-1), then two FMAs per pixel -- instead of four loads and four multiply-adds per pixel and class.
+// CTA = 16 output rows x 512 columns; its 3 x 34 x KC source window is staged in shared memory (clamped indices, like
+// the kernel above: weights, not values, are zeroed beyond the map); thread = one quad column x 8 rows (one source-row
+// pair), 32 running (best, arg) pairs in registers; labels leave as uchar4, scores (parity mode) as float4.
+template <int KC, bool SCORES>
+__global__ void __launch_bounds__(256, 2) tail_band_kernel(const TailParams P) {
+  constexpr int F = 16, TW = 512, NC = TW / F + 2;
+  __shared__ float ss[KC + 1][3][NC];                       // + one dummy class: the loop prefetches one ahead
+  __shared__ float sbias[KC];
+  pdl_trigger();
+  pdl_wait();
+  const int OW = P.w * F, OH = P.h * F;
+  const int m = blockIdx.y, kc = blockIdx.x;
+  const size_t plane = (size_t)P.h * P.w, oplane = (size_t)OH * OW;
+  for (int i = threadIdx.x; i < KC * 3 * NC; i += 256) {
+    const int c = i / (3 * NC), rem = i - c * 3 * NC, r = rem / NC, j = rem - r * NC;
+    const int sy = min(max(m - 1 + r, 0), P.h - 1), sx = min(max(kc * (TW / F) - 1 + j, 0), P.w - 1);
+    ss[c][r][j] = P.score[c * plane + (size_t)sy * P.w + sx];
+  }
+  if (threadIdx.x < 3 * NC) ss[KC][threadIdx.x / NC][threadIdx.x % NC] = 0.f;
+  if (threadIdx.x < KC) sbias[threadIdx.x] = P.bias ? P.bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int qx = threadIdx.x & 127, rh = threadIdx.x >> 7;
+  const int X0 = kc * TW + 4 * qx;
+  if (X0 >= OW) return;
+  const float inv = 1.f / (float)F, cen = (float)(2 * F - 1) / (float)(2 * F);
+  const int j0 = (X0 + F / 2) / F, kx = (X0 + F / 2) - j0 * F;
+  const int lc0 = j0 - (kc * (TW / F) - 1);                 // shared-memory column of source column j0 (j0-1: lc0-1)
+  const bool c0ok = j0 < P.w, c1ok = j0 >= 1;
+  float wx0[4], wx1[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    wx0[q] = c0ok ? 1.f - fabsf((float)(kx + q) * inv - cen) : 0.f;
+    wx1[q] = c1ok ? 1.f - fabsf((float)(kx + q + F) * inv - cen) : 0.f;
+  }
+  const int Yb = m * F + rh * 8;                            // first of this thread's 8 rows
+  const int i0 = m + rh, ky0 = rh ? 0 : 8;                  // (Y + 8) / 16 and (Y + 8) % 16 of row Yb
+  float wy0[8], wy1[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    wy0[r] = (i0 < P.h) ? 1.f - fabsf((float)(ky0 + r) * inv - cen) : 0.f;
+    wy1[r] = (i0 >= 1) ? 1.f - fabsf((float)(ky0 + r + F) * inv - cen) : 0.f;
+  }
+  float best[8][4];
+  unsigned arg[8];                                          // four 8-bit class ids per row
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    arg[r] = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) best[r][q] = -INFINITY;
+  }
+  const float* s0 = &ss[0][1 + rh][lc0];                    // source row i0   (class stride 3 * NC)
+  const float* s1 = &ss[0][rh][lc0];                        // source row i0-1
+  float a0 = s0[0], a1 = s0[-1], b0 = s1[0], b1 = s1[-1];
+  float* so = SCORES ? P.score_out + (size_t)Yb * OW + X0 : nullptr;
+  // the class loop stays rolled: its body (8 rows x 4 pixels) is ~4 KB of code that all 19 iterations reuse from the
+  // instruction cache; fully unrolled it is > 100 KB of straight-line code and instruction fetch becomes the limit
+#pragma unroll 1
+  for (int c = 0; c < KC; ++c) {
+    float top[4], bot[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      top[q] = __fmaf_rn(a1, wx1[q], __fmul_rn(a0, wx0[q]));
+      bot[q] = __fmaf_rn(b1, wx1[q], __fmul_rn(b0, wx0[q]));
+    }
+    const float b = sbias[c];
+    s0 += 3 * NC; s1 += 3 * NC;                             // next class's taps, in flight under this class's math
+    a0 = s0[0]; a1 = s0[-1]; b0 = s1[0]; b1 = s1[-1];
+    const unsigned cb = (unsigned)c * 0x01010101u;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q] = __fadd_rn(__fmaf_rn(wy1[r], bot[q], __fmul_rn(wy0[r], top[q])), b);
+        if (v[q] > best[r][q]) {                            // strict: ties keep the lowest class
+          best[r][q] = v[q];
+          arg[r] = (arg[r] & ~(0xffu << (8 * q))) | (cb & (0xffu << (8 * q)));
+        }
+      }
+      if (SCORES && Yb + r < OH) *reinterpret_cast<float4*>(so + (size_t)r * OW) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (SCORES) so += oplane;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (Yb + r < OH) *reinterpret_cast<unsigned*>(P.label + (size_t)(Yb + r) * OW + X0) = arg[r];
+}
+
 }  // namespace
 
 cudaError_t launch_stem(const StemParams& P, cudaStream_t stream) {
@@ -511,6 +603,52 @@ cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* 
   return launch_k(nchw_to_split_kernel, grid, dim3(256), 0, stream, src, C, H * W, hi, lo, ld, bias, act);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Finalize-time weight composition (shortcut iii): a 1x1 convolution that directly follows a
+// 4x4/s2 transposed convolution (accel_18.py:204-213: `18_feat_upsampling` -> `18_fc6`, no bias / activation in
+// between) is one transposed convolution with weights  out[c][n][t] = sum_m conv1x1[n][m] * deconv[c][m][t].
+// For a fixed input channel c the deconv slab [mid][16] is contiguous: block = (64 n) x (16 t) outputs of one c,
+// thread = 4 n x 1 t, fp32 operands staged in shared memory, fp64 accumulation.  Runs once per handle.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fold_deconv_1x1_kernel(const float* __restrict__ deconv,
+                                                              const float* __restrict__ conv1x1, float* __restrict__ out,
+                                                              int mid, int cout) {
+  __shared__ float sw[64][33];       // conv1x1[n0 + i][m0 + j]
+  __shared__ float sd[32][16];       // deconv[c][m0 + j][t]
+  const int c = blockIdx.y, n0 = blockIdx.x * 64;
+  const int t = threadIdx.x & 15, ng = threadIdx.x >> 4;          // n = n0 + ng + 16 * k
+  const float* dslab = deconv + (size_t)c * mid * 16;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int m0 = 0; m0 < mid; m0 += 32) {
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+      const int r = i >> 5, j = i & 31;
+      sw[r][j] = (n0 + r < cout && m0 + j < mid) ? conv1x1[(size_t)(n0 + r) * mid + m0 + j] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 32 * 16; i += 256)
+      sd[i >> 4][i & 15] = (m0 + (i >> 4) < mid) ? dslab[(size_t)m0 * 16 + i] : 0.f;
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const double d = (double)sd[j][t];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = fma((double)sw[ng + 16 * k][j], d, acc[k]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int n = n0 + ng + 16 * k;
+    if (n < cout) out[((size_t)c * cout + n) * 16 + t] = (float)acc[k];
+  }
+}
+
+cudaError_t launch_fold_deconv_1x1(const float* deconv, const float* conv1x1, float* out, int cin, int mid, int cout,
+                                   cudaStream_t stream) {
+  fold_deconv_1x1_kernel<<<dim3((cout + 63) / 64, cin), 256, 0, stream>>>(deconv, conv1x1, out, mid, cout);
+  cudaError_t e = cudaGetLastError();
+  return e != cudaSuccess ? e : cudaStreamSynchronize(stream);
+}
+
 cudaError_t launch_split_to_nchw(const __half* hi, const __half* lo, int ld, int C, int H, int W, float* dst,
                                  cudaStream_t stream) {
   dim3 grid((H * W + 31) / 32, (C + 31) / 32);
@@ -530,8 +668,14 @@ cudaError_t launch_fuse_lowres(const FuseParams& P, cudaStream_t stream) {
 
 cudaError_t launch_tail(const TailParams& P, cudaStream_t stream) {
   const int work = (P.w * P.factor / 4) * (P.h * P.factor);
-  static int minb = -1;
+  static int minb = -1, band = -1;
   if (minb < 0) { const char* e = getenv("ACCEL_TAIL_MINB"); minb = e && *e ? atoi(e) : 4; }
+  if (band < 0) { const char* e = getenv("ACCEL_TAIL_BAND"); band = !(e && e[0] == '0'); }
+  if (band && P.K == 19 && P.factor == 16) {
+    const dim3 grid((P.w * 16 + 511) / 512, P.h);
+    return P.score_out ? launch_k(tail_band_kernel<19, true>, grid, dim3(256), 0, stream, P)
+                       : launch_k(tail_band_kernel<19, false>, grid, dim3(256), 0, stream, P);
+  }
   if (P.K == 19 && minb == 4) return launch_k(tail_kernel<19, 4>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
   if (P.K == 19 && minb == 6) return launch_k(tail_kernel<19, 6>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
   if (P.K == 19) return launch_k(tail_kernel<19>, dim3((work + 255) / 256), dim3(256), 0, stream, P);

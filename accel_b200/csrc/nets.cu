@@ -6,6 +6,8 @@
 // Concats are zero-copy channel views, BatchNorm/bias/activation/residual live in conv epilogues,
 // Deconvolution(k4,s2)+Crop(1,1) is run as four 2x2-tap phase convolutions, and the x16 score
 // upsampling + fusion + argmax is one tail kernel.
+#include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "graph.h"
@@ -70,9 +72,13 @@ int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out) {
     g.deconv4(s, st, feat, deconv_name, deconv_c, bias_epi(deconv_name, ACT_LEAKY), g.new_view(cat, skip_c, deconv_c));
     const size_t i2 = s.size();
     g.upflow(s, f, up_name, std::string(up_name) + "_bias", g.new_view(cat, skip_c + deconv_c, 2));
+    // The flow head is the longest chain of a level (9 taps over the whole concat against 4 taps per deconv phase,
+    // plus the upsampling behind it): planned for a quarter of the SMs like the phases it took 89 us at level 2 while
+    // the phases next to it took 41 us.  It is planned for half of the SMs instead (ACCEL_FLOWHEAD_WIDTH overrides).
+    static const int head_width = [] { const char* e = getenv("ACCEL_FLOWHEAD_WIDTH"); return e && *e ? std::max(1, atoi(e)) : 2; }();
     for (size_t i = i0; i < s.size(); ++i) {
       s[i].par_group = grp;
-      s[i].par_width = 4;
+      s[i].par_width = (i < i1) ? head_width : 4;
       if (i >= i1 && i < i2) s[i].par_branch = 1 + s[i].phase_y * 2 + s[i].phase_x;     // branches 1..4: deconv phases
       else s[i].par_branch = (i < i1) ? 5 : 5;                                          // branch 5: flow head -> upflow
     }
@@ -152,7 +158,7 @@ std::vector<std::vector<std::string>> units_50() {
 
 // ---- pre-activation basic-block trunk + deformable conv5 (Accel-18 / Accel-34 R branch) ----------------
 int preact_branch(Graph& g, Seq& s, const std::string& st, int H, int W, const std::string& pre,
-                  const std::vector<int>& units, const std::string& letters) {
+                  const std::vector<int>& units, const std::string& letters, bool fold_fc6) {
   const float eps = 2e-5f;
   int x = g.stem(s, st, X_DATA, X_NONE, H, W, false, 1.f, pre + "bn_data", pre + "conv0", 3,
                  bn_epi(pre + "bn0", ACT_RELU, eps));
@@ -214,6 +220,10 @@ int preact_branch(Graph& g, Seq& s, const std::string& st, int H, int W, const s
     be.res = sc;
     xx = g.dcn(s, st, a, off, pre + "res5" + L + "_branch2b", 512, 4, be);
   }
+  // `<pre>fc6` directly follows `<pre>feat_upsampling` (accel_18.py:204-213; no bias, BN or
+  // activation in between), so the two linear maps run as ONE 512 -> 1024 transposed conv whose weights are composed
+  // at finalize (34.4 instead of 103.1 GFLOP at 1024x2048).  ACCEL_FOLD_FC6=0 keeps the graph as written.
+  if (fold_fc6) return g.deconv4(s, st, xx, pre + "feat_upsampling", 1024, bias_epi(pre + "fc6", ACT_RELU), -1, pre + "fc6", 2048);
   return g.deconv4(s, st, xx, pre + "feat_upsampling", 2048, EpiSpec());
 }
 
@@ -252,6 +262,8 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
     return false;
   }
   const int h = H / 16, w = W / 16;
+  const char* ff = getenv("ACCEL_FOLD_FC6");
+  const bool fold_fc6 = !(ff && ff[0] == '0');
 
   // key frame: R101-DCN + head (get_key_test_symbol)
   {
@@ -297,8 +309,8 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
           const std::string pre = std::to_string(version) + "_";
           int f = preact_branch(g, s, "rbranch", H, W, pre,
                                 version == 18 ? std::vector<int>{2, 2, 2} : std::vector<int>{3, 4, 6},
-                                version == 18 ? "ab" : "abc");
-          sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K);
+                                version == 18 ? "ab" : "abc", fold_fc6);
+          sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K, X_NONE, fold_fc6);
         }
         for (size_t i = r0; i < s.size(); ++i) s[i].lane = 1;
         const int fused = g.new_tensor(K, h, w, true);
@@ -333,8 +345,8 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
         const std::string pre = std::to_string(version) + "_";
         int f = preact_branch(g, s, "rbranch", H, W, pre,
                               version == 18 ? std::vector<int>{2, 2, 2} : std::vector<int>{3, 4, 6},
-                              version == 18 ? "ab" : "abc");
-        sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K);
+                              version == 18 ? "ab" : "abc", fold_fc6);
+        sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K, X_NONE, fold_fc6);
       }
       for (size_t i = r0; i < s.size(); ++i) s[i].lane = 1;
       const int fused = g.new_tensor(K, h, w, true);

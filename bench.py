@@ -487,7 +487,17 @@ def run_native(a):
                 "achieved": gflop_step * a.steps / (ms_max / 1e3) / 1e3 , "unit": "TFLOP/s (reference-graph flops / whole step time)",
                 "peak": tf_peak, "peak_kind": peak_kind + " bf16 dense sustained"}
         conv["frac"] = conv["achieved"] / tf_peak
-        conv["executed_fp16_mma_tflops"] = 3.0 * conv["achieved"]          # fp16x3: three tensor-core passes per reference flop
+        # executed = reference-graph flops minus the exact algebraic folds (<v>_fc6 o <v>_feat_upsampling
+        # as one 512->1024 transposed conv, 34.4 instead of 103.1 GFLOP; --linear-head: no fc6 GEMM on cur frames), times
+        # three tensor-core passes per flop (fp16x3)
+        folded = 0.0
+        if a.version in ("18", "34") and os.environ.get("ACCEL_FOLD_FC6", "1") != "0":
+            folded += 68.7
+        if lin_main:
+            folded += 34.4
+        exec_step = gflop_step - (I - 1) * folded * scale
+        conv["executed_graph_gflop_per_step"] = exec_step
+        conv["executed_fp16_mma_tflops"] = 3.0 * exec_step * a.steps / (ms_max / 1e3) / 1e3
         conv["executed_frac"] = conv["executed_fp16_mma_tflops"] / tf_peak
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -137,3 +137,28 @@ def test_errors_are_reported_not_swallowed(frames):
     with pytest.raises(RuntimeError, match="fc6_bias"):
         Engine("dff", H, W, params=missing)
     eng.close()
+
+
+@pytest.mark.parametrize("version", ["18", "34"])
+def test_r_head_fold_on_and_off_agree_with_oracle(version, frames, monkeypatch):
+    """`<v>_fc6 o <v>_feat_upsampling` runs as one composed 512 -> 1024 transposed conv by default (SURVEY.md 7-iii,
+    accel_18.py:204-213); ACCEL_FOLD_FC6=0 runs the two layers as written.  Both must sit inside the score tolerance
+    of the oracle (which always evaluates the graph as written) and agree with each other far inside it."""
+    params = synthetic.make_params(version)
+    with torch.no_grad():
+        rk = nets.key_forward(params, frames[0])
+        rc = nets.cur_forward(params, version, frames[1], frames[0], rk["res5c_relu_output"])
+    ref_score = rc[nets.output_key(version)]
+    scores = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("ACCEL_FOLD_FC6", fold)
+        eng = Engine(version, H, W, params=params)
+        dev = eng.torch_device
+        score = torch.empty(1, 19, H, W, device=dev)
+        label = torch.empty(H, W, dtype=torch.uint8, device=dev)
+        eng.cur_forward(frames[1].to(dev), frames[0].to(dev), rk["res5c_relu_output"].to(dev), None, score, label)
+        assert (score.cpu() - ref_score).abs().max().item() < SCORE_TOL
+        _label_check(label.cpu().numpy(), ref_score)
+        scores[fold] = score.cpu()
+        eng.close()
+    assert (scores["1"] - scores["0"]).abs().max().item() < 2e-4
