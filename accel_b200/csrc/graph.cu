@@ -814,6 +814,21 @@ bool Graph::finalize(std::string* err) {
       }
     }
   }
+  // score-level fusion directly followed by the tail: the band tail kernel applies `corr_weight` to its own source
+  // window, so the separate low-resolution launch is dropped (ACCEL_TAIL_FUSE=0 keeps it)
+  {
+    const char* tf = getenv("ACCEL_TAIL_FUSE");
+    if (!(tf && tf[0] == '0'))
+      for (auto& kv : seqs_) {
+        std::vector<Op>& ops = kv.second;
+        for (size_t i = 0; i + 1 < ops.size(); ++i) {
+          Op &f = ops[i], &t = ops[i + 1];
+          if (f.type != OP_FUSE || t.type != OP_TAIL || t.in != f.out || !tail_band_supported(t.tail.K, t.tail.factor)) continue;
+          f.skip = true;
+          t.tail.fuse_a = f.fuse.a; t.tail.fuse_b = f.fuse.b; t.tail.fuse_w = f.fuse.w;
+        }
+      }
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) {
     *err = std::string("CUDA error during finalize: ") + cudaGetErrorString(cudaGetLastError());
     return false;
@@ -1022,6 +1037,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
         ++launches;
         break;
       case OP_FUSE:
+        if (op.skip) break;                                  // evaluated inside the tail kernel that follows
         ce = launch_fuse_lowres(op.fuse, stream);
         ++launches;
         break;

@@ -73,6 +73,7 @@ struct Op {
   int engine = ENG_AUTO;
   std::string bn_in;         // stem: input BatchNorm (bn_data)
   int stem_pool = 0;
+  bool skip = false;         // OP_FUSE whose work the following band tail kernel does itself (TailParams::fuse_*)
   int src_warp = 0;          // OP_TO_SPLIT: read the warp op's fp32 output (caller's feat_out or the scratch)
   std::string split_bias;    // OP_TO_SPLIT: per-channel bias added + `split_act` applied during the conversion
   int split_act = 0;

@@ -136,7 +136,13 @@ struct TailParams {
   int factor;                // 16
   uint8_t* label;            // (h*factor, w*factor)
   float* score_out;          // fp32 planar (K, h*factor, w*factor) or nullptr
+  // optional: `score` = fuse_w (K, 2K) applied to concat(fuse_a, fuse_b) (FuseParams), evaluated inside the band
+  // kernel for each CTA's source window instead of by a launch of its own (only where tail_band_supported())
+  const float* fuse_a;
+  const float* fuse_b;
+  const float* fuse_w;
 };
+bool tail_band_supported(int K, int factor);
 cudaError_t launch_tail(const TailParams& P, cudaStream_t stream);
 
 // ---- frame ingest + metric (kernels_io.cu) ---------------------------------------------------------------

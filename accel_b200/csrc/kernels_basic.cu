@@ -447,20 +447,44 @@ __global__ void __launch_bounds__(256, MINB) tail_kernel(const TailParams P) {
 // CTA = 16 output rows x 512 columns; its 3 x 34 x KC source window is staged in shared memory (clamped indices, like
 // the kernel above: weights, not values, are zeroed beyond the map); thread = one quad column x 8 rows (one source-row
 // pair), 32 running (best, arg) pairs in registers; labels leave as uchar4, scores (parity mode) as float4.
-template <int KC, bool SCORES>
+// FUSE: the low-resolution scores are `fuse_w` (KC x 2KC, corr_weight) applied to concat(fuse_a, fuse_b) -- the
+// score-level fusion of accel_18.py:229-235 moved to feature resolution (fuse_lowres_kernel) -- evaluated here for the
+// CTA's own 3 x 34 source window, with that kernel's operation order (bit-identical), instead of by a separate launch.
+template <int KC, bool SCORES, bool FUSE>
 __global__ void __launch_bounds__(256, 2) tail_band_kernel(const TailParams P) {
   constexpr int F = 16, TW = 512, NC = TW / F + 2;
   __shared__ float ss[KC + 1][3][NC];                       // + one dummy class: the loop prefetches one ahead
   __shared__ float sbias[KC];
+  __shared__ float sraw[FUSE ? 2 * KC : 1][3 * NC];
+  __shared__ float sw[FUSE ? KC : 1][2 * KC];
   pdl_trigger();
+  if (FUSE)
+    for (int i = threadIdx.x; i < KC * 2 * KC; i += 256) sw[i / (2 * KC)][i % (2 * KC)] = P.fuse_w[i];
   pdl_wait();
   const int OW = P.w * F, OH = P.h * F;
   const int m = blockIdx.y, kc = blockIdx.x;
   const size_t plane = (size_t)P.h * P.w, oplane = (size_t)OH * OW;
-  for (int i = threadIdx.x; i < KC * 3 * NC; i += 256) {
-    const int c = i / (3 * NC), rem = i - c * 3 * NC, r = rem / NC, j = rem - r * NC;
-    const int sy = min(max(m - 1 + r, 0), P.h - 1), sx = min(max(kc * (TW / F) - 1 + j, 0), P.w - 1);
-    ss[c][r][j] = P.score[c * plane + (size_t)sy * P.w + sx];
+  if (FUSE) {
+    for (int i = threadIdx.x; i < 2 * KC * 3 * NC; i += 256) {
+      const int c = i / (3 * NC), rem = i - c * 3 * NC, r = rem / NC, j = rem - r * NC;
+      const int sy = min(max(m - 1 + r, 0), P.h - 1), sx = min(max(kc * (TW / F) - 1 + j, 0), P.w - 1);
+      const float* src = c < KC ? P.fuse_a + c * plane : P.fuse_b + (c - KC) * plane;
+      sraw[c][rem] = src[(size_t)sy * P.w + sx];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KC * 3 * NC; i += 256) {
+      const int c = i / (3 * NC), px = i - c * 3 * NC;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2 * KC; ++j) acc = fmaf(sw[c][j], sraw[j][px], acc);
+      (&ss[c][0][0])[px] = acc;
+    }
+  } else {
+    for (int i = threadIdx.x; i < KC * 3 * NC; i += 256) {
+      const int c = i / (3 * NC), rem = i - c * 3 * NC, r = rem / NC, j = rem - r * NC;
+      const int sy = min(max(m - 1 + r, 0), P.h - 1), sx = min(max(kc * (TW / F) - 1 + j, 0), P.w - 1);
+      ss[c][r][j] = P.score[c * plane + (size_t)sy * P.w + sx];
+    }
   }
   if (threadIdx.x < 3 * NC) ss[KC][threadIdx.x / NC][threadIdx.x % NC] = 0.f;
   if (threadIdx.x < KC) sbias[threadIdx.x] = P.bias ? P.bias[threadIdx.x] : 0.f;
@@ -666,6 +690,11 @@ cudaError_t launch_fuse_lowres(const FuseParams& P, cudaStream_t stream) {
   return launch_k(fuse_lowres_kernel, dim3((npix + 127) / 128), dim3(128), (size_t)P.K * 2 * P.K * sizeof(float), stream, P);
 }
 
+bool tail_band_supported(int K, int factor) {
+  const char* e = getenv("ACCEL_TAIL_BAND");
+  return !(e && e[0] == '0') && K == 19 && factor == 16;
+}
+
 cudaError_t launch_tail(const TailParams& P, cudaStream_t stream) {
   const int work = (P.w * P.factor / 4) * (P.h * P.factor);
   static int minb = -1, band = -1;
@@ -673,9 +702,13 @@ cudaError_t launch_tail(const TailParams& P, cudaStream_t stream) {
   if (band < 0) { const char* e = getenv("ACCEL_TAIL_BAND"); band = !(e && e[0] == '0'); }
   if (band && P.K == 19 && P.factor == 16) {
     const dim3 grid((P.w * 16 + 511) / 512, P.h);
-    return P.score_out ? launch_k(tail_band_kernel<19, true>, grid, dim3(256), 0, stream, P)
-                       : launch_k(tail_band_kernel<19, false>, grid, dim3(256), 0, stream, P);
+    if (P.fuse_w)
+      return P.score_out ? launch_k(tail_band_kernel<19, true, true>, grid, dim3(256), 0, stream, P)
+                         : launch_k(tail_band_kernel<19, false, true>, grid, dim3(256), 0, stream, P);
+    return P.score_out ? launch_k(tail_band_kernel<19, true, false>, grid, dim3(256), 0, stream, P)
+                       : launch_k(tail_band_kernel<19, false, false>, grid, dim3(256), 0, stream, P);
   }
+  if (P.fuse_w) return cudaErrorInvalidValue;              // only the band kernel evaluates the fusion itself
   if (P.K == 19 && minb == 4) return launch_k(tail_kernel<19, 4>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
   if (P.K == 19 && minb == 6) return launch_k(tail_kernel<19, 6>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
   if (P.K == 19) return launch_k(tail_kernel<19>, dim3((work + 255) / 256), dim3(256), 0, stream, P);
