@@ -529,17 +529,28 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
 
   const std::vector<float>* w = host_param(op.weight, err);
   if (!w) return false;
-  std::vector<__half> hi, lo;
-  std::vector<float> prescale;
-  pack_weights(w->data(), op.kind, op.cout, wcin, op.ksize, op.phase_y, op.phase_x, P.Cout_pad,
-               op.kind == 2 ? P.Cin_pad : P.Cin_pad, P.ntaps, hi, lo, prescale);
-  __half* dhi = (__half*)dev_alloc(hi.size() * sizeof(__half));
-  __half* dlo = (__half*)dev_alloc(lo.size() * sizeof(__half));
-  if (!dhi || !dlo) { *err = "out of device memory packing " + op.name; return false; }
-  cudaMemcpy(dhi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
-  cudaMemcpy(dlo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
-  P.w_hi = dhi;
-  P.w_lo = dlo;
+  // One packed device copy per (parameter, packing): the key / cur / cur_lin plans repeat FlowNet and the R branch,
+  // and Accel-101's correction net shares the key net's weights (accel_101.py:161) -- packing them once also lets
+  // concurrently running plans hit the same lines in L2.
+  const std::string pkey = op.weight + "|" + std::to_string(op.kind) + "|" + std::to_string(op.phase_y) + std::to_string(op.phase_x) +
+                           "|" + std::to_string(op.cout) + "|" + std::to_string(wcin) + "|" + std::to_string(op.ksize) + "|" +
+                           std::to_string(P.Cout_pad) + "|" + std::to_string(P.Cin_pad) + "|" + std::to_string(P.ntaps);
+  auto pit = packed_.find(pkey);
+  if (pit == packed_.end()) {
+    PackedWeights pw;
+    std::vector<__half> hi, lo;
+    pack_weights(w->data(), op.kind, op.cout, wcin, op.ksize, op.phase_y, op.phase_x, P.Cout_pad,
+                 op.kind == 2 ? P.Cin_pad : P.Cin_pad, P.ntaps, hi, lo, pw.prescale);
+    pw.hi = (__half*)dev_alloc(hi.size() * sizeof(__half));
+    pw.lo = (__half*)dev_alloc(lo.size() * sizeof(__half));
+    if (!pw.hi || !pw.lo) { *err = "out of device memory packing " + op.name; return false; }
+    cudaMemcpy(pw.hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    cudaMemcpy(pw.lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    pit = packed_.emplace(pkey, std::move(pw)).first;
+  }
+  const std::vector<float>& prescale = pit->second.prescale;
+  P.w_hi = pit->second.hi;
+  P.w_lo = pit->second.lo;
 
   Epilogue& E = P.epi;
   E = Epilogue{};
@@ -834,6 +845,7 @@ bool Graph::finalize(std::string* err) {
     return false;
   }
   host_.clear();
+  for (auto& kv : packed_) std::vector<float>().swap(kv.second.prescale);
   finalized_ = true;
   return true;
 }

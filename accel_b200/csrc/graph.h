@@ -186,6 +186,8 @@ class Graph {
   std::vector<const Op*> event_op_;
   std::vector<std::pair<std::string, float>> times_;
   std::vector<std::string> bilinear_checks_;
+  struct PackedWeights { __half* hi = nullptr; __half* lo = nullptr; std::vector<float> prescale; };
+  std::map<std::string, PackedWeights> packed_;          // device copies of packed conv weights, shared between plans
   struct FoldSpec { std::string out, deconv, conv1x1; int cin, mid, cout; };
   std::vector<FoldSpec> folds_;          // derived parameters: out = conv1x1 o deconv, computed at finalize
   int label_scratch_ = -1;
