@@ -56,19 +56,25 @@ struct alignas(64) TcParams {
   int tma_out;     // 1: the main output leaves through shared memory + TMA tensor stores (3-D map), 2: 5-D map (transposed-conv phase)
   int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = no TMA stores
   int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
+  int fused;       // split-K only: the CTA that delivers a tile's LAST partial slab sums the slabs (in split order) and
+                   // runs the epilogue itself -- no splitk_epilogue_kernel launch (ACCEL_TC_FUSED_SPLITK)
+  unsigned* counters;   // fused: arrivals per output tile, self-resetting (behind the partial slabs)
   int8_t dy[kMaxTaps];
   int8_t dx[kMaxTaps];
 };
 
 
 // NCAT: hi*hi and hi*lo issued as ONE MMA over [B_hi ; B_lo] (N = 2*BN <= 256), see the MMA issuer.
-template <bool NCAT>
+// FUSED: in-kernel split-K tail (TcParams::fused); a template parameter so that the default instantiations keep their
+// register allocation.
+template <bool NCAT, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float epi_sc[2][2][256];          // [accumulator][scale | shift][channel of the tile]
   __shared__ __align__(8) uint64_t res_bars[4];              // TMA epilogue: residual landed in staging buffer [chunk set][buffer]
+  __shared__ int s_last;                                     // fused split-K: this CTA delivered the tile's last slab
 
   // operand ring: [stage][A_hi | A_lo | B_hi | B_lo]
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -368,6 +374,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
       if (++acc == 2) { acc = 0; accph ^= 1; }
+      if (FUSED) {
+        // Deterministic in-kernel split-K tail (the threadFenceReduction pattern): every epilogue thread fences its
+        // slab stores, one thread counts the tile's arrivals, and the CTA that arrives last sums all slabs in split
+        // order -- the same order and operations as splitk_epilogue_kernel, so the result is bit-identical -- and
+        // applies the epilogue.  Nobody waits for anybody: no deadlock with persistent CTAs.  s_last is rewritten
+        // only after the next item's `bar.sync 1` pair, so every thread has read it by then.
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          const unsigned old = atomicAdd(P.counters + tile, 1u);
+          const int last = old == (unsigned)(P.splits - 1);
+          if (last) P.counters[tile] = 0u;                    // every split has arrived: ready for the next launch
+          s_last = last;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (s_last) {
+          __threadfence();
+          if (valid) {
+            const size_t slab = (size_t)npix * P.Cout_pad;
+            for (int cc = cset * 32; cc < P.BN; cc += 64) {
+              const int n0 = nbase + cc;
+              if (n0 >= E.Cout) break;
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+              const float* src = P.partial + ((size_t)y * P.Wo + x) * P.Cout_pad + n0;
+              for (int sp = 0; sp < P.splits; ++sp, src += slab) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 t = __ldcg(reinterpret_cast<const float4*>(src) + q);
+                  v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                }
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (n0 + g * 8 < E.Cout) epilogue_store<8>(E, pix, n0 + g * 8, v + g * 8);
+            }
+          }
+        }
+      }
     }
     }
   }
@@ -750,6 +796,8 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   const int tiles = tiles_m * P.n_tiles;
   P.splits = splits;
   plan->partial_bytes = splits > 1 ? (size_t)splits * C.Ho * C.Wo * C.Cout_pad * sizeof(float) : 0;
+  P.fused = (splits > 1 && !P.pair && env_int("ACCEL_TC_FUSED_SPLITK", 0) != 0) ? 1 : 0;
+  if (P.fused) plan->partial_bytes += (size_t)tiles * sizeof(unsigned);          // arrival counters behind the slabs
   int items = tiles * splits;
   plan->grid = items < num_sms ? items : num_sms;
   if (P.pair) {
@@ -757,7 +805,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     const int ncl = items < num_sms / 2 ? items : num_sms / 2;
     plan->grid = 2 * ncl;
   }
-  plan->launches = splits > 1 ? 2 : 1;
+  plan->launches = (splits > 1 && !P.fused) ? 2 : 1;
   {
     auto al32 = [](const void* p) { return ((uintptr_t)p & 31) == 0; };
     const Epilogue& E = C.epi;
@@ -829,6 +877,8 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   if (first_time_on_device(ONCE_CONV_TC)) {
     cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -841,7 +891,15 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
 
 void tc_plan_destroy(TcPlan* plan) { delete plan; }
 size_t tc_plan_partial_bytes(const TcPlan* plan) { return plan->partial_bytes; }
-void tc_plan_set_partial(TcPlan* plan, float* partial) { plan->p.partial = partial; }
+void tc_plan_set_partial(TcPlan* plan, float* partial) {
+  TcParams& P = plan->p;
+  P.partial = partial;
+  if (P.fused) {
+    const size_t tiles = (size_t)P.tiles_x * P.tiles_y * P.n_tiles;
+    P.counters = reinterpret_cast<unsigned*>(partial + (size_t)P.splits * P.Ho * P.Wo * P.Cout_pad);
+    cudaMemset(P.counters, 0, tiles * sizeof(unsigned));
+  }
+}
 int tc_plan_launches(const TcPlan* plan) { return plan->launches; }
 
 cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_raw, cudaStream_t stream) {
@@ -849,10 +907,12 @@ cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_r
   if (ext_nchw) P.epi.out_nchw = ext_nchw;
   P.epi.raw_nchw = ext_raw;
   cudaError_t e = P.pair ? launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, 2u, P)
-                         : P.ncat ? launch_k(conv_tc_kernel<true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
-                                  : launch_k(conv_tc_kernel<false>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
+                  : P.fused ? (P.ncat ? launch_k(conv_tc_kernel<true, true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
+                                      : launch_k(conv_tc_kernel<false, true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P))
+                  : P.ncat ? launch_k(conv_tc_kernel<true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
+                           : launch_k(conv_tc_kernel<false>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
   if (e != cudaSuccess) return e;
-  if (P.splits > 1) return launch_splitk_epilogue(P.partial, P.splits, P.Ho * P.Wo, P.Cout_pad, P.Wo, P.epi, stream);
+  if (P.splits > 1 && !P.fused) return launch_splitk_epilogue(P.partial, P.splits, P.Ho * P.Wo, P.Cout_pad, P.Wo, P.epi, stream);
   return cudaSuccess;
 }
 
