@@ -138,6 +138,26 @@ def test_conv_layer_matches_torch(case, engine):
     assert (out - ref).abs().max().item() < _tol(ref)
 
 
+@pytest.mark.parametrize("case", [(2048, 1024, 8, 16, 1, 1, 0, 1), (512, 512, 2, 4, 3, 1, 1, 1), (1026, 2, 2, 4, 3, 1, 1, 1)])
+def test_fused_splitk_tail_is_bit_identical(case, monkeypatch):
+    """ACCEL_TC_FUSED_SPLITK=1 (the CTA that delivers a tile's last partial slab sums the slabs and runs the epilogue
+    itself; measured slower and off by default) must give exactly the bits of the two-launch split-K path:
+    same slabs, same summation order, same epilogue."""
+    cin, cout, h, w, k, s, p, d = case
+    x = _rand(1, cin, h, w, seed=40)
+    wt = _rand(cout, cin, k, k, seed=41, scale=(2.0 / (cin * k * k)) ** 0.5)
+    scale, shift = torch.rand(cout, generator=torch.Generator().manual_seed(42)) + 0.5, _rand(cout, seed=43, scale=0.1)
+    res = _rand(1, cout, (h + 2 * p - d * (k - 1) - 1) // s + 1, (w + 2 * p - d * (k - 1) - 1) // s + 1, seed=44)
+    outs = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("ACCEL_TC_FUSED_SPLITK", fused)
+        monkeypatch.setenv("ACCEL_TC_SPLITS", "4")
+        outs.append(E.conv_layer(x.to(DEV), wt, "conv", s, p, d, scale, shift, act=1, residual=res.to(DEV), engine=2).cpu())
+    assert torch.equal(outs[0], outs[1])
+    ref = F.relu(F.conv2d(x, wt, None, s, p, d) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+    assert (outs[1] - ref).abs().max().item() < _tol(ref)
+
+
 @pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("cin,cout,h,w", [(1024, 512, 2, 4), (386, 64, 8, 16), (512, 2048, 4, 8)])
 def test_deconv_layer_matches_torch(cin, cout, h, w, engine):
