@@ -137,12 +137,17 @@ class TestLoader:
                              "part of this path; decode at the configured scale" % (tuple(im.shape[:2]), (target, max_size)))
         return im
 
-    def get_batch(self):                                              # loader.py:278-303
+    def _ingest(self, rec, frameid):
+        """get_rpn_testbatch -> get_image -> transform (lib/utils/image.py:224-235) for one frame: the uint8 BGR
+        image goes to the device and `accel_preprocess` builds the fp32 `data` tensor there (no CPU path)."""
         from . import engine as E
+        im = self._frame_u8(rec, frameid).to(self.device, non_blocking=True)
+        return E.preprocess(im.contiguous(), None, tuple(float(m) for m in self.cfg.network.PIXEL_MEANS))
+
+    def get_batch(self):                                              # loader.py:278-303
         rec = self.roidb[self.cur_roidb_index]
         self.cur_seg_len = rec["frame_seg_len"]
-        im = self._frame_u8(rec, self.cur_frameid).to(self.device, non_blocking=True)
-        data = E.preprocess(im.contiguous(), None, tuple(float(m) for m in self.cfg.network.PIXEL_MEANS))
+        data = self._ingest(rec, self.cur_frameid)
         im_info = torch.tensor([[data.shape[2], data.shape[3], 1.0]], dtype=torch.float32)
         if self.key_frameid == self.cur_frameid:                      # key frame
             self.data_key = data.clone()
