@@ -2,7 +2,9 @@
 """Generates tests/golden/accel_<version>_128x256.npz from the CPU oracle (CPU only, ~2 min).
 
 The reference (SamvitJ/Accel) ships no golden vectors and MXNet cannot be imported here (SURVEY.md
-section 8c), so these fixtures pin the ORACLE: seeded synthetic weights (accel_b200/synthetic.py,
+section 8c).  This generator needs only the oracle; tests/golden/make_reference_wired.py is the one that wrote the
+committed files: it produces the same arrays from the REFERENCE'S OWN symbol files (executed on oracle/mxstub.py),
+after checking that they equal this oracle bit for bit.  These fixtures pin the ORACLE: seeded synthetic weights (accel_b200/synthetic.py,
 seed 0) and a 3-frame synthetic clip (stream 0) through oracle/schedule.py with the reference's
 chained loop (dff_deeplab/demo.py:228-250), interval 3.  Stored per frame: the uint8 label map, the
 low-resolution quantities that determine it (flow, fp16-rounded full score volume is too large, so
@@ -33,6 +35,11 @@ def golden_for(version):
     frames = synthetic.make_frames(FRAMES, H, W)
     with torch.no_grad():
         res = oracle_schedule.run(params, version, frames, INTERVAL, "chained", keep=("label", "score", "feat", "flow"))
+    return pack(res)
+
+
+def pack(res):
+    """Per-frame results (dicts with 'label', 'score', 'feat', optional 'flow') -> the arrays of one fixture file."""
     out = {"height": H, "width": W, "interval": INTERVAL, "sub": SUB}
     for i, r in enumerate(res):
         score = r["score"]

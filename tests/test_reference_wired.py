@@ -1,0 +1,104 @@
+"""Graph wiring PINNED against the reference's own code (CPU).
+
+tests/golden/make_reference_wired.py executes dff_deeplab/symbols/accel_{18,34,50,101}.py +
+resnet_v1_101_flownet_deeplab.py themselves (on oracle/mxstub.py, a stand-in for `mxnet.symbol` that evaluates with
+oracle/ops.py), checks the result against oracle/nets.py bit for bit, and writes the golden fixtures from that run.  Here:
+
+  * the committed accel_<v>_128x256.npz fixtures ARE the files that script wrote (SHA-256 of every array) -- so the GPU
+    golden tests (tests/test_golden.py) compare the CUDA path with outputs of the reference's own graph code;
+  * the C ABI enumerates exactly the arguments + auxiliary states of the reference's graphs, with the same shapes;
+  * output names are the reference's;
+  * where /root/reference is present (the build container; not the GPU box) the whole thing is re-executed live.
+
+What this does NOT pin is the arithmetic inside each MXNet operator ([MXNet-ext] in oracle/ops.py): MXNet itself is
+not available."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from accel_b200 import _lib, synthetic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF = "/root/reference"
+VERSIONS = ["dff", "18", "34", "50", "101"]
+W = np.load(os.path.join(GOLDEN, "reference_wired_128x256.npz"))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("version", VERSIONS)
+def test_committed_fixtures_are_the_reference_wired_run(version):
+    g = np.load(os.path.join(GOLDEN, "accel_%s_128x256.npz" % version))
+    keys = [k[len(version) + 5:] for k in W.files if k.startswith(version + "_sha_")]
+    assert sorted(keys) == sorted(g.files) and len(keys) >= 15
+    for k in keys:
+        assert _sha(g[k]) == str(W["%s_sha_%s" % (version, k)]), k
+
+
+@pytest.mark.parametrize("version", VERSIONS)
+def test_abi_parameters_are_the_reference_graphs_arguments(lib, version):
+    cfg = _lib.AccelConfig(_lib.VERSION_CODE[version], 128, 256, 19, 0, 0)
+    h = C.c_void_p()
+    assert lib.accel_create(C.byref(cfg), C.byref(h)) == 0, lib.accel_last_error(None)
+    got = {}
+    name, shape, ndim = C.c_char_p(), (C.c_int64 * 4)(), C.c_int()
+    for i in range(lib.accel_param_count(h)):
+        assert lib.accel_param_info(h, i, C.byref(name), shape, C.byref(ndim)) == 0
+        got[name.value.decode()] = "x".join(str(shape[j]) for j in range(ndim.value))
+    lib.accel_destroy(h)
+    want = dict(zip([str(n) for n in W[version + "_args"]], [str(s) for s in W[version + "_arg_shapes"]]))
+    want.update(zip([str(n) for n in W[version + "_auxs"]], [str(s) for s in W[version + "_aux_shapes"]]))
+    # the reference's graphs also carry nodes whose output nobody reads on this path (get_flownet's
+    # `Convolution5_scale`, ...flownet_deeplab.py:1805-1807): the checkpoint has them, the hot path does not need them
+    dead = {k for k in want if k.startswith("Convolution5_scale")}
+    missing = set(want) - dead - set(got)
+    extra = set(got) - set(want)
+    assert not missing and not extra, (sorted(missing)[:5], sorted(extra)[:5])
+    for k in got:
+        assert got[k] == want[k], (k, got[k], want[k])
+
+
+def test_output_names_are_the_reference_graphs():
+    for v in VERSIONS:
+        assert [str(x) for x in W[v + "_key_outputs"]] == ["data_key", "feat_key", "res5c_relu_output", "croped_score_output"]
+        score = "croped_score_output" if v in ("101", "dff") else "correction_output"
+        assert [str(x) for x in W[v + "_cur_outputs"]] == ["data_key", "warping_feat_output", score]
+
+
+def test_synthetic_parameters_cover_the_reference_inventory():
+    """accel_b200/synthetic.make_params (the weights every parity test and the bench use) names exactly what the
+    reference's graphs list, with the shapes the graphs imply."""
+    for v in VERSIONS:
+        p = synthetic.make_params(v)
+        names = [str(n) for n in W[v + "_args"]] + [str(n) for n in W[v + "_auxs"]]
+        shapes = [str(s) for s in W[v + "_arg_shapes"]] + [str(s) for s in W[v + "_aux_shapes"]]
+        for n, s in zip(names, shapes):
+            assert n in p and "x".join(str(int(x)) for x in p[n].shape) == s, n
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "dff_deeplab", "symbols")), reason="reference tree not present")
+@pytest.mark.parametrize("version", ["dff", "18", "101"])
+def test_reference_symbol_files_executed_live_equal_oracle(version):
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_reference_wired as M
+    from oracle import mxstub
+    from oracle import schedule as oracle_schedule
+    classes = mxstub.load_reference_symbols(REF)
+    params = synthetic.make_params(version)
+    frames = synthetic.make_frames(3, 128, 256)
+    key, cur, score_name = M.build(classes, version)
+    with torch.no_grad():
+        res = M.run_chained(key, cur, score_name, params, frames, 3)
+        orc = oracle_schedule.run(params, version, frames, 3, "chained", keep=("label", "score", "feat", "flow"))
+    for a, b in zip(res, orc):
+        assert torch.equal(a["score"], b["score"]) and torch.equal(a["feat"], b["feat"])
+        assert np.array_equal(np.asarray(a["label"]), np.asarray(b["label"]))
+        if a["flow"] is not None:
+            assert torch.equal(a["flow"], b["flow"])
