@@ -26,6 +26,8 @@ What IS pinned against the reference's own code, by executing it in the build co
   ``tests/golden/accel_<v>_128x256.npz`` are written from that run (``tests/golden/make_reference_wired.py``,
   ``tests/test_reference_wired.py``).  Layer order, parameter names and shapes, kernel / stride / pad / dilate /
   eps / fix_gamma / no_bias of every node and the output names are therefore the reference's, not a reading of it;
+  the same script runs the frame loop of the reference's ``dff_deeplab/demo.py`` (:165-256) itself over those graphs
+  and gets the same uint8 label maps;
 * the host-side functions around the graphs (``transform``, ``fast_hist``, ``per_class_iu``, ``getpallete``,
   ``im_segment``, ``TestLoader.next/get_batch``, the greedy video -> GPU split, ``load_param``):
   ``tests/golden/make_reference_vectors.py`` executes them and ``tests/test_reference_vectors.py`` compares.

@@ -83,6 +83,104 @@ def run_chained(key, cur, score_name, params, frames, interval):
     return out
 
 
+def run_reference_demo_loop(ref, key, cur, version, params, frames_u8, interval):
+    """Executes the frame loop of the reference's dff_deeplab/demo.py ITSELF -- from `data = []` (:165) through the
+    palettised save (:256): ingest with the reference's `resize` / `transform`, `data_key` = previous frame, warm-up,
+    key / cur dispatch on `idx % key_frame_interval`, `feat` carried through `im_segment`, argmax -> uint8 -- with
+    stand-ins only for what is absent here: cv2 (frames come from memory), MXNet NDArray / DataBatch / Predictor
+    (the predictor evaluates the reference-built graph through oracle/mxstub.py), PIL's Image (captures the arrays).
+    Returns the uint8 label maps the loop handed to `Image.fromarray`."""
+    import re
+    import types
+
+    import make_reference_vectors as RV              # the ast / exec helpers and the numpy-1 shim
+
+    lines = open(os.path.join(ref, "dff_deeplab/demo.py")).read().splitlines()
+    start = [i for i, l in enumerate(lines) if l.strip() == "data = []"][0]
+    end = [i for i, l in enumerate(lines) if "segmentation_result.save(" in l][0]
+    indent = len(lines[start]) - len(lines[start].lstrip())
+    code = "\n".join(l[indent:] for l in lines[start:end + 1]) + "\n"
+    code = re.sub(r"^(\s*)print (?!\()(.*)$", r"\1print(\2)", code, flags=re.M)         # Python 2 print statements
+
+    class ND:                                           # the slice of mx.nd.NDArray the loop touches
+        def __init__(self, t):
+            self.t = t
+
+        @property
+        def shape(self):
+            return tuple(self.t.shape)
+
+        def asnumpy(self):
+            return self.t.numpy()
+
+    class DataBatch:
+        def __init__(self, data, label, pad, index, provide_data, provide_label):
+            self.data, self.label, self.pad, self.index = data, label, pad, index
+            self.provide_data, self.provide_label = provide_data, provide_label
+
+    class Predictor:                                    # core/tester.py:22-35 over the reference-built graph
+        def __init__(self, symbol, data_names, label_names, context=None, max_data_shapes=None, provide_data=None,
+                     provide_label=None, arg_params=None, aux_params=None):
+            self.symbol, self.data_names = symbol, data_names
+            self.params = dict(arg_params)
+            self.params.update(aux_params)
+
+        def predict(self, batch):
+            feed = dict(self.params)
+            feed.update({k: v.t for k, v in zip(self.data_names, batch.data[0])})
+            with torch.no_grad():
+                out = self.symbol.eval_dict(feed)
+            return [RV.HasKeyDict((k, ND(v)) for k, v in out.items())]
+
+    captured = []
+
+    class _Img:
+        def __init__(self, a):
+            captured.append(np.array(a, copy=True))
+
+        def putpalette(self, p):
+            assert len(p) == 768
+
+        def save(self, path):
+            pass
+
+    aux_names = set(key.list_auxiliary_states()) | set(cur.list_auxiliary_states())
+    arg_params = {k: v for k, v in params.items() if k not in aux_names}
+    aux_params = {k: v for k, v in params.items() if k in aux_names}
+    names = ["frame_%06d.png" % i for i in range(len(frames_u8))]
+    by_name = dict(zip(names, [f.numpy() for f in frames_u8]))
+    cv2 = types.SimpleNamespace(IMREAD_COLOR=1, IMREAD_IGNORE_ORIENTATION=128, INTER_LINEAR=1,
+                                imread=lambda name, flags: by_name[name],
+                                resize=lambda im, a, b, fx, fy, interpolation: (im if fx == fy == 1.0 else None))
+    mx = types.SimpleNamespace(
+        nd=types.SimpleNamespace(array=lambda a: ND(torch.from_numpy(np.asarray(a, dtype=np.float32)))),      # float64 -> float32
+        io=types.SimpleNamespace(DataBatch=DataBatch), gpu=lambda i: ("gpu", i),
+        ndarray=types.SimpleNamespace(argmax=lambda x, axis: ND(torch.from_numpy(ops.argmax_channel(x.t).astype(np.float32)))))
+    h, w = frames_u8[0].shape[:2]
+    ns_cfg = types.SimpleNamespace
+    config = ns_cfg(SCALES=[(min(h, w), max(h, w))], network=ns_cfg(IMAGE_STRIDE=0, PIXEL_MEANS=np.array([103.06, 115.90, 123.15]),
+                                                                   DFF_FEAT_DIM=2048), TEST=ns_cfg(NMS=0.3))
+    img_ns = {"np": RV.np1, "cv2": cv2}
+    ns = {
+        "np": RV.np1, "mx": mx, "cv2": cv2, "xrange": range, "config": config, "image_names": names,
+        "os": types.SimpleNamespace(path=types.SimpleNamespace(exists=lambda p: True, split=os.path.split)),
+        "resize": RV._exec_function("lib/utils/image.py", "resize", img_ns),
+        "transform": RV._exec_function("lib/utils/image.py", "transform", img_ns),
+        "im_segment": RV._exec_function("dff_deeplab/core/tester.py", "im_segment", {}),
+        "getpallete": RV._exec_function("dff_deeplab/demo.py", "getpallete", {"np": RV.np1}),
+        "load_param": lambda prefix, epoch, process=False: ((arg_params, aux_params) if prefix.endswith("m1") else ({}, {})),
+        "cur_path": "/nowhere/", "model1": "m1", "model2": "m2", "Predictor": Predictor, "key_sym": key, "cur_sym": cur,
+        "gpu_nms_wrapper": lambda thresh, dev: None, "key_frame_interval": interval, "num_classes": 19,
+        "version": "101" if version == "dff" else version,    # DFF's score output is named like Accel-101's (demo.py:244)
+        "tic": lambda: None, "toc": lambda: 0.0, "Image": types.SimpleNamespace(fromarray=_Img), "output_dir": "/nowhere",
+    }
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(code, "dff_deeplab/demo.py:%d-%d" % (start + 1, end + 1), "exec"), ns)
+    return captured
+
+
 def inventory(key, cur, params):
     args, auxs = [], []
     for s in (key, cur):
@@ -113,6 +211,17 @@ def main():
                                      % (version, i, k, (a[k] - b[k]).abs().max().item()))
             if not np.array_equal(np.asarray(a["label"]), np.asarray(b["label"])):
                 raise SystemExit("%s frame %d: label maps differ" % (version, i))
+        # the reference's own demo.py frame loop, executed over the same graphs from uint8 BGR frames, ends in the same
+        # uint8 label maps
+        frames_u8 = synthetic.make_frames_u8(FRAMES, H, W)
+        for f8, f in zip(frames_u8, frames):
+            assert torch.equal(synthetic.transform(f8), f)
+        demo_labels = run_reference_demo_loop(ref, key, cur, version, params, frames_u8, INTERVAL)
+        assert len(demo_labels) == FRAMES
+        for i, (lab, r) in enumerate(zip(demo_labels, res)):
+            if lab.dtype != np.uint8 or not np.array_equal(lab, np.asarray(r["label"])):
+                raise SystemExit("%s frame %d: demo.py's loop produced a different label map" % (version, i))
+        out["%s_demo_loop_frames" % version] = np.int64(len(demo_labels))
         g = make_golden.pack(res)
         np.savez_compressed(os.path.join(HERE, "accel_%s_%dx%d.npz" % (version, H, W)), **g)
         for k, a in g.items():

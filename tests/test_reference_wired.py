@@ -102,3 +102,31 @@ def test_reference_symbol_files_executed_live_equal_oracle(version):
         assert np.array_equal(np.asarray(a["label"]), np.asarray(b["label"]))
         if a["flow"] is not None:
             assert torch.equal(a["flow"], b["flow"])
+
+
+def test_fixture_records_the_demo_loop_check():
+    """make_reference_wired.py also executed the frame loop of the reference's dff_deeplab/demo.py (:165-256) over the
+    same graphs from uint8 frames and required its uint8 label maps to equal the fixtures'."""
+    for v in VERSIONS:
+        assert int(W[v + "_demo_loop_frames"]) == 3
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "dff_deeplab", "symbols")), reason="reference tree not present")
+def test_reference_demo_loop_executed_live_equals_scheduler_oracle():
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_reference_wired as M
+    from oracle import mxstub
+    from oracle import schedule as oracle_schedule
+    version, interval = "18", 2
+    classes = mxstub.load_reference_symbols(REF)
+    params = synthetic.make_params(version)
+    frames_u8 = synthetic.make_frames_u8(5, 128, 256, stream=1)
+    key, cur, _ = M.build(classes, version)
+    labels = M.run_reference_demo_loop(REF, key, cur, version, params, frames_u8, interval)
+    with torch.no_grad():
+        orc = oracle_schedule.run(params, version, [synthetic.transform(f) for f in frames_u8], interval, "chained")
+    assert len(labels) == 5
+    for lab, r in zip(labels, orc):
+        assert lab.dtype == np.uint8 and np.array_equal(lab, np.asarray(r["label"]))
+
