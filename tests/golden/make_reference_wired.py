@@ -94,6 +94,7 @@ def run_reference_demo_loop(ref, key, cur, version, params, frames_u8, interval)
     import types
 
     import make_reference_vectors as RV              # the ast / exec helpers and the numpy-1 shim
+    RV.REF = ref
 
     lines = open(os.path.join(ref, "dff_deeplab/demo.py")).read().splitlines()
     start = [i for i, l in enumerate(lines) if l.strip() == "data = []"][0]
