@@ -13,7 +13,7 @@ SYMBOLS = (
     "accel_create", "accel_destroy", "accel_last_error", "accel_param_count", "accel_param_info",
     "accel_set_param", "accel_finalize", "accel_key_forward", "accel_cur_forward", "accel_key_forward_lin",
     "accel_cur_forward_lin", "accel_flownet",
-    "accel_warp", "accel_fuse_argmax", "accel_preprocess", "accel_confusion", "accel_conv_layer", "accel_last_launch_count",
+    "accel_warp", "accel_fuse_argmax", "accel_preprocess", "accel_confusion", "accel_conv_layer", "accel_head", "accel_last_launch_count",
     "accel_set_profiling", "accel_stage_times", "accel_op_times",
 )
 
@@ -60,6 +60,7 @@ def load():
     lib.accel_confusion.argtypes = [u8p, u8p, C.c_size_t, ip, vp, vp]
     lib.accel_conv_layer.argtypes = [ip, vp, ip, ip, ip, vp, ip, ip, ip, ip, ip, ip, vp, vp, vp, ip, vp, ip, vp, ip,
                                      C.c_char_p, ip]
+    lib.accel_head.argtypes = [vp, ip, ip, ip, vp, vp, ip, vp, vp, ip, vp, ip, C.c_char_p, ip]
     lib.accel_last_launch_count.argtypes = [vp]
     lib.accel_set_profiling.argtypes = [vp, ip]
     lib.accel_stage_times.argtypes = [vp, C.POINTER(cp), fp, ip]

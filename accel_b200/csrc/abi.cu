@@ -415,3 +415,47 @@ extern "C" int accel_conv_layer(int kind, const float* in, int cin, int hin, int
     return fail("unknown C++ exception", 4);
   }
 }
+
+// Operator-level DeepLab head (SURVEY.md 8b `accel_head`): fc6 1x1 + bias + ReLU -> score 1x1 + bias at feature
+// resolution, through the same plan machinery and kernels the graphs use (two tcgen05 convs).
+extern "C" int accel_head(const float* feat, int cin, int height, int width, const float* fc6_weight, const float* fc6_bias,
+                          int mid, const float* score_weight, const float* score_bias, int num_classes, float* score_lowres,
+                          int device, char* err, int errlen) {
+  auto fail = [&](const std::string& m, int code) {
+    if (err && errlen > 0) snprintf(err, errlen, "%s", m.c_str());
+    return code;
+  };
+  try {
+    if (!feat || !fc6_weight || !fc6_bias || !score_weight || !score_bias || !score_lowres) return fail("null argument", 1);
+    if (cin < 1 || mid < 1 || num_classes < 1 || height < 1 || width < 1) return fail("bad shape", 1);
+    if (no_device(err, errlen)) return 6;
+    Graph g(device, 0);
+    std::vector<Op>& s = g.seq("head");
+    const int x = g.new_tensor(cin, height, width);
+    g.to_split(s, X_DATA, x);
+    EpiSpec e1;
+    e1.bias = "fc6_bias";
+    e1.act = ACT_RELU;
+    const int y = g.conv(s, "head", x, "fc6", mid, 1, 1, 0, 1, e1);
+    EpiSpec e2;
+    e2.bias = "score_bias";
+    e2.act = ACT_NONE;
+    const int z = g.conv(s, "head", y, "score", num_classes, 1, 1, 0, 1, e2);
+    g.to_nchw(s, z, X_AUX_OUT);
+    std::string msg;
+    const int64_t w1[4] = {mid, cin, 1, 1}, b1[1] = {mid}, w2[4] = {num_classes, mid, 1, 1}, b2[1] = {num_classes};
+    const bool ok = g.set_param("fc6_weight", fc6_weight, w1, 4, &msg) && g.set_param("fc6_bias", fc6_bias, b1, 1, &msg) &&
+                    g.set_param("score_weight", score_weight, w2, 4, &msg) && g.set_param("score_bias", score_bias, b2, 1, &msg);
+    if (!ok) return fail(msg, 1);
+    void* ext[X_COUNT] = {nullptr};
+    ext[X_DATA] = (void*)feat;
+    ext[X_AUX_OUT] = score_lowres;
+    if (!g.run("head", ext, 0, &msg)) return fail(msg, 1);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()), 5);
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(e.what(), 3);
+  } catch (...) {
+    return fail("unknown C++ exception", 4);
+  }
+}

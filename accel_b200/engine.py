@@ -263,6 +263,28 @@ def confusion(pred, label, hist=None, num_classes=NUM_CLASSES):
     return hist
 
 
+def head(feat, fc6_weight, fc6_bias, score_weight, score_bias):
+    """accel_head: ReLU(fc6(feat)) -> score at feature resolution (accel_18.py:177-191); feat (1,C,h,w) CUDA fp32, the four
+    parameters host or device tensors in MXNet layout.  Returns the (1,K,h,w) low-resolution score map."""
+    lib = _lib.load()
+    _, cin, h, w = feat.shape
+    host = lambda t: np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32)
+    w1, b1, w2, b2 = host(fc6_weight), host(fc6_bias), host(score_weight), host(score_bias)
+    mid, k = w1.shape[0], w2.shape[0]
+    if w1.shape[1] != cin or w2.shape[1] != mid or b1.shape != (mid,) or b2.shape != (k,):
+        raise ValueError("accel_head: inconsistent parameter shapes")
+    out = torch.empty(1, k, h, w, device=feat.device)
+    err = C.create_string_buffer(512)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    with torch.cuda.device(feat.device):
+        torch.cuda.synchronize()
+        rc = lib.accel_head(_ptr(feat.contiguous()), cin, h, w, p(w1), p(b1), mid, p(w2), p(b2), k, _ptr(out),
+                            feat.device.index or 0, err, 512)
+    if rc != 0:
+        raise RuntimeError("accel_head failed: %s" % err.value.decode())
+    return out
+
+
 def conv_layer(x, weight, kind="conv", stride=1, pad=0, dilate=1, scale=None, shift=None, act=0, residual=None,
                offset=None, deform_groups=1, engine=0):
     """One layer through the library's kernels (parity-test hook, accel_conv_layer)."""

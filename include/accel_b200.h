@@ -129,6 +129,17 @@ int accel_preprocess(const uint8_t* bgr_hwc, int height, int width, const double
 int accel_confusion(const uint8_t* pred, const uint8_t* label, size_t count, int num_classes, int64_t* hist,
                     void* stream);
 
+/* The DeepLab task head at feature resolution, accel_18.py:177-191 (L branch) / :208-221 (R branch):
+ *   relu_fc6 = ReLU(Convolution(feat, fc6_weight (mid,cin,1,1), fc6_bias)),  score = Convolution(relu_fc6,
+ *   score_weight (num_classes,mid,1,1), score_bias)
+ * feat (1,cin,height,width) and score_lowres (1,num_classes,height,width) are fp32 NCHW in DEVICE memory, the four
+ * parameter arrays HOST memory in MXNet layout.  The x16 `upsampling` + Crop + argmax that follow are
+ * accel_fuse_argmax.  Builds and runs a two-layer plan on the fly (operator-level entry point: weights are packed
+ * per call; the whole-graph entry points keep them resident). */
+int accel_head(const float* feat, int cin, int height, int width, const float* fc6_weight, const float* fc6_bias, int mid,
+               const float* score_weight, const float* score_bias, int num_classes, float* score_lowres, int device,
+               char* err, int errlen);
+
 /* One convolution-like layer through the same kernels the graphs use; parity-test hook.
  *   kind: 0 Convolution, 1 Deconvolution(k4,s2,p1 after crop), 2 DeformableConvolution(3x3,s1),
  *         3 the 7x7/s2/p3 stem over one fp32 NCHW frame (cin 3), 4 FlowNet's stem over the frame pair

@@ -74,6 +74,9 @@ def test_no_cpu_fallback(lib):
     assert b"no CUDA device" in lib.accel_last_error(h) or b"never set" in lib.accel_last_error(h)
     buf = (C.c_float * 16)()
     assert lib.accel_warp(buf, buf, (C.c_float * 16)(), 1, 2, 2, None) != 0
+    err = C.create_string_buffer(256)
+    assert lib.accel_head(buf, 4, 2, 2, buf, buf, 2, buf, buf, 2, buf, 0, err, 256) == 6 and b"CUDA" in err.value
+    assert lib.accel_conv_layer(0, buf, 1, 4, 4, buf, 1, 1, 1, 0, 1, 1, None, None, None, 0, None, 0, buf, 0, err, 256) == 6
     lib.accel_destroy(h)
     from accel_b200.engine import Engine
     with pytest.raises(RuntimeError):

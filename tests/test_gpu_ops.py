@@ -103,6 +103,17 @@ def test_tail_ties_take_lowest_class():
     assert np.all(label0 == 0)
 
 
+# ----------------------------------------------------------------------------- task head (a3 / a7)
+@pytest.mark.parametrize("cin,mid,k,h,w", [(2048, 1024, 19, 8, 16), (512, 256, 19, 5, 7)])
+def test_head_matches_torch(cin, mid, k, h, w):
+    feat = F.relu(_rand(1, cin, h, w, seed=50))
+    w1, b1 = _rand(mid, cin, 1, 1, seed=51, scale=(2.0 / cin) ** 0.5), _rand(mid, seed=52, scale=0.1)
+    w2, b2 = _rand(k, mid, 1, 1, seed=53, scale=(2.0 / mid) ** 0.5), _rand(k, seed=54, scale=0.1)
+    ref = F.conv2d(F.relu(F.conv2d(feat, w1, b1)), w2, b2)
+    out = E.head(feat.to(DEV), w1, b1, w2, b2).cpu()
+    assert out.shape == ref.shape and (out - ref).abs().max().item() < _tol(ref)
+
+
 # ----------------------------------------------------------------------------- conv engines (a1, a3-a9)
 CONV_CASES = [
     # cin, cout, h, w, k, stride, pad, dil
