@@ -130,3 +130,28 @@ def test_reference_demo_loop_executed_live_equals_scheduler_oracle():
     for lab, r in zip(labels, orc):
         assert lab.dtype == np.uint8 and np.array_equal(lab, np.asarray(r["label"]))
 
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "dff_deeplab", "symbols")), reason="reference tree not present")
+def test_operator_defaults_the_reference_graphs_rely_on():
+    """The stub fills MXNet's documented defaults where the reference omits an argument.  On the inference graphs that
+    happens only for: Convolution no_bias=False / stride 1 / pad 0, Deconvolution pad 0, Concat dim=1 and
+    pooling_convention='valid' on the two unnamed max pools of the R18/R34 trunks -- never for BatchNorm's eps /
+    fix_gamma, Deconvolution's no_bias, LeakyReLU's slope or anything of DeformableConvolution."""
+    from oracle import mxstub
+    classes = mxstub.load_reference_symbols(REF)
+    cfg = mxstub.reference_config()
+    relied = set()
+    for v in ("18", "34", "50", "101"):
+        inst = classes[v]()
+        for sym in (inst.get_key_test_symbol(cfg), inst.get_cur_test_symbol(cfg)):
+            for n in sym._walk():
+                a = n.attrs
+                need = {"BatchNorm": ("eps", "fix_gamma"), "Convolution": ("no_bias", "stride", "pad", "kernel", "num_filter"),
+                        "Deconvolution": ("no_bias", "pad", "stride", "kernel", "num_filter"), "Pooling": ("pooling_convention", "kernel", "stride", "pool_type"),
+                        "DeformableConvolution": ("no_bias", "stride", "pad", "dilate", "kernel", "num_filter", "num_deformable_group"),
+                        "LeakyReLU": ("slope", "act_type"), "Concat": ("dim",), "Crop": ("offset",),
+                        "GridGenerator": ("transform_type",), "Activation": ("act_type",)}.get(n.op, ())
+                relied |= {(n.op, k) for k in need if k not in a}
+    assert relied == {("Convolution", "no_bias"), ("Convolution", "stride"), ("Convolution", "pad"), ("Deconvolution", "pad"),
+                      ("Concat", "dim"), ("Pooling", "pooling_convention")}, relied
+
