@@ -83,13 +83,35 @@ def run_chained(key, cur, score_name, params, frames, interval):
     return out
 
 
-def run_reference_demo_loop(ref, key, cur, version, params, frames_u8, interval):
+def _py2_prints(code):
+    """`print x` -> `print(x)`, including statements that continue over several lines inside open parentheses."""
+    out, lines, i = [], code.split("\n"), 0
+    while i < len(lines):
+        line = lines[i]
+        body = line.lstrip()
+        if body.startswith("print ") and not body.startswith("print ("):
+            stmt = body[len("print "):]
+            depth = stmt.count("(") - stmt.count(")")
+            while depth > 0 and i + 1 < len(lines):
+                i += 1
+                stmt += "\n" + lines[i]
+                depth += lines[i].count("(") - lines[i].count(")")
+            out.append(line[:len(line) - len(body)] + "print(" + stmt + ")")
+        else:
+            out.append(line)
+        i += 1
+    return "\n".join(out)
+
+
+def run_reference_demo_loop(ref, key, cur, version, params, frames_u8, interval, gt_labels=None):
     """Executes the frame loop of the reference's dff_deeplab/demo.py ITSELF -- from `data = []` (:165) through the
     palettised save (:256): ingest with the reference's `resize` / `transform`, `data_key` = previous frame, warm-up,
     key / cur dispatch on `idx % key_frame_interval`, `feat` carried through `im_segment`, argmax -> uint8 -- with
     stand-ins only for what is absent here: cv2 (frames come from memory), MXNet NDArray / DataBatch / Predictor
     (the predictor evaluates the reference-built graph through oracle/mxstub.py), PIL's Image (captures the arrays).
-    Returns the uint8 label maps the loop handed to `Image.fromarray`."""
+    Returns the uint8 label maps the loop handed to `Image.fromarray`.  With `gt_labels` (one (H,W) uint8 array or None
+    per frame) the rest of main() runs too (:258-282: label matching by file name, `fast_hist`, `hist += curr_hist`, the
+    per-frame / cumulative / final mIoU prints) and (label maps, hist, printed lines) is returned."""
     import re
     import types
 
@@ -99,9 +121,11 @@ def run_reference_demo_loop(ref, key, cur, version, params, frames_u8, interval)
     lines = open(os.path.join(ref, "dff_deeplab/demo.py")).read().splitlines()
     start = [i for i, l in enumerate(lines) if l.strip() == "data = []"][0]
     end = [i for i, l in enumerate(lines) if "segmentation_result.save(" in l][0]
+    if gt_labels is not None:
+        end = [i for i, l in enumerate(lines) if l.strip() == "print 'done'"][0] - 1
     indent = len(lines[start]) - len(lines[start].lstrip())
     code = "\n".join(l[indent:] for l in lines[start:end + 1]) + "\n"
-    code = re.sub(r"^(\s*)print (?!\()(.*)$", r"\1print(\2)", code, flags=re.M)         # Python 2 print statements
+    code = _py2_prints(code)                                                            # Python 2 print statements
 
     class ND:                                           # the slice of mx.nd.NDArray the loop touches
         def __init__(self, t):
@@ -145,10 +169,16 @@ def run_reference_demo_loop(ref, key, cur, version, params, frames_u8, interval)
         def save(self, path):
             pass
 
+    frame_name = lambda i: "aachen_%06d_%06d_leftImg8bit.png" % (i // 30, i)
+    label_name = lambda i: "aachen_%06d_%06d_gtFine_trainIds.png" % (i // 30, i)
+    gt_by_name = {}
+    if gt_labels is not None:
+        gt_by_name = {label_name(i): g for i, g in enumerate(gt_labels) if g is not None}
+
     aux_names = set(key.list_auxiliary_states()) | set(cur.list_auxiliary_states())
     arg_params = {k: v for k, v in params.items() if k not in aux_names}
     aux_params = {k: v for k, v in params.items() if k in aux_names}
-    names = ["frame_%06d.png" % i for i in range(len(frames_u8))]
+    names = [frame_name(i) for i in range(len(frames_u8))]
     by_name = dict(zip(names, [f.numpy() for f in frames_u8]))
     cv2 = types.SimpleNamespace(IMREAD_COLOR=1, IMREAD_IGNORE_ORIENTATION=128, INTER_LINEAR=1,
                                 imread=lambda name, flags: by_name[name],
@@ -173,13 +203,20 @@ def run_reference_demo_loop(ref, key, cur, version, params, frames_u8, interval)
         "cur_path": "/nowhere/", "model1": "m1", "model2": "m2", "Predictor": Predictor, "key_sym": key, "cur_sym": cur,
         "gpu_nms_wrapper": lambda thresh, dev: None, "key_frame_interval": interval, "num_classes": 19,
         "version": "101" if version == "dff" else version,    # DFF's score output is named like Accel-101's (demo.py:244)
-        "tic": lambda: None, "toc": lambda: 0.0, "Image": types.SimpleNamespace(fromarray=_Img), "output_dir": "/nowhere",
+        "tic": lambda: None, "toc": lambda: 0.0, "output_dir": "/nowhere",
+        "Image": types.SimpleNamespace(fromarray=_Img, open=lambda name: gt_by_name[name]),
+        "label_files": sorted(gt_by_name),
+        "fast_hist": RV._exec_function("dff_deeplab/demo.py", "fast_hist", {"np": RV.np1}),
+        "per_class_iu": RV._exec_function("dff_deeplab/demo.py", "per_class_iu", {"np": RV.np1}),
     }
     import contextlib
     import io
-    with contextlib.redirect_stdout(io.StringIO()):
+    printed = io.StringIO()
+    with contextlib.redirect_stdout(printed), np.errstate(divide="ignore", invalid="ignore"):
         exec(compile(code, "dff_deeplab/demo.py:%d-%d" % (start + 1, end + 1), "exec"), ns)
-    return captured
+    if gt_labels is None:
+        return captured
+    return captured, np.asarray(ns["hist"]), printed.getvalue().splitlines()
 
 
 def inventory(key, cur, params):

@@ -123,12 +123,25 @@ def test_reference_demo_loop_executed_live_equals_scheduler_oracle():
     params = synthetic.make_params(version)
     frames_u8 = synthetic.make_frames_u8(5, 128, 256, stream=1)
     key, cur, _ = M.build(classes, version)
-    labels = M.run_reference_demo_loop(REF, key, cur, version, params, frames_u8, interval)
+    rng = np.random.RandomState(0)
+    gts = [None, rng.randint(0, 19, (128, 256)).astype(np.uint8), None, rng.randint(0, 19, (128, 256)).astype(np.uint8), None]
+    gts[3][::3] = 255                                                  # Cityscapes ignore label
+    labels, hist, printed = M.run_reference_demo_loop(REF, key, cur, version, params, frames_u8, interval, gt_labels=gts)
     with torch.no_grad():
         orc = oracle_schedule.run(params, version, [synthetic.transform(f) for f in frames_u8], interval, "chained")
     assert len(labels) == 5
     for lab, r in zip(labels, orc):
         assert lab.dtype == np.uint8 and np.array_equal(lab, np.asarray(r["label"]))
+    # the accuracy tail of main() (:258-282): label matching, fast_hist accumulation, nanmean / round of the mIoU prints
+    from oracle import io as oio
+    mine = sum(oio.fast_hist(np.asarray(orc[i]["label"]).flatten(), gts[i].flatten(), 19) for i in (1, 3))
+    assert np.array_equal(mine, hist)
+    cum = [l for l in printed if l.startswith("(cum) mIoU")]
+    final = [l for l in printed if l.startswith("===> final mIoU")]
+    assert len(cum) == 2 and len(final) == 1
+    assert final[0] == "===> final mIoU {mIoU:.3f}".format(mIoU=oio.mean_iou(mine))
+    first = oio.fast_hist(np.asarray(orc[1]["label"]).flatten(), gts[1].flatten(), 19)
+    assert cum[0] == "(cum) mIoU {mIoU:.3f}".format(mIoU=oio.mean_iou(first))
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "dff_deeplab", "symbols")), reason="reference tree not present")
