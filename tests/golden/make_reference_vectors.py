@@ -17,6 +17,7 @@ Functions executed (file:line in the reference):
   im_segment                   dff_deeplab/core/tester.py:158-171
   TestLoader.next / get_batch  dff_deeplab/core/loader.py:259-303   (key_frame_flag stream, data_key bookkeeping)
   greedy video -> GPU split    dff_rfcn/function/test_rcnn.py:60-67
+  config + update_config       dff_deeplab/config/config.py on experiments/dff_deeplab/cfgs/dff_deeplab_vid_demo.yaml
   load_param, load_param_multi lib/utils/load_model.py:4-116          (whole module, `mxnet` replaced by a stub whose
                                                                       nd.load returns the dict the test also saves)
 """
@@ -241,6 +242,49 @@ def main():
         out["loadparam_%s_arg_vals" % tag] = numpy.array([arg[k] for k in sorted(arg)])
         out["loadparam_%s_aux_keys" % tag] = numpy.array(sorted(aux))
         out["loadparam_%s_aux_vals" % tag] = numpy.array([aux[k] for k in sorted(aux)])
+
+    # ---- dff_deeplab/config/config.py + experiments/dff_deeplab/cfgs/dff_deeplab_vid_demo.yaml ----------------------------
+    class EasyDict(dict):                              # easydict.EasyDict: attribute access, nested dicts converted
+        def __init__(self, d=None, **kw):
+            super().__init__()
+            for k, v in dict(d or {}, **kw).items():
+                self[k] = v
+
+        def __setitem__(self, k, v):
+            super().__setitem__(k, EasyDict(v) if isinstance(v, dict) and not isinstance(v, EasyDict) else v)
+
+        __setattr__ = __setitem__
+
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    import yaml as real_yaml
+    fake_easydict = types.ModuleType("easydict")
+    fake_easydict.EasyDict = EasyDict
+    fake_yaml = types.ModuleType("yaml")
+    fake_yaml.load = lambda f: real_yaml.safe_load(f)          # yaml.load(f) without a Loader is PyYAML < 6 API
+    saved = {k: sys.modules.get(k) for k in ("easydict", "yaml")}
+    sys.modules["easydict"], sys.modules["yaml"] = fake_easydict, fake_yaml
+    try:
+        ns = {"__name__": "ref_config"}
+        exec(compile(open(os.path.join(REF, "dff_deeplab/config/config.py")).read(), "dff_deeplab/config/config.py", "exec"), ns)
+        ns["update_config"](os.path.join(REF, "experiments/dff_deeplab/cfgs/dff_deeplab_vid_demo.yaml"))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    cfg = ns["config"]
+    out["config_SCALES"] = numpy.array(cfg.SCALES[0])
+    out["config_PIXEL_MEANS"] = numpy.array(cfg.network.PIXEL_MEANS, dtype=numpy.float64)
+    out["config_IMAGE_STRIDE"] = numpy.int64(cfg.network.IMAGE_STRIDE)
+    out["config_DFF_FEAT_DIM"] = numpy.int64(cfg.network.DFF_FEAT_DIM)
+    out["config_NUM_CLASSES"] = numpy.int64(cfg.dataset.NUM_CLASSES)
+    out["config_KEY_FRAME_INTERVAL"] = numpy.int64(cfg.TEST.KEY_FRAME_INTERVAL)
 
     path = os.path.join(HERE, "reference_host_vectors.npz")
     numpy.savez_compressed(path, **out)

@@ -144,3 +144,18 @@ def test_load_param_key_handling_equals_reference(tag, tmp_path):
         for k, v in zip(want_keys, want_vals):
             a = np.asarray(got[k])
             assert a.shape == (2, 3) and np.all(a == np.float32(v))
+
+
+# ---------------------------------------------------------------- dff_deeplab/config/config.py + dff_deeplab_vid_demo.yaml
+def test_default_config_equals_reference_config():
+    """The reference's config.py was executed on its own demo yaml (update_config); loader.default_config, the synthetic
+    generator, the engine constants and bench.py's defaults carry the same values."""
+    from accel_b200 import netspec
+    cfg = loader.default_config()
+    assert list(cfg.SCALES[0]) == [int(x) for x in G["config_SCALES"]]
+    assert np.array_equal(np.asarray(cfg.network.PIXEL_MEANS, dtype=np.float64), G["config_PIXEL_MEANS"])
+    assert tuple(synthetic.PIXEL_MEANS_BGR) == tuple(float(x) for x in G["config_PIXEL_MEANS"])
+    assert cfg.network.IMAGE_STRIDE == int(G["config_IMAGE_STRIDE"])
+    assert cfg.network.DFF_FEAT_DIM == netspec.FEAT_DIM == int(G["config_DFF_FEAT_DIM"])
+    assert cfg.dataset.NUM_CLASSES == netspec.NUM_CLASSES == int(G["config_NUM_CLASSES"])
+    assert cfg.TEST.KEY_FRAME_INTERVAL == int(G["config_KEY_FRAME_INTERVAL"])
