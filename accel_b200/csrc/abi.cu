@@ -15,6 +15,7 @@ using namespace accel;
 struct AccelHandle {
   std::vector<OpTime> ops;
   AccelConfig cfg;
+  int interval = 0;            // frames of the whole-interval plan (accel_plan_interval), 0 = not planned
   Graph* graph;
   std::string err;
   const char* stage_names[32];
@@ -176,6 +177,59 @@ extern "C" int accel_cur_forward_lin(AccelHandle* h, const float* data, const fl
   if (!h->graph->run("cur_lin", ext, (cudaStream_t)stream, &h->err)) return 1;
   return check_stream_error(h);
   ACCEL_CATCH(h)
+}
+
+extern "C" int accel_rbranch_forward(AccelHandle* h, const float* data, float* score_out, uint8_t* label_out, void* stream) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!data) { h->err = "accel_rbranch_forward: data is NULL"; return 1; }
+  if (h->cfg.version != ACCEL_VERSION_18 && h->cfg.version != ACCEL_VERSION_34 && h->cfg.version != ACCEL_VERSION_50) {
+    h->err = "accel_rbranch_forward: only Accel-18/34/50 carry a correction network with its own head";
+    return 1;
+  }
+  void* ext[X_COUNT] = {nullptr};
+  ext[X_DATA] = (void*)data;
+  ext[X_SCORE_OUT] = score_out;
+  ext[X_LABEL_OUT] = label_out;
+  if (!h->graph->run("rbranch", ext, (cudaStream_t)stream, &h->err)) return 1;
+  return check_stream_error(h);
+  ACCEL_CATCH(h)
+}
+
+extern "C" int accel_plan_interval(AccelHandle* h, int interval) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!build_interval(*h->graph, h->cfg.version, h->cfg.height, h->cfg.width, h->cfg.num_classes, interval, &h->err)) return 1;
+  h->interval = interval;
+  return 0;
+  ACCEL_CATCH(h)
+}
+
+extern "C" int accel_interval_forward(AccelHandle* h, const float* const* frames, float* const* score_out,
+                                      uint8_t* const* label_out, void* stream) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (h->interval < 2) { h->err = "accel_interval_forward: call accel_plan_interval before accel_finalize"; return 1; }
+  if (!frames || !label_out) { h->err = "accel_interval_forward: frames and label_out are required"; return 1; }
+  void* ext[X_COUNT] = {nullptr};
+  for (int t = 0; t < h->interval; ++t) {
+    if (!frames[t] || !label_out[t]) { h->err = "accel_interval_forward: NULL frame or label pointer"; return 1; }
+    ext[X_FRAME0 + t] = (void*)frames[t];
+    ext[X_LABEL0 + t] = label_out[t];
+    ext[X_SCORE0 + t] = score_out ? score_out[t] : nullptr;
+  }
+  if (!h->graph->run("interval", ext, (cudaStream_t)stream, &h->err)) return 1;
+  return check_stream_error(h);
+  ACCEL_CATCH(h)
+}
+
+extern "C" int accel_graph_cache_stats(const AccelHandle* h, uint64_t* hits, uint64_t* misses) {
+  if (!h || !hits || !misses) return 1;
+  unsigned long long a = 0, b = 0;
+  h->graph->cache_stats(&a, &b);
+  *hits = a;
+  *misses = b;
+  return 0;
 }
 
 extern "C" int accel_flownet(AccelHandle* h, const float* data, const float* data_key, float* flow_out, void* stream) {

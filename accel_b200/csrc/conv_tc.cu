@@ -56,6 +56,9 @@ struct alignas(64) TcParams {
   int tma_out;     // 1: the main output leaves through shared memory + TMA tensor stores (3-D map), 2: 5-D map (transposed-conv phase)
   int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = no TMA stores
   int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
+  int kchains;     // 2: the K slices of a tile alternate between the two TMEM accumulator buffers and the epilogue sums
+                   // them in fp32 (round-to-nearest): the tensor core's own accumulation truncates, so its error grows
+                   // with the number of accumulation steps per accumulator; long-K layers only
   int fused;       // split-K only: the CTA that delivers a tile's LAST partial slab sums the slabs (in split order) and
                    // runs the epilogue itself -- no splitk_epilogue_kernel launch (ACCEL_TC_FUSED_SPLITK)
   unsigned* counters;   // fused: arrivals per output tile, self-resetting (behind the partial slabs)
@@ -156,15 +159,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * P.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const int acc_cols = NCAT ? 2 * P.BN : P.BN;
+      const bool two = P.kchains == 2;
       int s = 0, acc = 0;
       uint32_t ph = 0, accph = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int split = item % P.splits;
         const int kb = (int)(((long long)P.kiters * split) / P.splits);
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
-        mbar_wait(tempty0 + 8 * acc, accph ^ 1);
+        if (two) {
+          mbar_wait(tempty0, accph ^ 1);
+          mbar_wait(tempty0 + 8, accph ^ 1);
+        } else {
+          mbar_wait(tempty0 + 8 * acc, accph ^ 1);
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(acc * acc_cols);
+        int q = 0;                                        // K slice counter of this item
         for (int it = kb; it < ke; ++it) {
           mbar_wait(full0 + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -172,15 +181,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint64_t ah = umma_desc(sa), al = umma_desc(sa + a_bytes);
           const uint64_t bh = umma_desc(sa + 2 * a_bytes), bl = umma_desc(sa + 2 * a_bytes + b_bytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
+          for (int k = 0; k < BK / 16; ++k, ++q) {
             const uint64_t adv = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes along K inside the swizzle atom
-            const uint32_t first = (it > kb || k > 0) ? 1u : 0u;
+            // two chains: even slices accumulate in buffer 0, odd slices in buffer 1 (half the steps and half the
+            // magnitude per accumulator); the epilogue adds the buffers in fp32
+            const uint32_t d = tmem_base + (uint32_t)((two ? (q & 1) : acc) * acc_cols);
+            const uint32_t first = (q >= (two ? 2 : 1)) ? 1u : 0u;
             if (NCAT) {
               // B_hi and B_lo are adjacent in the stage with one row pitch: a single N = 2*BN operand.  Columns
-              // [0, BN) collect hi*hi (+ lo*hi below), columns [BN, 2BN) collect hi*lo; the tensor core reads the
-              // A_hi slice once instead of twice and issues two instructions instead of three.
+              // [0, BN) collect hi*hi, columns [BN, 2BN) collect hi*lo and -- issued into the upper half alone --
+              // lo*hi: the small cross terms never touch the big accumulator, whose truncating additions are the
+              // dominant rounding error.  The tensor core reads the A_hi slice once and issues two instructions.
               umma_f16(d, ah + adv, bh + adv, idesc2, first);
-              umma_f16(d, al + adv, bh + adv, idesc, 1u);
+              umma_f16(d + (uint32_t)P.BN, al + adv, bh + adv, idesc, 1u);
             } else {
               umma_f16(d, ah + adv, bh + adv, idesc, first);
               umma_f16(d, ah + adv, bl + adv, idesc, 1u);
@@ -190,8 +203,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull0 + 8 * acc);                    // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; accph ^= 1; }
+        if (two) {
+          umma_commit(tfull0);                            // both accumulators complete -> epilogue
+          umma_commit(tfull0 + 8);
+          accph ^= 1;
+        } else {
+          umma_commit(tfull0 + 8 * acc);                  // accumulator complete -> epilogue
+          if (++acc == 2) { acc = 0; accph ^= 1; }
+        }
       }
     }
   } else {
@@ -220,7 +239,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tma_load_3d(dst, &P.r_hi, bar, nt2 * P.BN + cc2, x02, y02);
         tma_load_3d(dst + 8192u, &P.r_lo, bar, nt2 * P.BN + cc2, x02, y02);
       };
-      int acc = 0, n = 0;
+      const bool two = P.kchains == 2;
+      const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
+      int acc = 0, sci = 0, n = 0;                          // sci: scale/shift staging slot, alternates per item
       uint32_t accph = 0;
       if (leader && has_res && (int)blockIdx.x < items) issue_res(blockIdx.x, cset * 32, 0);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -234,13 +255,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (et < P.BN) {
           const int c = nbase + et;
           const bool in = c < E.Cout;
-          epi_sc[acc][0][et] = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
-          epi_sc[acc][1][et] = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
+          epi_sc[sci][0][et] = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
+          epi_sc[sci][1][et] = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        mbar_wait(tfull0 + 8 * acc, accph);
+        if (two) {
+          mbar_wait(tfull0, accph);
+          mbar_wait(tfull0 + 8, accph);
+        } else {
+          mbar_wait(tfull0 + 8 * acc, accph);
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * (NCAT ? 2 * P.BN : P.BN));
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (two ? 0u : (uint32_t)acc * acc_cols);
         for (int cc = cset * 32; cc < P.BN; cc += 64, ++n) {
           const int b = n & 1;
           const uint32_t sb = sb0 + (uint32_t)b * 16384u;
@@ -253,9 +279,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           float v[32];
           tmem_ld32(taddr + cc, v);
+          if (two) {                                         // second chain's big half first: big + big, then the small halves
+            float v2[32];
+            tmem_ld32(taddr + acc_cols + cc, v2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          }
           if (NCAT) {
             float v2[32];
             tmem_ld32(taddr + P.BN + cc, v2);
+            if (two) {
+              float v3[32];
+              tmem_ld32(taddr + acc_cols + P.BN + cc, v3);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v2[i] += v3[i];
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
           }
@@ -272,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dl[0]), "=r"(dl[1]), "=r"(dl[2]), "=r"(dl[3]) : "r"(a + 8192u));
             }
           }
-          if (valid) epilogue_chunk32(E, pix, nbase + cc, v, rc, &epi_sc[acc][0][cc], &epi_sc[acc][1][cc], false);
+          if (valid) epilogue_chunk32(E, pix, nbase + cc, v, rc, &epi_sc[sci][0][cc], &epi_sc[sci][1][cc], false);
           uint32_t wh[16], wl[16];
           split32_words(v, wh, wl);
           stage_row64(sb, r, wh);
@@ -292,8 +330,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-        if (++acc == 2) { acc = 0; accph ^= 1; }
+        sci ^= 1;
+        if (two) {
+          if (lane == 0) { mbar_arrive(tempty0); mbar_arrive(tempty0 + 8); }
+          accph ^= 1;
+        } else {
+          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+          if (++acc == 2) { acc = 0; accph ^= 1; }
+        }
       }
       if (leader) bulk_wait0();
     } else {
@@ -310,7 +354,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int npix = P.Ho * P.Wo;
     const int et = threadIdx.x - 64;                       // 0 .. 255 among the epilogue threads
     const Epilogue& E = P.epi;
-    int acc = 0;
+    const bool two = P.kchains == 2;
+    const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
+    int acc = 0, sci = 0;                                  // sci: scale/shift staging slot, alternates per item
     uint32_t accph = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = item % P.splits, tile = item / P.splits;
@@ -323,8 +369,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (P.splits == 1 && et < P.BN) {                    // this tile's scale / shift -> shared memory
         const int c = nbase + et;
         const bool in = c < E.Cout;
-        epi_sc[acc][0][et] = (in && P.epi.scale) ? __ldg(P.epi.scale + c) : 1.f;
-        epi_sc[acc][1][et] = (in && P.epi.shift) ? __ldg(P.epi.shift + c) : 0.f;
+        epi_sc[sci][0][et] = (in && P.epi.scale) ? __ldg(P.epi.scale + c) : 1.f;
+        epi_sc[sci][1][et] = (in && P.epi.shift) ? __ldg(P.epi.shift + c) : 0.f;
       }
       ResChunk rc{}, rc1{};
       if (use_res && valid) {
@@ -332,9 +378,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (cset * 32 + 64 < P.BN && nbase + cset * 32 + 96 <= E.Cout) load_res(E, pix, nbase + cset * 32 + 64, rc1);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");       // scale/shift visible to all epilogue warps
-      mbar_wait(tfull0 + 8 * acc, accph);
+      if (two) {
+        mbar_wait(tfull0, accph);
+        mbar_wait(tfull0 + 8, accph);
+      } else {
+        mbar_wait(tfull0 + 8 * acc, accph);
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * (NCAT ? 2 * P.BN : P.BN));
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (two ? 0u : (uint32_t)acc * acc_cols);
       for (int cc = cset * 32; cc < P.BN; cc += 64) {
         const int n0 = nbase + cc;
         if (n0 >= P.Cout_pad) break;
@@ -344,9 +395,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int i = 0; i < 32; ++i) v[i] = 1.f;
         } else {
           tmem_ld32(taddr + cc, v);
+          if (two) {
+            float v2[32];
+            tmem_ld32(taddr + acc_cols + cc, v2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          }
           if (NCAT) {
             float v2[32];
             tmem_ld32(taddr + P.BN + cc, v2);
+            if (two) {
+              float v3[32];
+              tmem_ld32(taddr + acc_cols + P.BN + cc, v3);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v2[i] += v3[i];
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
           }
@@ -360,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           } else if (P.vec32 && n0 + 32 <= E.Cout) {
-            epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[acc][0][cc], &epi_sc[acc][1][cc]);
+            epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[sci][0][cc], &epi_sc[sci][1][cc]);
           } else {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
@@ -372,8 +435,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-      if (++acc == 2) { acc = 0; accph ^= 1; }
+      sci ^= 1;
+      if (two) {
+        if (lane == 0) { mbar_arrive(tempty0); mbar_arrive(tempty0 + 8); }
+        accph ^= 1;
+      } else {
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
       if (FUSED) {
         // Deterministic in-kernel split-K tail (the threadFenceReduction pattern): every epilogue thread fences its
         // slab stores, one thread counts the tile's arrivals, and the CTA that arrives last sums all slabs in split
@@ -806,6 +875,14 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     plan->grid = 2 * ncl;
   }
   plan->launches = (splits > 1 && !P.fused) ? 2 : 1;
+  {
+    // Long K chains: split the accumulation over both TMEM buffers (TcParams::kchains).  ACCEL_TC_CHAINS: 0/1 never,
+    // 2 always, unset = when a split walks at least ACCEL_TC_CHAINS_MIN (6) K stages, i.e. 24 slices of 16.
+    const int mode = env_int("ACCEL_TC_CHAINS", -1);
+    const int kps = (P.kiters + splits - 1) / splits;
+    const bool want = mode == 2 || (mode < 0 && kps >= env_int("ACCEL_TC_CHAINS_MIN", 6));
+    P.kchains = (want && !P.pair && mode != 0 && mode != 1) ? 2 : 1;
+  }
   {
     auto al32 = [](const void* p) { return ((uintptr_t)p & 31) == 0; };
     const Epilogue& E = C.epi;

@@ -55,6 +55,15 @@ Graph::~Graph() {
   for (auto e : events_) cudaEventDestroy(e);
 }
 
+int Graph::num_sms_hint() const {
+  int n = 0, sms = 0;
+  if (cudaGetDeviceCount(&n) == cudaSuccess && device_ >= 0 && device_ < n &&
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_) == cudaSuccess && sms > 0)
+    return sms;
+  cudaGetLastError();
+  return 148;
+}
+
 int Graph::new_tensor(int C, int H, int W, bool f32) {
   Buffer b;
   Tensor t;
@@ -267,6 +276,25 @@ void Graph::warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, 
   cv.split_bias = bias;       // commuted L head: relu(warp(W*F) + fc6_bias) while converting
   cv.split_act = act;
   if (!bias.empty()) add_param(bias, {tensors_[out_split].C});
+  s.push_back(cv);
+}
+
+void Graph::warp_internal(std::vector<Op>& s, int src_f32, int flow_f32, int dst_f32, int out_split) {
+  Op op{};
+  op.type = OP_WARP;
+  op.stage = "warp";
+  op.name = "warping_feat";
+  op.in = flow_f32;
+  op.out = out_split;
+  op.src_f32 = src_f32;
+  op.dst_f32 = dst_f32;
+  s.push_back(op);
+  Op cv{};
+  cv.type = OP_TO_SPLIT;
+  cv.stage = "warp_to_head";
+  cv.name = "warping_feat(nchw->split)";
+  cv.src_f32 = dst_f32;
+  cv.out = out_split;
   s.push_back(cv);
 }
 
@@ -596,7 +624,8 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
   }
   if (eng == ENG_TC) {
     char msg[256] = {0};
-    const int sm_budget = (op.par_group && op.par_width > 1 && branches_enabled()) ? std::max(8, num_sms_ / op.par_width) : num_sms_;
+    const int sm_budget = op.sm_budget > 0 ? std::min(op.sm_budget, num_sms_)
+                          : (op.par_group && op.par_width > 1 && branches_enabled()) ? std::max(8, num_sms_ / op.par_width) : num_sms_;
     op.tc = tc_plan_create(P, sm_budget, msg, sizeof(msg));
     if (!op.tc) { *err = std::string("tcgen05 plan failed for ") + op.name + ": " + msg; return false; }
     const size_t pb = tc_plan_partial_bytes(op.tc);
@@ -729,7 +758,7 @@ bool Graph::finalize(std::string* err) {
           E.osy = E.osx = 1; E.OHf = to.H; E.OWf = to.W;
           if (use_tc) {
             char msg[256] = {0};
-            op.stem_tc = stem_tc_plan_create(S, dhi, dlo, num_sms_, msg, sizeof(msg));
+            op.stem_tc = stem_tc_plan_create(S, dhi, dlo, op.sm_budget > 0 ? std::min(op.sm_budget, num_sms_) : num_sms_, msg, sizeof(msg));
             if (!op.stem_tc) { *err = std::string("tcgen05 stem plan failed for ") + op.name + ": " + msg; return false; }
           }
           break;
@@ -767,6 +796,14 @@ bool Graph::finalize(std::string* err) {
         case OP_WARP: {
           const Tensor& tf = tensors_[op.in];
           WarpParams& Wp = op.warp;
+          if (op.src_f32 >= 0) {                               // whole-interval plan: internal fp32 source / destination
+            const Tensor& ts = tensors_[op.src_f32];
+            Wp.feat = bufs_[ts.buf].f;
+            Wp.out_nchw = bufs_[tensors_[op.dst_f32].buf].f;
+            Wp.flow = bufs_[tf.buf].f;
+            Wp.C = ts.C; Wp.H = tf.H; Wp.W = tf.W;
+            break;
+          }
           if (!warp_scratch_ && op.out >= 0) {
             const Tensor& to = tensors_[op.out];
             warp_scratch_ = (float*)dev_alloc((size_t)to.C * to.H * to.W * sizeof(float));
@@ -864,6 +901,7 @@ bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t
   for (auto& c : graph_cache_) {
     if (c.which == which && memcmp(c.ext, ext, sizeof(c.ext)) == 0) {
       c.stamp = ++graph_clock_;
+      ++cache_hits_;
       last_launches_ = c.launches;
       cudaError_t ce = cudaGraphLaunch(c.exec, stream);
       if (ce != cudaSuccess) { *err = std::string("cudaGraphLaunch failed: ") + cudaGetErrorString(ce); return false; }
@@ -874,6 +912,7 @@ bool Graph::run(const std::string& which, void* const ext[X_COUNT], cudaStream_t
     *err = "cudaStreamCreate failed";
     return false;
   }
+  ++cache_misses_;                                  // a new pointer set: one stream capture + instantiate (~100x a replay)
   cudaError_t ce = cudaStreamBeginCapture(capture_stream_, cudaStreamCaptureModeThreadLocal);
   if (ce != cudaSuccess) { *err = std::string("cudaStreamBeginCapture failed: ") + cudaGetErrorString(ce); return false; }
   const bool ok = run_eager(which, ext, capture_stream_, err);
@@ -1035,6 +1074,11 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
         break;
       case OP_WARP: {
         WarpParams Wp = op.warp;
+        if (op.src_f32 >= 0) {
+          ce = launch_warp(Wp, stream);
+          ++launches;
+          break;
+        }
         Wp.feat = (const float*)ext[op.ext_in0];
         Wp.out_nchw = op.ext_out != X_NONE ? (float*)ext[op.ext_out] : nullptr;
         if (!Wp.feat) { *err = "missing feat_key"; return false; }
@@ -1063,7 +1107,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
       }
       case OP_TO_SPLIT: {
         const Tensor& to = tensors_[op.out];
-        const float* src = (const float*)ext[op.ext_in0];
+        const float* src = op.src_f32 >= 0 ? bufs_[tensors_[op.src_f32].buf].f : (const float*)ext[op.ext_in0];
         if (!src && op.src_warp) src = warp_scratch_;
         if (!src) { *err = "missing input tensor"; return false; }
         ce = launch_nchw_to_split(src, to.C, to.H, to.W, bufs_[to.buf].hi + to.coff, bufs_[to.buf].lo + to.coff, to.ld,
@@ -1098,6 +1142,21 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
       cudaEventRecord(events_[ev++], stream);
       event_stage_.push_back(op.stage);
       event_op_.push_back(&op);
+    }
+    static const bool debug_sums = [] { const char* e = getenv("ACCEL_DEBUG_SUMS"); return e && e[0] == '1'; }();
+    if (debug_sums && op.out >= 0 && !tensors_[op.out].f32) {
+      // debugging aid: checksum of every op's split output (hi plane, real channels), printed in launch order
+      cudaStreamSynchronize(stream);
+      const Tensor& to = tensors_[op.out];
+      std::vector<__half> hbuf((size_t)to.H * to.W * to.ld);
+      cudaMemcpy(hbuf.data(), bufs_[to.buf].hi, hbuf.size() * sizeof(__half), cudaMemcpyDeviceToHost);
+      double sum = 0.0, asum = 0.0;
+      for (size_t px = 0; px < (size_t)to.H * to.W; ++px)
+        for (int c = 0; c < to.C; ++c) {
+          const double v = (double)__half2float(hbuf[px * to.ld + to.coff + c]);
+          sum += v; asum += fabs(v);
+        }
+      fprintf(stderr, "ACCEL_SUM %s/%s C=%d coff=%d ld=%d sum=%.6e abs=%.6e\n", op.stage.c_str(), op.name.c_str(), to.C, to.coff, to.ld, sum, asum);
     }
   }
   if (cur_group && (ce = join_all()) != cudaSuccess) { *err = std::string("join failed: ") + cudaGetErrorString(ce); return false; }

@@ -12,8 +12,13 @@
 
 namespace accel {
 
+constexpr int kMaxInterval = 16;     // frames of one key interval the whole-interval plan accepts
 enum Ext { X_NONE = 0, X_DATA, X_DATA_KEY, X_FEAT_KEY, X_FEAT_OUT, X_SCORE_OUT, X_LABEL_OUT, X_FLOW_OUT, X_AUX_IN,
-           X_AUX_OUT, X_G_KEY, X_G_OUT, X_COUNT };   // X_G_*: fc6's linear part W*F (1,1024,h,w) of the commuted L head
+           X_AUX_OUT, X_G_KEY, X_G_OUT,              // X_G_*: fc6's linear part W*F (1,1024,h,w) of the commuted L head
+           X_FRAME0,                                 // whole-interval plan: frame i of the interval = X_FRAME0 + i
+           X_LABEL0 = X_FRAME0 + kMaxInterval,       //   its label map
+           X_SCORE0 = X_LABEL0 + kMaxInterval,       //   its score volume (optional)
+           X_COUNT = X_SCORE0 + kMaxInterval };
 
 struct Tensor {
   int C = 0, H = 0, W = 0;
@@ -75,6 +80,9 @@ struct Op {
   int stem_pool = 0;
   bool skip = false;         // OP_FUSE whose work the following band tail kernel does itself (TailParams::fuse_*)
   int src_warp = 0;          // OP_TO_SPLIT: read the warp op's fp32 output (caller's feat_out or the scratch)
+  int src_f32 = -1;          // OP_WARP / OP_TO_SPLIT: internal fp32 planar source tensor (instead of an external pointer)
+  int dst_f32 = -1;          // OP_WARP: internal fp32 planar destination tensor (whole-interval plan: the chained features)
+  int sm_budget = 0;         // > 0: plan this op's persistent kernels for that many SMs (a chain of the whole-interval plan)
   std::string split_bias;    // OP_TO_SPLIT: per-channel bias added + `split_act` applied during the conversion
   int split_act = 0;
   const float* split_bias_dev = nullptr;
@@ -134,6 +142,8 @@ class Graph {
   void require_bilinear(const std::string& name, int num_classes);
   void warp(std::vector<Op>& s, int ext_feat, int flow_f32, int out_split, int ext_out, const std::string& bias = "",
             int act = 0);
+  // whole-interval plan: source and destination are internal fp32 planar tensors (the chained warped features)
+  void warp_internal(std::vector<Op>& s, int src_f32, int flow_f32, int dst_f32, int out_split);
   void upflow(std::vector<Op>& s, int flow_f32, const std::string& wname, const std::string& bname, int out_view);
   void fuse(std::vector<Op>& s, int a_f32, int b_f32, const std::string& wname, int out_f32);
   void tail(std::vector<Op>& s, int score_f32, const std::string& bias_name, int ext_label, int ext_score);
@@ -151,12 +161,14 @@ class Graph {
   bool run(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err);
   bool run_eager(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err);
   int last_launches() const { return last_launches_; }
+  void cache_stats(unsigned long long* hits, unsigned long long* misses) const { *hits = cache_hits_; *misses = cache_misses_; }
   void set_profiling(bool on) { profiling_ = on; }
   const std::vector<std::pair<std::string, float>>& stage_times();
   std::vector<OpTime> op_times();   // per launch group of the last profiled run
   const Tensor& tensor(int id) const { return tensors_[id]; }
   int flags() const { return flags_; }
   int num_sms() const { return num_sms_; }
+  int num_sms_hint() const;            // SM count of the handle's device when one is visible (before finalize), else 148
 
  private:
   bool resolve_conv(Op& op, std::string* err);
@@ -204,7 +216,8 @@ class Graph {
   std::vector<CachedGraph> graph_cache_;
   std::set<std::string> warmed_;
   cudaStream_t capture_stream_ = nullptr;
-  static constexpr int kMaxBranches = 5;
+  static constexpr int kMaxBranches = 2 * kMaxInterval;
+  unsigned long long cache_hits_ = 0, cache_misses_ = 0;
   cudaStream_t side_[kMaxBranches] = {nullptr};
   cudaEvent_t fork_ev_ = nullptr, join_ev_[kMaxBranches] = {nullptr};
   cudaStream_t lane_stream_ = nullptr;
@@ -222,5 +235,9 @@ class Graph {
 
 // Accel graphs (nets.cu)
 bool build_accel(Graph& g, int version, int H, int W, int num_classes, std::string* err);
+// Whole-interval plan "interval": key frame + (interval-1) chained cur frames issued as ONE launch sequence in which the
+// per-frame chains (R101 of the key frame, FlowNet of every frame pair, the correction branch of every cur frame) are
+// parallel branches, each planned for its share of the SMs (nets.cu).
+bool build_interval(Graph& g, int version, int H, int W, int num_classes, int interval, std::string* err);
 
 }  // namespace accel

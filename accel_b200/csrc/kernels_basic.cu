@@ -344,7 +344,9 @@ __global__ void __launch_bounds__(256) nchw_to_split_kernel(const float* __restr
   __syncthreads();
   const int pl = threadIdx.x >> 3, g = threadIdx.x & 7;
   const int p = p0 + pl;
-  if (p < npix && c0 + g * 8 < ld) {
+  // only the tensor's own channels (rounded up to the 8-channel store): the destination may be a channel view of a
+  // wider concat buffer whose other channels belong to another producer
+  if (p < npix && c0 + g * 8 < C && c0 + g * 8 < ld) {
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = tile[g * 8 + i][pl];
@@ -686,7 +688,7 @@ cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
 
 cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,
                                  cudaStream_t stream, const float* bias, int act) {
-  dim3 grid((H * W + 31) / 32, (ld + 63) / 64);
+  dim3 grid((H * W + 31) / 32, (C + 63) / 64);
   return launch_k(nchw_to_split_kernel, grid, dim3(256), 0, stream, src, C, H * W, hi, lo, ld, bias, act);
 }
 

@@ -34,9 +34,12 @@ EpiSpec bias_epi(const std::string& conv, int act) {
 }
 
 // ---- FlowNet-S -----------------------------------------------------------------------------------
-int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out) {
+// ext_cur / ext_ref: external slots of the frame pair; inner_branches = false: the refinement levels stay one chain
+// (whole-interval plan: the chain itself is a branch next to the other frames' chains)
+int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out, int ext_cur = X_DATA, int ext_ref = X_DATA_KEY,
+            bool inner_branches = true) {
   const std::string st = "flownet";
-  int r1 = g.stem(s, st, X_DATA, X_DATA_KEY, H, W, true, 1.0f / 255.0f, "", "flow_conv1", 6,
+  int r1 = g.stem(s, st, ext_cur, ext_ref, H, W, true, 1.0f / 255.0f, "", "flow_conv1", 6,
                   bias_epi("flow_conv1", ACT_LEAKY));
   const Tensor t1 = g.tensor(r1);                                   // (64, H/4, W/4)
   const int c5 = g.new_tensor(128 + 64 + 2, t1.H / 2, t1.W / 2);     // Concat5
@@ -65,7 +68,7 @@ int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out) {
     // x2 upsampling, and the four output phases of the feature deconvolution.  They write disjoint channel ranges
     // of the next concat buffer, so they run as parallel branches (forked streams -> parallel graph nodes), each
     // deconv phase planned for a quarter of the SMs.
-    const int grp = g.new_par_group();
+    const int grp = inner_branches ? g.new_par_group() : 0;
     const size_t i0 = s.size();
     g.conv(s, st, feat, flow_name, 2, 3, 1, 1, 1, fe);
     const size_t i1 = s.size();
@@ -76,7 +79,7 @@ int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out) {
     // plus the upsampling behind it): planned for a quarter of the SMs like the phases it took 89 us at level 2 while
     // the phases next to it took 41 us.  It is planned for half of the SMs instead (ACCEL_FLOWHEAD_WIDTH overrides).
     static const int head_width = [] { const char* e = getenv("ACCEL_FLOWHEAD_WIDTH"); return e && *e ? std::max(1, atoi(e)) : 2; }();
-    for (size_t i = i0; i < s.size(); ++i) {
+    for (size_t i = i0; inner_branches && i < s.size(); ++i) {
       s[i].par_group = grp;
       s[i].par_width = (i < i1) ? head_width : 4;
       if (i >= i1 && i < i2) s[i].par_branch = 1 + s[i].phase_y * 2 + s[i].phase_x;     // branches 1..4: deconv phases
@@ -108,10 +111,11 @@ struct DeformCfg {
   int off_ch, off_pad, off_dil, dg;
 };
 
+// ext_data: external slot of the frame; final_f32 >= 0: the last layer also writes that internal fp32 planar tensor
 int bottleneck_net(Graph& g, Seq& s, const std::string& st, int H, int W, const std::string& prefix,
                    const std::vector<std::vector<std::string>>& stage_units, DeformCfg d, int ext_feat_out,
-                   int final_out_view) {
-  int x = g.stem(s, st, X_DATA, X_NONE, H, W, false, 1.f, "", prefix + "conv1", 3, bn_epi(prefix + "bn_conv1", ACT_RELU));
+                   int final_out_view, int ext_data = X_DATA, int final_f32 = -1) {
+  int x = g.stem(s, st, ext_data, X_NONE, H, W, false, 1.f, "", prefix + "conv1", 3, bn_epi(prefix + "bn_conv1", ACT_RELU));
   x = g.pool(s, st, x, 3, 2, 0, true, true);                        // pool1: 3x3/s2, pooling_convention='full'
   const int mids[4] = {64, 128, 256, 512};
   for (int si = 0; si < 4; ++si) {
@@ -140,6 +144,7 @@ int bottleneck_net(Graph& g, Seq& s, const std::string& st, int H, int W, const 
       EpiSpec ce = bn_epi(b + "_branch2c", ACT_RELU);
       ce.res = sc;
       if (last) ce.ext_out = ext_feat_out;
+      if (last && final_f32 >= 0) ce.out_f32 = final_f32;
       x = g.conv(s, st, m, r + "_branch2c", 4 * mid, 1, 1, 0, 1, ce, last ? final_out_view : -1);
     }
   }
@@ -158,9 +163,9 @@ std::vector<std::vector<std::string>> units_50() {
 
 // ---- pre-activation basic-block trunk + deformable conv5 (Accel-18 / Accel-34 R branch) ----------------
 int preact_branch(Graph& g, Seq& s, const std::string& st, int H, int W, const std::string& pre,
-                  const std::vector<int>& units, const std::string& letters, bool fold_fc6) {
+                  const std::vector<int>& units, const std::string& letters, bool fold_fc6, int ext_data = X_DATA) {
   const float eps = 2e-5f;
-  int x = g.stem(s, st, X_DATA, X_NONE, H, W, false, 1.f, pre + "bn_data", pre + "conv0", 3,
+  int x = g.stem(s, st, ext_data, X_NONE, H, W, false, 1.f, pre + "bn_data", pre + "conv0", 3,
                  bn_epi(pre + "bn0", ACT_RELU, eps));
   // max pool, then stage1_unit1's bn1 + relu on the pooled map (unit 1 never reads the raw input:
   // its shortcut conv also takes act1, :80-81)
@@ -249,7 +254,135 @@ int head(Graph& g, Seq& s, const std::string& st, int feat, const std::string& f
   return sc;
 }
 
+// The correction ("R") network of Accel-18/34/50 with its own DeepLab head: returns the low-res fp32 score map
+// (accel_18.py:199-221, accel_50.py:195-216).  On its own it is the plain DeepLab-<v> segmentation net (BASELINE config 1).
+int rbranch_scores(Graph& g, Seq& s, int version, int H, int W, int K, bool fold_fc6, int ext_data = X_DATA) {
+  if (version == 50) {
+    int f = bottleneck_net(g, s, "rbranch", H, W, "50_", units_50(), DeformCfg{72, 2, 2, 4}, X_NONE, -1, ext_data);
+    return head(g, s, "rhead", f, "curr_fc6", "curr_score", "curr_upsampling", K);
+  }
+  const std::string pre = std::to_string(version) + "_";
+  int f = preact_branch(g, s, "rbranch", H, W, pre, version == 18 ? std::vector<int>{2, 2, 2} : std::vector<int>{3, 4, 6},
+                        version == 18 ? "ab" : "abc", fold_fc6, ext_data);
+  return head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K, X_NONE, fold_fc6);
+}
+
 }  // namespace
+
+// ---- whole-interval plan ------------------------------------------------------------------------------------
+// One key interval of the chained schedule (dff_deeplab/demo.py:228-250) as ONE launch sequence: frame 0 through the
+// key graph, frames 1..I-1 through the cur graph with data_key = the previous frame and feat_key = the previous
+// frame's (warped) feature.  Everything that depends on a frame alone -- R101 of the key frame, FlowNet of every
+// (frame, previous frame) pair, the correction network of every cur frame -- is an independent chain; the chains
+// are parallel branches of one section, each planned for a share of the SMs proportional to its flops, so the GPU
+// works on the whole interval's tiles at once instead of one small layer at a time (temporal batching; precedent:
+// dff_rfcn/demo_batch.py:76-96).  Only the flow-guided warps are sequential (warp_t reads warp_{t-1}); they and the
+// heads / fusion / tails that consume them follow the parallel section.
+bool build_interval(Graph& g, int version, int H, int W, int K, int interval, std::string* err) {
+  if (interval < 2 || interval > kMaxInterval) {
+    *err = "accel_plan_interval: interval must be in [2, " + std::to_string(kMaxInterval) + "]";
+    return false;
+  }
+  if (!g.seq("interval").empty()) { *err = "accel_plan_interval: already planned"; return false; }
+  if (g.finalized()) { *err = "accel_plan_interval must precede accel_finalize"; return false; }
+  const int h = H / 16, w = W / 16, I = interval;
+  const char* ff = getenv("ACCEL_FOLD_FC6");
+  const bool fold_fc6 = !(ff && ff[0] == '0');
+  Seq& s = g.seq("interval");
+  const int grp = g.new_par_group();
+  struct Chain { size_t begin, end; };
+  std::vector<Chain> chains;
+  auto close_chain = [&](size_t b) { chains.push_back({b, s.size()}); };
+
+  // chain 0: key frame -- R101-DCN, its head and its tail (get_key_test_symbol)
+  std::vector<int> feat(I);                                  // fp32 planar features: F_0 = res5c_relu, F_t = warp_t(F_{t-1})
+  for (int t = 0; t < I; ++t) feat[t] = g.new_tensor(2048, h, w, true);
+  {
+    const size_t b = s.size();
+    int f0 = bottleneck_net(g, s, "backbone", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_NONE, -1, X_FRAME0, feat[0]);
+    int sc = head(g, s, "head", f0, "fc6", "score", "upsampling", K);
+    g.tail(s, sc, "", X_LABEL0, X_SCORE0);
+    close_chain(b);
+  }
+  // FlowNet of every frame pair
+  std::vector<int> flow(I, -1);
+  for (int t = 1; t < I; ++t) {
+    const size_t b = s.size();
+    flow[t] = flownet(g, s, H, W, X_NONE, X_FRAME0 + t, X_FRAME0 + t - 1, false);
+    close_chain(b);
+  }
+  // correction network of every cur frame
+  std::vector<int> cat(I, -1), sr(I, -1);
+  for (int t = 1; t < I && version != 0; ++t) {
+    const size_t b = s.size();
+    if (version == 101) {
+      cat[t] = g.new_tensor(4096, h, w);
+      bottleneck_net(g, s, "rbranch", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_NONE, g.new_view(cat[t], 2048, 2048),
+                     X_FRAME0 + t);
+    } else {
+      sr[t] = rbranch_scores(g, s, version, H, W, K, fold_fc6, X_FRAME0 + t);
+    }
+    close_chain(b);
+  }
+  // SM shares proportional to the chains' flops
+  {
+    std::vector<double> fl(chains.size(), 0.0);
+    double total = 0.0;
+    for (size_t c = 0; c < chains.size(); ++c) {
+      for (size_t i = chains[c].begin; i < chains[c].end; ++i) fl[c] += s[i].flops;
+      total += fl[c];
+    }
+    const int sms = g.num_sms_hint();
+    const char* mb = getenv("ACCEL_IVL_MIN_SMS");
+    const int min_sms = mb && *mb ? std::max(1, atoi(mb)) : 8;
+    std::vector<int> share(chains.size());
+    int used = 0;
+    for (size_t c = 0; c < chains.size(); ++c) {
+      share[c] = std::max(min_sms, (int)(sms * fl[c] / total));
+      used += share[c];
+    }
+    // hand out / take back the rounding remainder, largest chains first
+    for (int guard = 0; used != sms && guard < 4 * sms; ++guard) {
+      size_t best = 0;
+      for (size_t c = 1; c < chains.size(); ++c)
+        if (fl[c] / share[c] > fl[best] / share[best]) best = c;
+      if (used < sms) { ++share[best]; ++used; continue; }
+      size_t worst = chains.size();
+      for (size_t c = 0; c < chains.size(); ++c)
+        if (share[c] > min_sms && (worst == chains.size() || fl[c] / share[c] < fl[worst] / share[worst])) worst = c;
+      if (worst == chains.size()) break;
+      --share[worst]; --used;
+    }
+    for (size_t c = 0; c < chains.size(); ++c)
+      for (size_t i = chains[c].begin; i < chains[c].end; ++i) {
+        s[i].par_group = grp;
+        s[i].par_branch = (int)c + 1;
+        s[i].par_width = 1;
+        s[i].sm_budget = share[c];
+      }
+  }
+  // sequential part: the chained warps and what consumes them
+  for (int t = 1; t < I; ++t) {
+    if (version == 101) {
+      g.warp_internal(s, feat[t - 1], flow[t], feat[t], g.new_view(cat[t], 0, 2048));
+      int fused = g.conv(s, "fusion", cat[t], "corr", 2048, 1, 1, 0, 1, bias_epi("corr", ACT_NONE));
+      int sc = head(g, s, "head", fused, "fc6", "score", "upsampling", K);
+      g.tail(s, sc, "", X_LABEL0 + t, X_SCORE0 + t);
+    } else {
+      const int warped = g.new_tensor(2048, h, w);
+      g.warp_internal(s, feat[t - 1], flow[t], feat[t], warped);
+      const int sl = head(g, s, "head", warped, "fc6", "score", "upsampling", K);
+      if (version == 0) {
+        g.tail(s, sl, "", X_LABEL0 + t, X_SCORE0 + t);
+      } else {
+        const int fused = g.new_tensor(K, h, w, true);
+        g.fuse(s, sl, sr[t], "corr", fused);
+        g.tail(s, fused, "corr_bias", X_LABEL0 + t, X_SCORE0 + t);
+      }
+    }
+  }
+  return true;
+}
 
 bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
   if (H <= 0 || W <= 0 || H % 128 || W % 128) {
@@ -300,18 +433,8 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
       if (version == 0) {
         g.tail(s, sl, "", X_LABEL_OUT, X_SCORE_OUT);
       } else {
-        int sr;
         const size_t r0 = s.size();                       // R branch + R head: a lane of its own (reads only `data`)
-        if (version == 50) {
-          int f = bottleneck_net(g, s, "rbranch", H, W, "50_", units_50(), DeformCfg{72, 2, 2, 4}, X_NONE, -1);
-          sr = head(g, s, "rhead", f, "curr_fc6", "curr_score", "curr_upsampling", K);
-        } else {
-          const std::string pre = std::to_string(version) + "_";
-          int f = preact_branch(g, s, "rbranch", H, W, pre,
-                                version == 18 ? std::vector<int>{2, 2, 2} : std::vector<int>{3, 4, 6},
-                                version == 18 ? "ab" : "abc", fold_fc6);
-          sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K, X_NONE, fold_fc6);
-        }
+        const int sr = rbranch_scores(g, s, version, H, W, K, fold_fc6);
         for (size_t i = r0; i < s.size(); ++i) s[i].lane = 1;
         const int fused = g.new_tensor(K, h, w, true);
         const size_t j0 = s.size();
@@ -336,18 +459,8 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
     if (version == 0) {
       g.tail(s, sl, "", X_LABEL_OUT, X_SCORE_OUT);
     } else {
-      int sr;
       const size_t r0 = s.size();
-      if (version == 50) {
-        int f = bottleneck_net(g, s, "rbranch", H, W, "50_", units_50(), DeformCfg{72, 2, 2, 4}, X_NONE, -1);
-        sr = head(g, s, "rhead", f, "curr_fc6", "curr_score", "curr_upsampling", K);
-      } else {
-        const std::string pre = std::to_string(version) + "_";
-        int f = preact_branch(g, s, "rbranch", H, W, pre,
-                              version == 18 ? std::vector<int>{2, 2, 2} : std::vector<int>{3, 4, 6},
-                              version == 18 ? "ab" : "abc", fold_fc6);
-        sr = head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K, X_NONE, fold_fc6);
-      }
+      const int sr = rbranch_scores(g, s, version, H, W, K, fold_fc6);
       for (size_t i = r0; i < s.size(); ++i) s[i].lane = 1;
       const int fused = g.new_tensor(K, h, w, true);
       const size_t j0 = s.size();
@@ -355,6 +468,12 @@ bool build_accel(Graph& g, int version, int H, int W, int K, std::string* err) {
       s[j0].join_lane = 1;
       g.tail(s, fused, "corr_bias", X_LABEL_OUT, X_SCORE_OUT);
     }
+  }
+  // the correction network on its own = plain DeepLab-<v> on one frame (accel_rbranch_forward; BASELINE config 1)
+  if (version == 18 || version == 34 || version == 50) {
+    Seq& s = g.seq("rbranch");
+    const int sr = rbranch_scores(g, s, version, H, W, K, fold_fc6);
+    g.tail(s, sr, "", X_LABEL_OUT, X_SCORE_OUT);
   }
   return true;
 }

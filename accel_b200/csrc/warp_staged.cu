@@ -12,6 +12,8 @@
 // NCHW rows are written coalesced.  Per-pixel tap offsets and bilinear weights are computed once per CTA and kept
 // in registers for all channels.  Arithmetic and operation order are those of the gather kernel (and the oracle):
 // the result is bit-identical.  When the band does not fit (wild flow fields), the CTA gathers from global memory.
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -247,16 +249,33 @@ cudaError_t launch_warp_staged(const WarpParams& P, cudaStream_t stream) {
   const int W = P.W, H = P.H;
   if (W < 8 || (W & 3) || W > WS_TILE) return cudaErrorNotSupported;
   if (((uintptr_t)P.feat & 15) != 0) return cudaErrorNotSupported;
-  static int max_smem = 0, sms = 0, threads = 512, cb = 4, stage_cap = 0, th_cap = 0;
-  if (!max_smem) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    threads = env_int("ACCEL_WARP_THREADS", 512);          // tuning aids (tools/bench_warp.py)
-    cb = env_int("ACCEL_WARP_CB", 4);
-    stage_cap = env_int("ACCEL_WARP_RMAX", 0);
-    th_cap = env_int("ACCEL_WARP_TH", 0);
+  // per-device launch configuration, filled once per device under a lock (several GPUs may be driven from the threads
+  // of one process: loader.pred_eval_multiprocess)
+  struct DevCfg { int max_smem = 0, sms = 0; };
+  static std::mutex mu;
+  static DevCfg cfgs[64];
+  static int threads = 512, cb = 4, stage_cap = 0, th_cap = 0;
+  static bool env_read = false;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorNotSupported;
+  int max_smem, sms;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!env_read) {
+      threads = env_int("ACCEL_WARP_THREADS", 512);          // tuning aids (tools/bench_warp.py)
+      cb = env_int("ACCEL_WARP_CB", 4);
+      stage_cap = env_int("ACCEL_WARP_RMAX", 0);
+      th_cap = env_int("ACCEL_WARP_TH", 0);
+      env_read = true;
+    }
+    DevCfg& c = cfgs[dev];
+    if (!c.max_smem) {
+      cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&c.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    max_smem = c.max_smem;
+    sms = c.sms;
   }
   int th = WS_TILE / W;
   if (th > H) th = H;

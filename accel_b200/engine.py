@@ -17,18 +17,35 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _check_f32_cuda(name, t, shape):
+def _check_f32_cuda(name, t, shape, device=None):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
         raise TypeError("%s must be a contiguous CUDA float32 tensor" % name)
     if tuple(t.shape) != tuple(shape):
         raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    if device is not None and t.device != device:
+        raise ValueError("%s lives on %s, the engine on %s" % (name, t.device, device))
+    if t.data_ptr() % 16:
+        raise ValueError("%s must be 16-byte aligned (got a view at an odd offset)" % name)
+
+
+def _check_u8_cuda(name, t, shape, device=None):
+    """Label maps are written with 4-byte (uchar4) stores: uint8, contiguous, exact shape, 4-byte aligned."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA uint8 tensor" % name)
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    if device is not None and t.device != device:
+        raise ValueError("%s lives on %s, the engine on %s" % (name, t.device, device))
+    if t.data_ptr() % 4:
+        raise ValueError("%s must be 4-byte aligned (got a view at an odd offset)" % name)
 
 
 class Engine:
     """Owns the device copies of the weights and the key/cur plans; the caller owns all I/O tensors
     (SURVEY.md section 8b "Ownership")."""
 
-    def __init__(self, version, height, width, params=None, device=0, num_classes=NUM_CLASSES, flags=0):
+    def __init__(self, version, height, width, params=None, device=0, num_classes=NUM_CLASSES, flags=0, interval=None):
+        """interval: also build the whole-interval plan for that many frames (accel_plan_interval; chained schedule)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("accel_b200: no CUDA device visible -- this path has no CPU fallback")
@@ -44,8 +61,21 @@ class Engine:
         self._h = h
         self.flags = int(flags)
         self.torch_device = torch.device("cuda", self.device)
+        self.interval = 0
+        if interval is not None and int(interval) > 1:
+            self.plan_interval(int(interval))
         if params is not None:
             self.set_params(params)
+
+    def plan_interval(self, interval):
+        """accel_plan_interval: must precede finalize (set_params(..., finalize=True))."""
+        if self.lib.accel_plan_interval(self._h, int(interval)) != 0:
+            raise RuntimeError("accel_plan_interval failed: %s" % self._err())
+        self.interval = int(interval)
+
+    @property
+    def supports_interval(self):
+        return self.interval > 1
 
     # ---- parameters -----------------------------------------------------------------------------
     def param_spec(self):
@@ -96,13 +126,16 @@ class Engine:
 
     def key_forward(self, data, feat_out=None, score_out=None, label_out=None, g_out=None):
         """g_out: optional (1,1024,H/16,W/16) output of fc6's linear part (accel_key_forward_lin)."""
-        _check_f32_cuda("data", data, (1, 3, self.height, self.width))
+        dv = self.torch_device
+        _check_f32_cuda("data", data, (1, 3, self.height, self.width), dv)
         if feat_out is not None:
-            _check_f32_cuda("feat_out", feat_out, self.feat_shape)
+            _check_f32_cuda("feat_out", feat_out, self.feat_shape, dv)
         if score_out is not None:
-            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width))
+            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width), dv)
         if g_out is not None:
-            _check_f32_cuda("g_out", g_out, self.g_shape)
+            _check_f32_cuda("g_out", g_out, self.g_shape, dv)
+        if label_out is not None:
+            _check_u8_cuda("label_out", label_out, (self.height, self.width), dv)
         with torch.cuda.device(self.torch_device):
             if g_out is not None:
                 rc = self.lib.accel_key_forward_lin(self._h, _ptr(data), _ptr(feat_out), _ptr(g_out), _ptr(score_out),
@@ -114,13 +147,16 @@ class Engine:
             raise RuntimeError("accel_key_forward failed: %s" % self._err())
 
     def cur_forward(self, data, data_key, feat_key, feat_out=None, score_out=None, label_out=None):
-        _check_f32_cuda("data", data, (1, 3, self.height, self.width))
-        _check_f32_cuda("data_key", data_key, (1, 3, self.height, self.width))
-        _check_f32_cuda("feat_key", feat_key, self.feat_shape)
+        dv = self.torch_device
+        _check_f32_cuda("data", data, (1, 3, self.height, self.width), dv)
+        _check_f32_cuda("data_key", data_key, (1, 3, self.height, self.width), dv)
+        _check_f32_cuda("feat_key", feat_key, self.feat_shape, dv)
         if feat_out is not None:
-            _check_f32_cuda("feat_out", feat_out, self.feat_shape)
+            _check_f32_cuda("feat_out", feat_out, self.feat_shape, dv)
         if score_out is not None:
-            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width))
+            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width), dv)
+        if label_out is not None:
+            _check_u8_cuda("label_out", label_out, (self.height, self.width), dv)
         with torch.cuda.device(self.torch_device):
             rc = self.lib.accel_cur_forward(self._h, _ptr(data), _ptr(data_key), _ptr(feat_key), _ptr(feat_out),
                                             _ptr(score_out), _ptr(label_out), self._stream())
@@ -130,22 +166,73 @@ class Engine:
     def cur_forward_lin(self, data, data_key, g_key, g_out=None, score_out=None, label_out=None):
         """Cur-frame graph with the L head commuted through the warp (accel_cur_forward_lin): warps g_key = W_fc6 * F
         instead of the 2048-channel feature; DFF / Accel-18/34/50 only."""
-        _check_f32_cuda("data", data, (1, 3, self.height, self.width))
-        _check_f32_cuda("data_key", data_key, (1, 3, self.height, self.width))
-        _check_f32_cuda("g_key", g_key, self.g_shape)
+        dv = self.torch_device
+        _check_f32_cuda("data", data, (1, 3, self.height, self.width), dv)
+        _check_f32_cuda("data_key", data_key, (1, 3, self.height, self.width), dv)
+        _check_f32_cuda("g_key", g_key, self.g_shape, dv)
         if g_out is not None:
-            _check_f32_cuda("g_out", g_out, self.g_shape)
+            _check_f32_cuda("g_out", g_out, self.g_shape, dv)
         if score_out is not None:
-            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width))
+            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width), dv)
+        if label_out is not None:
+            _check_u8_cuda("label_out", label_out, (self.height, self.width), dv)
         with torch.cuda.device(self.torch_device):
             rc = self.lib.accel_cur_forward_lin(self._h, _ptr(data), _ptr(data_key), _ptr(g_key), _ptr(g_out),
                                                 _ptr(score_out), _ptr(label_out), self._stream())
         if rc != 0:
             raise RuntimeError("accel_cur_forward_lin failed: %s" % self._err())
 
+    def rbranch_forward(self, data, score_out=None, label_out=None):
+        """accel_rbranch_forward: the correction network + its head alone = plain DeepLab-<v> on one frame."""
+        dv = self.torch_device
+        _check_f32_cuda("data", data, (1, 3, self.height, self.width), dv)
+        if score_out is not None:
+            _check_f32_cuda("score_out", score_out, (1, self.num_classes, self.height, self.width), dv)
+        if label_out is not None:
+            _check_u8_cuda("label_out", label_out, (self.height, self.width), dv)
+        with torch.cuda.device(dv):
+            rc = self.lib.accel_rbranch_forward(self._h, _ptr(data), _ptr(score_out), _ptr(label_out), self._stream())
+        if rc != 0:
+            raise RuntimeError("accel_rbranch_forward failed: %s" % self._err())
+
+    def interval_forward(self, frames, labels, scores=None):
+        """accel_interval_forward: one whole key interval (chained schedule).  frames: `interval` fp32 (1,3,H,W) CUDA
+        tensors; labels: `interval` uint8 (H,W) CUDA tensors (or one (interval,H,W) tensor); scores: None or a list of
+        (1,19,H,W) tensors / None."""
+        I = self.interval
+        if I < 2:
+            raise RuntimeError("Engine was built without interval=...: no whole-interval plan")
+        dv = self.torch_device
+        if len(frames) != I or len(labels) != I or (scores is not None and len(scores) != I):
+            raise ValueError("interval_forward needs exactly %d frames / label maps" % I)
+        vp = C.c_void_p
+        fr, lb, sc = (vp * I)(), (vp * I)(), (vp * I)()
+        for t in range(I):
+            _check_f32_cuda("frames[%d]" % t, frames[t], (1, 3, self.height, self.width), dv)
+            _check_u8_cuda("labels[%d]" % t, labels[t], (self.height, self.width), dv)
+            fr[t], lb[t] = frames[t].data_ptr(), labels[t].data_ptr()
+            if scores is not None and scores[t] is not None:
+                _check_f32_cuda("scores[%d]" % t, scores[t], (1, self.num_classes, self.height, self.width), dv)
+                sc[t] = scores[t].data_ptr()
+        with torch.cuda.device(dv):
+            rc = self.lib.accel_interval_forward(self._h, fr, sc if scores is not None else None, lb, self._stream())
+        if rc != 0:
+            raise RuntimeError("accel_interval_forward failed: %s" % self._err())
+
+    def graph_cache_stats(self):
+        """(hits, misses) of the handle's CUDA-graph cache: a miss = one stream capture + instantiate."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.lib.accel_graph_cache_stats(self._h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def flownet(self, data, data_key, flow_out=None):
+        dv = self.torch_device
+        _check_f32_cuda("data", data, (1, 3, self.height, self.width), dv)
+        _check_f32_cuda("data_key", data_key, (1, 3, self.height, self.width), dv)
         if flow_out is None:
             flow_out = torch.empty(1, 2, self.height // 16, self.width // 16, device=self.torch_device)
+        else:
+            _check_f32_cuda("flow_out", flow_out, (1, 2, self.height // 16, self.width // 16), dv)
         with torch.cuda.device(self.torch_device):
             rc = self.lib.accel_flownet(self._h, _ptr(data), _ptr(data_key), _ptr(flow_out), self._stream())
         if rc != 0:

@@ -32,10 +32,26 @@ class Symbol:
         self.version, self.kind = str(version), kind
 
     def list_outputs(self):
+        if self.kind == "deeplab":                    # deeplab/symbols/resnet_v1_101_deeplab.py:798-803
+            return ["softmax_output"]
         if self.kind == "key":                        # accel_18.py:157
             return ["data_key", "feat_key", "res5c_relu_output", "croped_score_output"]
         score = "croped_score_output" if self.version in ("101", "dff") else "correction_output"
         return ["data_key", "warping_feat_output", score]          # accel_18.py:237, accel_101.py:191
+
+
+class deeplab:
+    """deeplab/symbols/resnet_v1_101_deeplab.py get_symbol(is_train=False) shaped stand-in for BASELINE config 1: the
+    correction network of Accel-<version> alone (its own DeepLab head) on one frame.  Output names follow the test
+    symbol (:798-803): `softmax_output`; deeplab/core/tester.py:84-85 takes its argmax."""
+
+    def __init__(self, version="18"):
+        self.version = str(version)
+
+    def get_symbol(self, cfg=None, is_train=False):
+        if is_train:
+            raise NotImplementedError("training graphs are out of scope (SURVEY.md section 8)")
+        return Symbol(self.version, "deeplab")
 
 
 class _AccelSymbols:
@@ -79,9 +95,30 @@ class DataBatch:
 _ENGINES = {}
 
 
+def _fingerprint(*dicts):
+    """Content fingerprint of the parameter dicts: names, shapes and a CRC-32 of every array's bytes.  Keying the
+    engine cache on id() alone would silently reuse stale device weights after `arg_params.update(other_ckpt)`, or
+    when a freed dict's id is recycled."""
+    import zlib
+
+    import numpy as np
+    crc = 0
+    n = 0
+    for d in dicts:
+        for name in sorted(d or {}):
+            v = d[name]
+            a = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            a = np.ascontiguousarray(a)
+            crc = zlib.crc32(name.encode(), crc)
+            crc = zlib.crc32(repr((a.shape, str(a.dtype))).encode(), crc)
+            crc = zlib.crc32(memoryview(a).cast("B"), crc)
+            n += 1
+    return (n, crc & 0xFFFFFFFF)
+
+
 def _shared_engine(version, height, width, device, arg_params, aux_params, flags):
-    # The key and cur Predictors of one demo share weights (same arg_params dict): one handle serves both.
-    key = (version, height, width, device, id(arg_params), id(aux_params), flags)
+    # The key and cur Predictors of one demo share weights (same arg_params contents): one handle serves both.
+    key = (version, height, width, device, _fingerprint(arg_params, aux_params), flags)
     eng = _ENGINES.get(key)
     if eng is None:
         params = dict(arg_params or {})
@@ -98,6 +135,10 @@ class Predictor:
     def __init__(self, symbol, data_names, label_names, context=None, max_data_shapes=None, provide_data=None,
                  provide_label=None, arg_params=None, aux_params=None, engine=None, emit_scores=True, flags=0):
         names = list(data_names)
+        if symbol.kind == "deeplab":                  # deeplab/function/test_deeplab.py:66-75: data_names = ['data']
+            if "data" not in names:
+                raise ValueError("data_names must contain 'data'")
+            names = names + [n for n in ("data_key", "feat_key") if n not in names]
         if not all(k in names for k in ("data", "data_key", "feat_key")):
             raise ValueError("data_names must contain 'data', 'data_key', 'feat_key' (demo.py:184; TestLoader adds "
                              "'im_info', core/loader.py:214)")
@@ -120,8 +161,16 @@ class Predictor:
 
     def predict(self, data_batch):
         """Returns [ {output_name: tensor} ] for the single device, like tester.py:32-35."""
-        data, data_key, feat_key = (data_batch.data[0][i] for i in self._slots)
         eng = self.engine
+        if self.symbol.kind == "deeplab":
+            data = data_batch.data[0][self._slots[0]]
+            eng.rbranch_forward(data, self._score, self._label)
+            out = {"label_output": self._label}
+            if self.emit_scores:                      # SoftmaxOutput at inference = softmax over classes (:800)
+                out["croped_score_output"] = self._score
+                out["softmax_output"] = torch.softmax(self._score, dim=1)
+            return [out]
+        data, data_key, feat_key = (data_batch.data[0][i] for i in self._slots)
         feat_out = self._feat[self._flip]
         if self.symbol.kind == "cur" and feat_key.data_ptr() == feat_out.data_ptr():
             self._flip ^= 1                           # chained schedule feeds our own output back in

@@ -172,6 +172,20 @@ def segment_frame(engine, state, data, interval, schedule, label_out, score_out=
     return is_key
 
 
+def segment_interval(engine, state, frames, labels, scores=None):
+    """One whole key interval of the chained schedule through the whole-interval plan (accel_interval_forward): the
+    caller holds all `interval` frames (a video file, a decode queue; demo.py:165-185 preloads the clip).  Same
+    graphs and inputs as `interval` calls of segment_frame; only the issue order on the GPU changes: the per-frame
+    chains run concurrently.  labels: (interval,H,W) uint8 tensor or list of (H,W) tensors."""
+    if state.pending is not None:                               # a lookahead left over from the frame-by-frame loop
+        torch.cuda.current_stream(engine.torch_device).wait_event(state.pending["event"])
+        state.pending = None
+    engine.interval_forward(list(frames), [labels[t] for t in range(len(frames))], scores)
+    state.key_frame = frames[0]
+    state.prev_frame = frames[-1]
+    state.index = 0                                             # the next frame is a key frame again
+
+
 class VideoPipeline:
     """One video stream from HOST frames to HOST label maps -- the loop body of dff_deeplab/demo.py:228-252
     with the frame ingest of demo.py:170-175 moved onto the GPU.
@@ -183,7 +197,8 @@ class VideoPipeline:
     confusion matrix against ground-truth label maps is accumulated on the device (demo.py:270-272)."""
 
     def __init__(self, engine, interval, schedule="chained", pixel_means_bgr=None, depth=2, lookahead=True,
-                 linear_head=False):
+                 linear_head=False, batched=False):
+        """batched: submit_interval() runs whole intervals through the engine's whole-interval plan."""
         if schedule not in SCHEDULES:
             raise ValueError("schedule must be one of %s" % (SCHEDULES,))
         if interval < 1:
@@ -212,6 +227,50 @@ class VideoPipeline:
         self.kslot = 0
         self.pre_key = None                                           # {"host": pinned frame, "data": fp32 tensor}
         self.hist = torch.zeros(engine.num_classes, engine.num_classes, dtype=torch.int64, device=dev)
+        self.batched = bool(batched)
+        if self.batched:
+            if schedule != "chained" or engine.interval != self.interval:
+                raise ValueError("batched pipeline needs an Engine built with interval=%d and the chained schedule" % self.interval)
+            I = self.interval
+            self.iv_u8 = [[torch.empty(H, W, 3, dtype=torch.uint8, device=dev) for _ in range(I)] for _ in range(2)]
+            self.iv_f32 = [[torch.empty(1, 3, H, W, device=dev) for _ in range(I)] for _ in range(2)]
+            self.iv_label = [torch.empty(I, H, W, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self.iv_in = [torch.cuda.Event() for _ in range(2)]      # set s: frames landed
+            self.iv_free = [torch.cuda.Event() for _ in range(2)]    # set s: u8 frames consumed by preprocess
+            self.iv_done = [torch.cuda.Event() for _ in range(2)]    # set s: label maps written
+            self.iv_out = [torch.cuda.Event() for _ in range(2)]     # set s: label maps copied to the host
+            self.iv_n = 0
+
+    def submit_interval(self, frames_u8_host, labels_host):
+        """Queues one whole key interval: `interval` pinned (H,W,3) uint8 BGR frames in, `interval` pinned (H,W) uint8
+        label maps out (valid once the returned events have completed).  H2D copies of interval k+1 and D2H copies of
+        interval k-1 overlap the plan of interval k (two buffer sets)."""
+        I = self.interval
+        if not self.batched or len(frames_u8_host) != I or len(labels_host) != I:
+            raise ValueError("submit_interval needs a batched pipeline and exactly %d frames" % I)
+        s = self.iv_n & 1
+        main = torch.cuda.current_stream(self.dev)
+        if self.iv_n >= 2:
+            self.copy_in.wait_event(self.iv_free[s])
+        with torch.cuda.stream(self.copy_in):
+            for t in range(I):
+                self.iv_u8[s][t].copy_(frames_u8_host[t], non_blocking=True)
+            self.iv_in[s].record(self.copy_in)
+        main.wait_event(self.iv_in[s])
+        for t in range(I):
+            self._E.preprocess(self.iv_u8[s][t], self.iv_f32[s][t], self.means)
+        self.iv_free[s].record(main)
+        if self.iv_n >= 2:
+            main.wait_event(self.iv_out[s])                                  # label set s has left for the host
+        segment_interval(self.engine, self.state, self.iv_f32[s], self.iv_label[s])
+        self.iv_done[s].record(main)
+        self.copy_out.wait_event(self.iv_done[s])
+        with torch.cuda.stream(self.copy_out):
+            for t in range(I):
+                labels_host[t].copy_(self.iv_label[s][t], non_blocking=True)
+            self.iv_out[s].record(self.copy_out)
+        self.iv_n += 1
+        return [self.iv_out[s]] * I
 
     def reset(self):
         """Start of a new video: the next frame is a key frame."""

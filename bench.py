@@ -43,13 +43,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--version", default="dff", choices=["dff", "18", "34", "50", "101"])
+    ap.add_argument("--version", default="101", choices=["dff", "18", "34", "50", "101"],
+                    help="default: Accel-101, BASELINE.json's north-star model (config 5); Accel-18 and DFF are reported as "
+                         "the extra objects `accel18` / `dff` of the same run")
     ap.add_argument("--interval", type=int, default=5)
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=2048)
     ap.add_argument("--schedule", default="chained", choices=["chained", "unchained"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `accel18` / `dff` extra objects")
+    ap.add_argument("--no-batched", action="store_true",
+                    help="headline = the frame-by-frame loop (with key-frame lookahead) instead of the whole-interval plan")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--linear-head", action="store_true",
                     help="headline run uses the commuted L head (accel_cur_forward_lin: warp W_fc6*F, 1024 channels); "
@@ -145,18 +150,21 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_fps(a, steps, warmup, budget_s=None):
-    """Times the CPU oracle (reference graph as written, PyTorch fp32, all host threads) one frame
-    per step, cycling through a key interval.  Returns (fps, detail)."""
+def cpu_oracle_fps(a, steps, warmup, budget_s=None, frames=None, keep_outputs=False):
+    """Times the CPU oracle (reference graph as written, PyTorch fp32, all host threads) ONE FRAME PER STEP,
+    cycling through a key interval of the workload's own frames.  Returns (fps, detail); with keep_outputs the
+    first key frame's and first cur frame's oracle outputs stay in detail["key_out"] / detail["cur_out"]."""
     import torch
     from accel_b200 import synthetic
     from oracle import nets
     torch.set_num_threads(os.cpu_count() or 1)
     p = synthetic.make_params(a.version)
-    frames = synthetic.make_frames(a.interval, a.height, a.width)
-    t_key, t_cur = [], []
+    if frames is None:
+        frames = synthetic.make_frames(2 * a.interval, a.height, a.width)[:a.interval]
+    t_key, t_cur, t_all = [], [], []
     feat = None
     n = 0
+    detail = {}
     t_start = time.perf_counter()
     with torch.no_grad():
         total = warmup + steps
@@ -175,8 +183,11 @@ def cpu_oracle_fps(a, steps, warmup, budget_s=None):
                 kind = "cur"
             score.argmax(dim=1)
             dt = time.perf_counter() - t0
+            if keep_outputs and (kind + "_out") not in detail:
+                detail[kind + "_out"] = {"score": score, "feat": feat, "index": idx}
             if i >= warmup:
                 (t_key if kind == "key" else t_cur).append(dt)
+                t_all.append(dt)
                 n += 1
             if budget_s is not None and time.perf_counter() - t_start > budget_s and t_key and t_cur:
                 break
@@ -189,23 +200,28 @@ def cpu_oracle_fps(a, steps, warmup, budget_s=None):
     else:
         per_interval = mk + (a.interval - 1) * mc
     fps = a.interval / per_interval
-    detail = {"key_s": mk, "cur_s": mc, "frames_timed": n}
+    detail.update({"key_s": mk, "cur_s": mc, "frames_timed": n, "timed_s": sum(t_all)})
     return fps, detail
 
 
 def run_reference(a):
+    """Reference arm: the reference's own CPU path for this workload is MXNet (absent here), so the arm times the CPU
+    oracle -- the reference graph as written, PyTorch fp32, all host threads.  One STEP = ONE FRAME of the workload (a
+    bounded sample of a 5-frame interval), cycling key, cur, cur, cur, cur: `steps` and `ms_per_step` are in those
+    one-frame steps (steps x ms_per_step = the timed wall time), `value` is the interval-weighted frames/s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     fps, d = cpu_oracle_fps(a, a.steps, a.warmup)
     cores = os.cpu_count() or 1
-    sample = "%d frames (1 per step, cycling the key interval: %.2fs/key frame, %.2fs/cur frame) of %s" % (
+    sample = "%d one-frame steps cycling the key interval (%.2fs/key frame, %.2fs/cur frame) of %s" % (
         d["frames_timed"], d["key_s"], d["cur_s"], workload_name(a))
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1000.0 * a.interval / fps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "schedule": a.schedule,
-                       "note": "CPU oracle (PyTorch fp32 restatement of the MXNet graph); MXNet itself cannot run here"},
+            "warmup": a.warmup, "ms_per_step": 1000.0 * d["timed_s"] / max(d["frames_timed"], 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "schedule": a.schedule, "frames_per_step": 1,
+                       "note": "CPU oracle (PyTorch fp32 restatement of the MXNet graph); MXNet itself cannot run here. "
+                               "A step is ONE frame (bounded sample); value = interval / (t_key + (interval-1) * t_cur)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -213,9 +229,31 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+STAGES = ("backbone", "flownet", "warp", "warp_to_head", "rbranch", "fusion", "head", "tail")   # the gathered per-stage slots
+
+
+class Stream:
+    """One synthetic video stream on one GPU: engine + 2 intervals of resident fp32 frames (uploaded as uint8 and
+    preprocessed on the device, bit-identical to synthetic.transform)."""
+
+    def __init__(self, version, H, W, I, stream_id, local, flags, E, synthetic, Engine, torch, n_frames=None, plan_interval=False):
+        self.version, self.I = version, I
+        self.eng = Engine(version, H, W, params=synthetic.make_params(version), device=local, flags=flags,
+                          interval=I if plan_interval else None)
+        self.dev = self.eng.torch_device
+        self.n_frames = n_frames or 2 * I
+        self.frames_u8 = synthetic.make_frames_u8(self.n_frames, H, W, stream=stream_id)
+        self.frames = [E.preprocess(f.to(self.dev)) for f in self.frames_u8]
+        self.label = torch.empty(H, W, dtype=torch.uint8, device=self.dev)
+        self.labels_ivl = torch.empty(I, H, W, dtype=torch.uint8, device=self.dev) if self.eng.supports_interval else None
+
+
 def run_native(a):
+    import zlib
+
     import torch
     import torch.distributed as dist
+    from accel_b200 import engine as E
     from accel_b200 import multigpu, scheduler, synthetic
     from accel_b200.engine import Engine
 
@@ -228,27 +266,12 @@ def run_native(a):
     multigpu.init("nccl", dev)
 
     H, W, I = a.height, a.width, a.interval
-    params = synthetic.make_params(a.version)
-    eng = Engine(a.version, H, W, params=params, device=local, flags=a.flags)
-    del params
-    # one stream per GPU: stream id = rank.  2 intervals of distinct frames, cycled.
-    n_frames = 2 * I
-    frames_u8 = synthetic.make_frames_u8(n_frames, H, W, stream=rank)
-    host = [synthetic.transform(f).pin_memory() for f in frames_u8]          # pinned fp32 (1,3,H,W)
-    frames = [h.to(dev) for h in host]
-    label = torch.empty(H, W, dtype=torch.uint8, device=dev)
-    label_host = torch.empty(H, W, dtype=torch.uint8).pin_memory()
-    lin_main = bool(a.linear_head) and eng.supports_linear_head
-    state = scheduler.StreamState(eng, linear_head=lin_main)
-
     look = not a.no_lookahead and I > 1
 
-    def step(s, last=False, state=state):
-        # key-frame lookahead: the next interval's key frame (already resident, like the reference's preloaded
-        # `data` list, demo.py:165-185) runs its key plan on a second stream under this interval's cur frames
-        for i in range(I):
-            nk = frames[(s * I + I) % n_frames] if (look and i == 0 and not last) else None
-            scheduler.segment_frame(eng, state, frames[(s * I + i) % n_frames], I, a.schedule, label, next_key_data=nk)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     def reset_state(st):
         if st.pending is not None:
@@ -256,24 +279,57 @@ def run_native(a):
             st.pending = None
         st.index = 0
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def timed_loop(S, steps, warmup, lookahead, linear_head=False, batched=False):
+        """W warm-up + K timed steps of stream S (one step = one key interval), CUDA events on the launching stream,
+        barrier + synchronize on both sides.  Returns (ms, state)."""
+        eng, frames, n_frames = S.eng, S.frames, S.n_frames
+        state = scheduler.StreamState(eng, linear_head=linear_head)
 
-    # priming: every distinct (frame, feature buffer, label buffer) pointer set is captured into its CUDA graph once;
-    # the pattern repeats every two intervals.  Then the W warm-up steps proper.
-    for s in range(4):
-        step(s, last=(s == 3))
-    reset_state(state)
-    for s in range(a.warmup):
-        step(s, last=(s == a.warmup - 1))
+        def step(s, last=False):
+            if batched:
+                base = (s * I) % n_frames
+                scheduler.segment_interval(eng, state, frames[base:base + I], S.labels_ivl)
+                return
+            for i in range(I):
+                nk = frames[(s * I + I) % n_frames] if (lookahead and i == 0 and not last) else None
+                scheduler.segment_frame(eng, state, frames[(s * I + i) % n_frames], I, a.schedule, S.label, next_key_data=nk)
+
+        # priming: every distinct (frame, feature buffer, label buffer) pointer set is captured into its CUDA graph
+        # once; the pattern repeats every two intervals.  Then the W warm-up steps proper.
+        for s in range(4):
+            step(s, last=(s == 3))
+        reset_state(state)
+        for s in range(warmup):
+            step(s, last=(s == warmup - 1))
+        reset_state(state)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for s in range(steps):
+            step(s, last=(s == steps - 1))
+        if state.key_stream is not None:
+            torch.cuda.current_stream().wait_stream(state.key_stream)
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1), state
+
+    # ---- the headline stream: one stream per GPU, stream id = rank (SURVEY.md 8e) ---------------------------------
+    want_batched = (not a.no_batched) and 1 < I <= 16 and a.schedule == "chained" and not a.linear_head and not (a.flags & 2)
+    S = Stream(a.version, H, W, I, rank, local, a.flags, E, synthetic, Engine, torch, plan_interval=want_batched)
+    eng, frames, frames_u8, label, n_frames = S.eng, S.frames, S.frames_u8, S.label, S.n_frames
+    lin_main = bool(a.linear_head) and eng.supports_linear_head
+    use_batched = want_batched and eng.supports_interval
+
+    # one profiled interval (untimed, eager, CUDA events between ops): per-stage time and launch count
+    state = scheduler.StreamState(eng, linear_head=lin_main)
+    for i in range(I):
+        scheduler.segment_frame(eng, state, frames[i], I, a.schedule, label)
     barrier()
     launches_per_step = 0
     eng.set_profiling(True)
     reset_state(state)
     warp_ms, stage_ms = [], {}
-    for i in range(I):                                                         # one profiled interval (untimed)
+    for i in range(I):
         scheduler.segment_frame(eng, state, frames[i], I, a.schedule, label)
         launches_per_step += eng.last_launch_count()
         for k, v in eng.stage_times().items():
@@ -281,46 +337,33 @@ def run_native(a):
             if k == "warp":
                 warp_ms.append(v)
     eng.set_profiling(False)
+    del state
     barrier()
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    reset_state(state)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for s in range(a.steps):
-        step(s, last=(s == a.steps - 1))
-    if state.key_stream is not None:
-        torch.cuda.current_stream().wait_stream(state.key_stream)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    if use_batched:
+        ms, _ = timed_loop(S, a.steps, a.warmup, False, batched=True)
+        launches_main = eng.last_launch_count()
+    else:
+        ms, _ = timed_loop(S, a.steps, a.warmup, look, linear_head=lin_main)
+        launches_main = launches_per_step
     if sampler:
         sampler.stop_flag = True
+
+    # the other issue orders of the same workload, same K steps: strictly online (frame by frame, nothing of a later
+    # frame starts before the current label map is issued) and, when the headline is the whole-interval plan, the
+    # key-frame lookahead loop
+    online_ms, _ = timed_loop(S, a.steps, a.warmup, False, linear_head=lin_main) if I > 1 else (None, None)
+    look_ms = None
+    if use_batched and look:
+        look_ms, _ = timed_loop(S, a.steps, a.warmup, True, linear_head=lin_main)
 
     # the same loop with the L head commuted through the warp (fc6(warp(F)) = warp(W*F) + b): extra object, same K steps
     lin_ms = None
     if eng.supports_linear_head and I > 1 and not lin_main:
-        st_lin = scheduler.StreamState(eng, linear_head=True)
-        for s in range(4):
-            step(s, last=(s == 3), state=st_lin)
-        reset_state(st_lin)
-        for s in range(a.warmup):
-            step(s, last=(s == a.warmup - 1), state=st_lin)
-        reset_state(st_lin)
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        l0.record()
-        for s in range(a.steps):
-            step(s, last=(s == a.steps - 1), state=st_lin)
-        if st_lin.key_stream is not None:
-            torch.cuda.current_stream().wait_stream(st_lin.key_stream)
-        l1.record()
-        barrier()
-        lin_ms = l0.elapsed_time(l1)
-        del st_lin
+        lin_ms, _ = timed_loop(S, a.steps, a.warmup, look, linear_head=True)
 
     # per-kernel timing of the warp launch, live, with CUDA events on the launching stream: 30 launches
     # rotating over three (source, destination) feature pairs (6 x 64 MiB -- 6 x 32 MiB with --linear-head -- > the 126 MB L2, so every read
@@ -328,7 +371,6 @@ def run_native(a):
     # driven by the stream's own FlowNet flow field.
     warp_evs = []
     if I > 1:
-        from accel_b200 import engine as _E
         h, w = H // 16, W // 16
         g = torch.Generator(device="cpu").manual_seed(7)
         warp_c = 1024 if lin_main else 2048
@@ -338,13 +380,13 @@ def run_native(a):
         flow_t = eng.flownet(frames[1], frames[0]).clone()      # the flow field FlowNet produces on this stream
         pairs = [(bufs[0], bufs[1]), (bufs[2], bufs[3]), (bufs[4], bufs[5])]
         for k in range(6):
-            _E.warp(pairs[k % 3][0], flow_t, pairs[k % 3][1])
+            E.warp(pairs[k % 3][0], flow_t, pairs[k % 3][1])
         n_warp = 30
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         w0.record()
         for k in range(n_warp):
-            _E.warp(pairs[k % 3][0], flow_t, pairs[k % 3][1])
+            E.warp(pairs[k % 3][0], flow_t, pairs[k % 3][1])
         w1.record()
         torch.cuda.synchronize()
         warp_evs = [w0.elapsed_time(w1) / n_warp]
@@ -360,21 +402,30 @@ def run_native(a):
     e2e_ms = e2e32_ms = None
     if not a.no_e2e:
         host_u8 = [f.contiguous().pin_memory() for f in frames_u8]
-        n_lab = 4
+        n_lab = 2 * I
         labels_host = [torch.empty(H, W, dtype=torch.uint8).pin_memory() for _ in range(n_lab)]
         lab_ev = [None] * n_lab
-        pipe = scheduler.VideoPipeline(eng, I, a.schedule, lookahead=look, linear_head=lin_main)
+        pipe = scheduler.VideoPipeline(eng, I, a.schedule, lookahead=look, linear_head=lin_main, batched=use_batched)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def e2e_step(s, last=False):
-            # the consumer takes label map k (its copy event has completed) before host buffer k % 4 is reused:
-            # at most 4 frames are in flight, every label map reaches the host inside the timed region
-            for i in range(I):
-                k = s * I + i
-                if lab_ev[k % n_lab] is not None:
-                    lab_ev[k % n_lab].synchronize()
-                nk = host_u8[(k + I) % n_frames] if (look and i == 0 and not last) else None
-                _, lab_ev[k % n_lab] = pipe.submit(host_u8[k % n_frames], labels_host[k % n_lab], next_key_host=nk)
+            # the consumer takes label map k (its copy event has completed) before host buffer k % n_lab is reused:
+            # at most n_lab frames are in flight, every label map reaches the host inside the timed region
+            if use_batched:
+                ks = [s * I + i for i in range(I)]
+                for k in ks:
+                    if lab_ev[k % n_lab] is not None:
+                        lab_ev[k % n_lab].synchronize()
+                evs = pipe.submit_interval([host_u8[k % n_frames] for k in ks], [labels_host[k % n_lab] for k in ks])
+                for k, ev in zip(ks, evs):
+                    lab_ev[k % n_lab] = ev
+            else:
+                for i in range(I):
+                    k = s * I + i
+                    if lab_ev[k % n_lab] is not None:
+                        lab_ev[k % n_lab].synchronize()
+                    nk = host_u8[(k + I) % n_frames] if (look and i == 0 and not last) else None
+                    _, lab_ev[k % n_lab] = pipe.submit(host_u8[k % n_frames], labels_host[k % n_lab], next_key_host=nk)
             if last:
                 pipe.sync()
 
@@ -390,8 +441,11 @@ def run_native(a):
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
+        del pipe
 
+        host = [f.cpu().pin_memory() for f in frames]                               # pinned fp32 (1,3,H,W)
         stage_in = [torch.empty(1, 3, H, W, device=dev) for _ in range(2)]
+        label_host = torch.empty(H, W, dtype=torch.uint8).pin_memory()
         state = scheduler.StreamState(eng, linear_head=lin_main)
 
         def e2e32_step(s):
@@ -411,21 +465,22 @@ def run_native(a):
         e1.record()
         barrier()
         e2e32_ms = e0.elapsed_time(e1)
+        del host, stage_in, state
 
     # optional: S independent streams per GPU, each with its own handle and CUDA stream (fills the SMs that one
     # stream's small layers leave idle).  Extra information; `value` stays one stream per GPU.
     multi = None
     if a.multi_stream > 1:
-        S = a.multi_stream
+        NS = a.multi_stream
         engines = [eng] + [Engine(a.version, H, W, params=synthetic.make_params(a.version), device=local, flags=a.flags)
-                           for _ in range(S - 1)]
-        cstreams = [torch.cuda.Stream(dev) for _ in range(S)]
+                           for _ in range(NS - 1)]
+        cstreams = [torch.cuda.Stream(dev) for _ in range(NS)]
         states = [scheduler.StreamState(e) for e in engines]
-        labels = [torch.empty(H, W, dtype=torch.uint8, device=dev) for _ in range(S)]
+        labels = [torch.empty(H, W, dtype=torch.uint8, device=dev) for _ in range(NS)]
 
         def ms_step(s):
             for i in range(I):
-                for k in range(S):
+                for k in range(NS):
                     with torch.cuda.stream(cstreams[k]):
                         scheduler.segment_frame(engines[k], states[k], frames[(s * I + i + k) % n_frames], I, a.schedule, labels[k])
 
@@ -444,17 +499,79 @@ def run_native(a):
             torch.cuda.current_stream().wait_stream(c)
         m1.record()
         barrier()
-        multi = {"streams_per_gpu": S, "ms_per_step": m0.elapsed_time(m1) / a.steps,
-                 "value": S * I * a.steps / (m0.elapsed_time(m1) / 1000.0) * world, "unit": "frames/s",
+        multi = {"streams_per_gpu": NS, "ms_per_step": m0.elapsed_time(m1) / a.steps,
+                 "value": NS * I * a.steps / (m0.elapsed_time(m1) / 1000.0) * world, "unit": "frames/s",
                  "note": "S independent video streams interleaved per GPU (own handle + CUDA stream each); not the headline"}
+        del engines, states
 
-    # ---- reduce: max time over ranks, total frames --------------------------------------------------
-    rows = multigpu.gather_rows([a.steps * I, ms, e2e_ms or 0.0, e2e32_ms or 0.0, lin_ms or 0.0], dev)   # the single metric collective
+    # ---- per-rank correctness evidence (SURVEY.md 8e struct): CRC-32 of the stream's first interval of label maps
+    # and the confusion matrix (demo.py:50-53) of those label maps against a synthetic ground truth ------------------
+    def stream_evidence(Sx, stream_id, batched):
+        st = scheduler.StreamState(Sx.eng, linear_head=False)
+        hist = torch.zeros(19, 19, dtype=torch.int64, device=dev)
+        yy = torch.arange(H, device=dev).view(H, 1) // 64
+        xx = torch.arange(W, device=dev).view(1, W) // 64
+        gt = ((xx + 3 * yy + stream_id) % 19).to(torch.uint8).contiguous()
+        labs = []
+        if batched:
+            scheduler.segment_interval(Sx.eng, st, Sx.frames[:I], Sx.labels_ivl)
+            labs = [Sx.labels_ivl[i].clone() for i in range(I)]
+        else:
+            for i in range(I):
+                scheduler.segment_frame(Sx.eng, st, Sx.frames[i], I, a.schedule, Sx.label)
+                labs.append(Sx.label.clone())
+        for l in labs:
+            E.confusion(l, gt, hist, 19)
+        torch.cuda.synchronize()
+        crc = zlib.crc32(torch.stack(labs).cpu().numpy().tobytes()) & 0xFFFFFFFF
+        return crc, hist.cpu()
+
+    crc_main, hist_main = stream_evidence(S, rank, use_batched)
+    crc_seq = crc_main
+    if use_batched:
+        crc_seq, _ = stream_evidence(S, rank, False)           # the frame-by-frame loop's label maps of the same frames
+
+    # ---- in-line parity against the CPU oracle at the workload's own size (rank 0 of a single-GPU run) + cpu_baseline
+    parity = cpu_base = None
+    if world == 1 and not a.no_cpu_baseline:
+        budget = 25.0
+        host_frames = [f.cpu() for f in frames[:I]]
+        v, d = cpu_oracle_fps(a, steps=2 * I, warmup=0, budget_s=budget, frames=host_frames, keep_outputs=True)
+        cpu_base = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                    "sample": "%d frames of the same workload on the CPU oracle (%.2fs/key, %.2fs/cur), "
+                              "~%ds budget" % (d["frames_timed"], d["key_s"], d["cur_s"], int(budget))}
+        parity = oracle_parity(eng, frames, d, torch, a.version)
+        del d, host_frames
+
+    # ---- the other north-star workloads, same K steps and warm-up, one object each -------------------------------
+    extras = {}
+    others = [] if a.no_extras else [v for v in ("18", "dff") if v != a.version]
+    del S, eng, frames
+    torch.cuda.empty_cache()
+    for v in others:
+        Sx = Stream(v, H, W, I, rank, local, a.flags, E, synthetic, Engine, torch, plan_interval=use_batched)
+        bx = use_batched and Sx.eng.supports_interval
+        mx, _ = timed_loop(Sx, a.steps, a.warmup, look and not bx, batched=bx)
+        ox, _ = timed_loop(Sx, a.steps, a.warmup, False)
+        extras[v] = (mx, ox, bx)
+        del Sx
+        torch.cuda.empty_cache()
+
+    # ---- reduce: max time over ranks, total frames: ONE all_gather of the per-rank struct -------------------------
+    def stage_of(name):
+        return sum(v for k, v in stage_ms.items() if k.split(":", 1)[1] == name or
+                   (name == "head" and k.split(":", 1)[1] == "rhead"))
+    row = [a.steps * I, ms, e2e_ms or 0.0, e2e32_ms or 0.0, lin_ms or 0.0, online_ms or 0.0, look_ms or 0.0]
+    for v in ("18", "dff"):
+        row += list(extras.get(v, (0.0, 0.0, False))[:2])
+    row += [stage_of(s) for s in STAGES]
+    row += [float(crc_main), float(crc_seq)]
+    row += [float(x) for x in hist_main.reshape(-1).tolist()]
+    rows = multigpu.gather_rows(row, dev)                       # the single metric collective
     fps, ms_max = multigpu.aggregate_throughput(rows[:, 0].tolist(), rows[:, 1].tolist())
-    e2e_max = float(rows[:, 2].max())
-    e2e32_max = float(rows[:, 3].max())
     frames_total = float(rows[:, 0].sum())
-    lin_max = float(rows[:, 4].max())
+    col = lambda j: float(rows[:, j].max())
+    e2e_max, e2e32_max, lin_max, online_max, look_max = col(2), col(3), col(4), col(5), col(6)
 
     if rank == 0:
         peaks = {}
@@ -469,23 +586,28 @@ def run_native(a):
         # NCHW feature -- to the handle's scratch -- so the same bytes are counted)
         warp_avg_ms = sum(warp_evs) / len(warp_evs) if warp_evs else None
         roofline = None
-        traffic = None
-        try:                                            # dram__bytes_read+write per launch from the committed ncu capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "warp_traffic.json")))["traffic_bytes_per_launch"]
+        traffic = traffic_src = None
+        try:                                            # dram__bytes_read+write per launch from this round's ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_warp_traffic.json")))
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj.get("source")
         except Exception:
             pass
         if warp_avg_ms:
             ach = wb / (warp_avg_ms * 1e-3) / 1e9
-            roofline = {"kernel": "warp_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+            roofline = {"kernel": "warp_kernel_staged", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
                         "algorithmic_bytes_per_launch": wb, "avg_launch_ms": warp_avg_ms,
                         "frac_of_8TBps_nominal": ach / 8000.0}
         scale = (H * W) / float(1024 * 2048)
         gflop_step = (GFLOP_KEY + (I - 1) * GFLOP_CUR[a.version]) * scale
-        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        conv = {"bound": "tensor", "reference_graph_gflop_per_step": gflop_step,
+        # a timed region under ~1 s runs at burst clocks: the burst cuBLAS figure is the apt denominator
+        timed_s = ms_max / 1e3
+        burst = timed_s < 1.0
+        tf_peak = peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained", 1644.2 if burst else 1379.1)
+        conv = {"kernel": "conv_tc_kernel", "bound": "tensor", "reference_graph_gflop_per_step": gflop_step,
                 "achieved": gflop_step * a.steps / (ms_max / 1e3) / 1e3 , "unit": "TFLOP/s (reference-graph flops / whole step time)",
-                "peak": tf_peak, "peak_kind": peak_kind + " bf16 dense sustained"}
+                "peak": tf_peak, "peak_kind": peak_kind + (" bf16 dense burst (timed region %.2f s)" % timed_s if burst
+                                                           else " bf16 dense sustained")}
         conv["frac"] = conv["achieved"] / tf_peak
         # executed = reference-graph flops minus the exact algebraic folds (<v>_fc6 o <v>_feat_upsampling
         # as one 512->1024 transposed conv, 34.4 instead of 103.1 GFLOP; --linear-head: no fc6 GEMM on cur frames), times
@@ -499,19 +621,38 @@ def run_native(a):
         conv["executed_graph_gflop_per_step"] = exec_step
         conv["executed_fp16_mma_tflops"] = 3.0 * exec_step * a.steps / (ms_max / 1e3) / 1e3
         conv["executed_frac"] = conv["executed_fp16_mma_tflops"] / tf_peak
+        mode = "interval plan (the interval's frames issued as one CUDA graph: per-frame chains run concurrently)" if use_batched \
+            else ("key-frame lookahead" if look else "online")
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "fp16x3 split (fp32-equivalent operands, fp32 accumulate)", "data": "synthetic",
                 "config": {"workload": workload_name(a), "schedule": a.schedule, "frames_per_step": I,
-                           "streams": world, "key_lookahead": bool(look), "linear_head": bool(lin_main), "l2": "working set per step exceeds the 126 MB L2 (frames 24 MiB each, "
+                           "streams": world, "issue_order": mode, "key_lookahead": bool(look and not use_batched),
+                           "linear_head": bool(lin_main), "l2": "working set per step exceeds the 126 MB L2 (frames 24 MiB each, "
                            "features 64 MiB, activations > 1 GiB); no explicit flush"},
-                "gpu_launches": launches_per_step * a.steps, "launches_per_step": launches_per_step,
+                "gpu_launches": launches_main * a.steps, "launches_per_step": launches_main,
                 "roofline": roofline, "roofline_conv": conv,
                 "stage_ms_per_interval": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
-                "stage_ms_note": "one untimed interval run eagerly with CUDA events between ops: kernels that the graphs run "
-                                 "as parallel branches / lanes / key lookahead (each planned for a fraction of the SMs) are "
-                                 "serialised here, so the stages sum to more than ms_per_step",
+                "stage_ms_note": "one untimed interval run eagerly, frame by frame, with CUDA events between ops: kernels that "
+                                 "the graphs run concurrently (branches / lanes / lookahead / the interval plan's per-frame "
+                                 "chains) are serialised here, so the stages sum to more than ms_per_step",
                 "clocks": sampler.summary() if sampler else None}
+        if online_ms is not None:
+            line["online"] = {"value": frames_total / (online_max / 1000.0), "unit": "frames/s", "ms_per_step": online_max / a.steps,
+                              "note": "same workload, same K steps, strictly frame by frame (batch 1, no lookahead, nothing of a "
+                                      "later frame is issued before the current frame's label map)"}
+        if look_ms is not None:
+            line["lookahead"] = {"value": frames_total / (look_max / 1000.0), "unit": "frames/s", "ms_per_step": look_max / a.steps,
+                                 "note": "frame-by-frame loop with the next interval's key plan on a second stream"}
+        names = {"18": "accel18", "dff": "dff"}
+        for j, v in enumerate(("18", "dff")):
+            if v in extras:
+                m_, o_ = col(7 + 2 * j), col(8 + 2 * j)
+                aa = argparse.Namespace(**vars(a)); aa.version = v
+                line[names[v]] = {"workload": workload_name(aa), "value": frames_total / (m_ / 1000.0), "unit": "frames/s",
+                                  "ms_per_step": m_ / a.steps, "steps": a.steps, "warmup": a.warmup,
+                                  "issue_order": "interval plan" if extras[v][2] else ("key-frame lookahead" if look else "online"),
+                                  "online": {"value": frames_total / (o_ / 1000.0), "ms_per_step": o_ / a.steps}}
         if e2e_ms is not None:
             line["e2e"] = {"value": frames_total / (e2e_max / 1000.0), "unit": "frames/s",
                            "h2d_bytes_per_step": I * 3 * H * W, "d2h_bytes_per_step": I * H * W,
@@ -519,8 +660,8 @@ def run_native(a):
                                    "label D2H every frame, inside the timed region; copies on side streams"}
             line["e2e_fp32"] = {"value": frames_total / (e2e32_max / 1000.0), "unit": "frames/s",
                                 "h2d_bytes_per_step": I * 3 * H * W * 4, "d2h_bytes_per_step": I * H * W,
-                                "note": "same loop fed the reference's upload format (pinned fp32 NCHW `data`), single stream"}
-            line["gpu_launches_e2e_per_step"] = launches_per_step + I
+                                "note": "frame-by-frame loop fed the reference's upload format (pinned fp32 NCHW `data`), single stream"}
+            line["gpu_launches_e2e_per_step"] = launches_main + I
         if lin_ms is not None:
             line["linear_head"] = {"value": frames_total / (lin_max / 1000.0), "unit": "frames/s",
                                    "ms_per_step": lin_max / a.steps,
@@ -530,15 +671,79 @@ def run_native(a):
                                            "headline -- `value` runs the reference's graphs as written"}
         if multi is not None:
             line["multi_stream"] = multi
-        if world == 1 and not a.no_cpu_baseline:
-            budget = 25.0
-            v, d = cpu_oracle_fps(a, steps=2 * I, warmup=0, budget_s=budget)
-            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "%d frames of the same workload on the CPU oracle (%.2fs/key, %.2fs/cur), "
-                                              "~%ds budget" % (d["frames_timed"], d["key_s"], d["cur_s"], int(budget))}
+        # the gathered per-rank struct: frames, elapsed, per-stage ms, label CRC, confusion matrix
+        ns = len(STAGES)
+        j0 = 11
+        hist_sum = rows[:, j0 + ns + 2:].sum(dim=0).to(torch.int64).reshape(19, 19)
+        iu = multigpu.per_class_iu(hist_sum)
+        line["per_rank"] = [{"rank": r, "stream": r, "frames": int(rows[r, 0]), "elapsed_ms": float(rows[r, 1]),
+                             "stage_ms": {s: round(float(rows[r, j0 + k]), 4) for k, s in enumerate(STAGES)},
+                             "label_crc32": "%08x" % int(rows[r, j0 + ns]),
+                             "label_crc32_frame_by_frame": "%08x" % int(rows[r, j0 + ns + 1]),
+                             "confusion_trace": int(rows[r, j0 + ns + 2:].reshape(19, 19).diag().sum()),
+                             "confusion_total": int(rows[r, j0 + ns + 2:].sum())} for r in range(world)]
+        line["merged"] = {"label_crc32_xor": "%08x" % int(_xor([int(rows[r, j0 + ns]) for r in range(world)])),
+                          "confusion_total": int(hist_sum.sum()), "confusion_trace": int(hist_sum.diag().sum()),
+                          "confusion_crc32": "%08x" % (zlib.crc32(hist_sum.numpy().tobytes()) & 0xFFFFFFFF),
+                          "mean_iu_vs_synthetic_gt": float(iu[~torch.isnan(iu)].mean()),
+                          "note": "label_crc32 = CRC-32 of the first interval's uint8 label maps of stream `rank` (the issue order of "
+                                  "`value`); confusion = fast_hist (demo.py:50-53) of those maps against a synthetic ground truth, "
+                                  "summed over ranks; stream s gives the same CRC on any rank count"}
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        if parity is not None:
+            line["parity"] = parity
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _xor(vals):
+    x = 0
+    for v in vals:
+        x ^= v
+    return x
+
+
+def oracle_parity(eng, frames, d, torch, version):
+    """GPU outputs of the workload's first key frame and first cur frame (through the C ABI, score volume on) against
+    the CPU oracle's outputs of the same frames kept by the cpu_baseline leg: the north-star's parity bar at the
+    benchmark's own size."""
+    from oracle import nets, ops  # noqa: F401  (checker only)
+    dev = eng.torch_device
+    H, W = eng.height, eng.width
+    feat = [torch.empty(eng.feat_shape, device=dev) for _ in range(2)]
+    score = torch.empty(1, eng.num_classes, H, W, device=dev)
+    label = torch.empty(H, W, dtype=torch.uint8, device=dev)
+    out = {"size": "%dx%d" % (H, W), "score_tolerance": 1e-3}
+
+    def compare(tag, ref_score):
+        err = (score.cpu() - ref_score).abs().max().item()
+        ref_label = torch.from_numpy(ops.argmax_channel(ref_score)[0].astype("uint8"))
+        top2 = ref_score.topk(2, dim=1).values
+        margin = (top2[:, 0] - top2[:, 1])[0]
+        diff = label.cpu() != ref_label
+        out[tag] = {"score_max_abs": err, "label_mismatch": int(diff.sum()), "pixels": H * W,
+                    "label_mismatch_where_margin_gt_2x_measured_err": int((diff & (margin > 2 * err)).sum()),
+                    "undecided_px_margin_le_2x_measured_err": int((margin <= 2 * err).sum()),
+                    "undecided_px_margin_le_2e-3": int((margin <= 2e-3).sum())}
+
+    eng.key_forward(frames[0], feat[0], score, label)
+    compare("key", d["key_out"]["score"])
+    if "cur_out" in d:
+        i = d["cur_out"]["index"]
+        # chained schedule, as in the timed loop: frames 1..i on the GPU's own key feature
+        src = 0
+        for t in range(1, i + 1):
+            eng.cur_forward(frames[t], frames[t - 1], feat[src], feat[src ^ 1], score, label)
+            src ^= 1
+        compare("cur", d["cur_out"]["score"])
+        out["cur"]["feat_max_abs"] = (feat[src].cpu() - d["cur_out"]["feat"]).abs().max().item()
+    out["score_max_abs"] = max(out[k]["score_max_abs"] for k in ("key", "cur") if k in out)
+    out["label_mismatch"] = sum(out[k]["label_mismatch"] for k in ("key", "cur") if k in out)
+    out["undecided_px"] = sum(out[k]["undecided_px_margin_le_2x_measured_err"] for k in ("key", "cur") if k in out)
+    out["label_mismatch_decided"] = sum(out[k]["label_mismatch_where_margin_gt_2x_measured_err"] for k in ("key", "cur") if k in out)
+    return out
 
 
 def emit(line):

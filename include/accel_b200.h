@@ -9,7 +9,9 @@
  *     the reference's Predictor exchanges (dff_deeplab/core/tester.py:22-35, demo.py:184), except
  *     where a parameter is documented as host memory.
  *   - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
- *     stream).  A handle is bound to one device and must not be used from two threads at once.
+ *     stream).  A handle is bound to one device and is NOT thread-safe: its graph cache, side streams and
+ *     profiling state are mutated by every forward, so use one handle per host thread (the reference runs
+ *     one predictor pair per GPU thread too, tester.py:309-313).
  *   - Every function returns 0 on success, non-zero on failure; accel_last_error() returns the
  *     message.  No C++ exception crosses this boundary.  There is no CPU fallback: without a CUDA
  *     device accel_create succeeds only far enough to enumerate parameters, and every compute entry
@@ -94,6 +96,31 @@ int accel_key_forward_lin(AccelHandle* h, const float* data, float* feat_out, fl
                           uint8_t* label_out, void* stream);
 int accel_cur_forward_lin(AccelHandle* h, const float* data, const float* data_key, const float* g_key, float* g_out,
                           float* score_out, uint8_t* label_out, void* stream);
+
+/* The correction network of Accel-18/34/50 with its own DeepLab head, alone (accel_18.py:199-227 without the L branch
+ * and the fusion; accel_50.py:195-216): the plain DeepLab-<v> segmentation of ONE frame, i.e. what deeplab/test.py's
+ * Predictor computes per image (deeplab/core/tester.py:84-85 takes the argmax of its softmax, which is the argmax of
+ * this score volume).  BASELINE config 1's network.  score_out (1,19,H,W) may be NULL; label_out (H,W) uint8. */
+int accel_rbranch_forward(AccelHandle* h, const float* data, float* score_out, uint8_t* label_out, void* stream);
+
+/* Whole key interval in one call, for callers that hold the interval's frames up front (dff_deeplab/demo.py:165-185
+ * preloads the whole clip; precedent for batching frames through the nets: dff_rfcn/demo_batch.py:76-96).
+ * accel_plan_interval (before accel_finalize) builds the plan for `interval` frames (2..16) of the CHAINED schedule
+ * (demo.py:228-250): frame 0 = key graph, frame t = cur graph with data_key = frame t-1 and feat_key = frame t-1's
+ * (warped) feature.  accel_interval_forward runs it: everything that depends on one frame alone (R101 of the key frame,
+ * FlowNet of every frame pair, the correction network of every cur frame) runs as concurrent chains, each on its
+ * share of the SMs; only the warps and the heads / fusion behind them are sequential.  Same arithmetic per layer as
+ * the frame-by-frame calls (tile shapes may differ, so results agree to fp32 re-association, not bit for bit).
+ *   frames     HOST array of `interval` DEVICE pointers, each (1,3,H,W) fp32
+ *   score_out  NULL, or HOST array of `interval` DEVICE pointers (1,19,H,W), entries may be NULL
+ *   label_out  HOST array of `interval` DEVICE pointers (H,W) uint8 */
+int accel_plan_interval(AccelHandle* h, int interval);
+int accel_interval_forward(AccelHandle* h, const float* const* frames, float* const* score_out, uint8_t* const* label_out,
+                           void* stream);
+
+/* CUDA-graph cache of the handle: every distinct set of caller pointers is captured once (a miss costs a stream
+ * capture + instantiate, ~100x a replay); callers that see `misses` grow per frame are passing fresh temporaries. */
+int accel_graph_cache_stats(const AccelHandle* h, uint64_t* hits, uint64_t* misses);
 
 /* FlowNet-S alone, get_flownet (resnet_v1_101_flownet_deeplab.py:1751-1808): flow_out (1,2,H/16,W/16),
  * channel 0 = dx, 1 = dy in feature-grid pixels, already multiplied by 2.5. */

@@ -185,6 +185,16 @@ def cur_forward(p, version, data, data_key, feat_key):
     if version == "dff":
         out["croped_score_output"] = croped
         return out
+    cur_croped = rbranch_forward(p, version, data)["croped_score_output"]
+    out["correction_output"] = _conv(p, torch.cat([croped, cur_croped], dim=1), "corr", bias=True)
+    return out
+
+
+def rbranch_forward(p, version, data):
+    """The correction network with its own DeepLab head, alone: accel_18.py:199-227 (R18 / R34 trunk + deformable
+    conv5 + `feat_upsampling` + `<v>_fc6/score/upsampling`), accel_50.py:195-216 (R50-DCN + `curr_*` head).  On its
+    own this is the plain DeepLab-<v> net of BASELINE config 1 (deeplab/core/tester.py:84-85 argmaxes its softmax)."""
+    version = str(version)
     if version in ("18", "34"):                                    # accel_18.py:199-227
         pre = version + "_"
         f = resnet_preact(p, data, pre, [2, 2, 2] if version == "18" else [3, 4, 6])
@@ -195,10 +205,9 @@ def cur_forward(p, version, data, data_key, feat_key):
         f = resnet_dcn_50(p, data)
         names = ("curr_fc6", "curr_score", "curr_upsampling")
     else:
-        raise ValueError("unknown Accel version %r" % version)
-    cur_croped, _ = deeplab_head(p, f, data, *names)
-    out["correction_output"] = _conv(p, torch.cat([croped, cur_croped], dim=1), "corr", bias=True)
-    return out
+        raise ValueError("no stand-alone correction network for version %r" % version)
+    cur_croped, lowres = deeplab_head(p, f, data, *names)
+    return {"croped_score_output": cur_croped, "score_lowres": lowres}
 
 
 def output_key(version):

@@ -81,3 +81,29 @@ def test_no_cpu_fallback(lib):
     from accel_b200.engine import Engine
     with pytest.raises(RuntimeError):
         Engine("dff", 128, 256)
+
+
+@pytest.mark.parametrize("version", ["dff", "18", "101"])
+def test_interval_plan_builds_on_cpu_and_adds_no_parameters(lib, version):
+    """accel_plan_interval is pure host logic until finalize: it must build without a GPU, enumerate exactly the
+    parameters of the frame-by-frame plans (same networks, same names), and reject bad intervals / double planning."""
+    rc, h = _create(lib, version)
+    assert rc == 0
+    n0 = lib.accel_param_count(h)
+    assert lib.accel_plan_interval(h, 1) != 0 and b"interval must be" in lib.accel_last_error(h)
+    assert lib.accel_plan_interval(h, 17) != 0
+    assert lib.accel_plan_interval(h, 5) == 0, lib.accel_last_error(h)
+    assert lib.accel_param_count(h) == n0
+    assert lib.accel_plan_interval(h, 5) != 0 and b"already planned" in lib.accel_last_error(h)
+    lib.accel_destroy(h)
+
+
+def test_interval_forward_needs_a_plan(lib):
+    rc, h = _create(lib, "dff")
+    assert rc == 0
+    ptrs = (C.c_void_p * 2)()
+    assert lib.accel_interval_forward(h, ptrs, None, ptrs, None) != 0
+    assert b"accel_plan_interval" in lib.accel_last_error(h)
+    assert lib.accel_rbranch_forward(h, C.c_void_p(16), None, None, None) != 0
+    assert b"correction network" in lib.accel_last_error(h)
+    lib.accel_destroy(h)

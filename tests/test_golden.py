@@ -24,9 +24,14 @@ def _check_frame(g, i, sub, label, score, feat, score_tol, flow=None):
     assert np.abs(feat[0, ::64] - g["feat_sub_%d" % i]).max() < score_tol
     rel = abs(float(feat.astype(np.float64).sum()) - float(g["feat_sum_%d" % i])) / float(g["feat_abs_sum_%d" % i])
     assert rel < 5e-5
-    decided = g["margin_%d" % i] > 2 * score_tol          # bit-exact wherever the oracle's top-2 margin is decided
+    # bit-exact wherever the oracle's top-2 margin exceeds twice the score tolerance (the fixture holds the full-
+    # resolution margin but only a sub-sampled score volume, so the band is 2*tol here, not 2*measured); the band
+    # is < 1 % of the frame and the total number of flipped labels is bounded and reported
+    decided = g["margin_%d" % i] > 2 * score_tol
     assert np.array_equal(label[decided], g["label_%d" % i][decided])
-    assert decided.mean() > 0.97
+    assert decided.mean() > 0.99
+    flips = int((label != g["label_%d" % i]).sum())
+    assert flips <= max(1, int(1e-3 * label.size)), "%d flipped labels" % flips
     if flow is not None and ("flow_%d" % i) in g:
         assert np.abs(flow - g["flow_%d" % i]).max() < 1e-4
 

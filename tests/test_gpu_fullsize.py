@@ -2,7 +2,8 @@
 
 * 384x640 / 256x384 / 384x256 (not powers of two; partial tiles in every layer): key + cur graphs of Accel-18, -50,
   -101 and DFF against the CPU oracle.
-* BASELINE.json's full 1024x2048, where the oracle is too slow for the GPU suite: size-independent properties --
+* BASELINE.json's full 1024x2048 (graph-level ORACLE parity at this size is tests/test_gpu_fullsize_oracle.py):
+  size-independent properties --
   the label map is bit-exactly the lowest-index argmax of the emitted score volume, production mode (no score
   volume) emits the same labels, two runs are bit-identical (deterministic split-K, fixed graphs), interval 1 equals
   the key graph on every frame, the key-frame lookahead equals the sequential loop, and warping with a zero / an
@@ -15,6 +16,7 @@ from accel_b200 import engine as E
 from accel_b200 import scheduler, synthetic
 from accel_b200.engine import Engine
 from oracle import nets, ops
+from parity_util import label_report
 
 pytestmark = pytest.mark.gpu
 SCORE_TOL = 1e-3
@@ -40,11 +42,7 @@ def test_odd_size_parity(version, H, W):
     assert torch.equal(feat2.cpu(), rc["warping_feat_output"]) or \
         (feat2.cpu() - rc["warping_feat_output"]).abs().max().item() < SCORE_TOL
     ref = rc[nets.output_key(version)]
-    assert (score.cpu() - ref).abs().max().item() < SCORE_TOL
-    top2 = ref.topk(2, dim=1).values
-    margin = (top2[:, 0] - top2[:, 1])[0].numpy()
-    diff = label.cpu().numpy() != ops.argmax_channel(ref)[0]
-    assert not (diff & (margin > 2 * SCORE_TOL)).any()
+    label_report(label, score.cpu(), ref, min_decided=0.995, max_mismatch_frac=5e-4)
     eng.close()
 
 

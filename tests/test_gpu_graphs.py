@@ -8,6 +8,7 @@ from accel_b200 import predictor as P
 from accel_b200 import scheduler, synthetic
 from accel_b200.engine import Engine
 from oracle import nets, ops
+from parity_util import label_report
 from oracle import schedule as oracle_schedule
 
 pytestmark = pytest.mark.gpu
@@ -15,15 +16,10 @@ SCORE_TOL = 1e-3          # north-star: max-abs on the fp32 score volume
 H, W = 128, 256
 
 
-def _label_check(label, ref_score):
-    """Bit-exact labels are required wherever the oracle itself is decided: pixels whose oracle
-    top-2 margin is below 2*SCORE_TOL may legitimately flip inside the score tolerance."""
-    ref_label = ops.argmax_channel(ref_score)[0]
-    top2 = ref_score.topk(2, dim=1).values
-    margin = (top2[:, 0] - top2[:, 1])[0].numpy()
-    diff = label != ref_label
-    assert not (diff & (margin > 2 * SCORE_TOL)).any()
-    return int(diff.sum())
+def _label_check(label, ref_score, gpu_score):
+    """tests/parity_util.py: zero mismatches wherever the oracle's top-2 margin exceeds twice the MEASURED score
+    error, that set covers >= 99 % of these small frames, and the total number of flipped pixels is bounded."""
+    return label_report(label, gpu_score, ref_score, min_decided=0.99, max_mismatch_frac=1e-3)
 
 
 @pytest.fixture(scope="module")
@@ -46,7 +42,7 @@ def test_key_and_cur_graph_parity(version, frames):
     eng.key_forward(d0, feat, score, label)
     assert (feat.cpu() - rk["res5c_relu_output"]).abs().max().item() < SCORE_TOL
     assert (score.cpu() - rk["croped_score_output"]).abs().max().item() < SCORE_TOL
-    _label_check(label.cpu().numpy(), rk["croped_score_output"])
+    _label_check(label.cpu().numpy(), rk["croped_score_output"], score.cpu())
     flow = eng.flownet(d1, d0)
     assert (flow.cpu() - rc["flow"]).abs().max().item() < 1e-4
     # feed the ORACLE's key feature so the cur graph is checked on identical inputs
@@ -54,7 +50,7 @@ def test_key_and_cur_graph_parity(version, frames):
     assert (feat2.cpu() - rc["warping_feat_output"]).abs().max().item() < SCORE_TOL
     ref_score = rc[nets.output_key(version)]
     assert (score.cpu() - ref_score).abs().max().item() < SCORE_TOL
-    _label_check(label.cpu().numpy(), ref_score)
+    _label_check(label.cpu().numpy(), ref_score, score.cpu())
     # production mode (no score volume, no feature copy) yields the same labels
     label2 = torch.empty_like(label)
     eng.cur_forward(d1, d0, rk["res5c_relu_output"].to(dev), None, None, label2)
@@ -83,7 +79,7 @@ def test_reference_loop_through_predictor_shim(schedule, frames):
         assert g["is_key"] == r["is_key"]
         assert (g["score"].cpu() - r["score"]).abs().max().item() < SCORE_TOL
         assert (g["feat"].cpu() - r["feat"]).abs().max().item() < SCORE_TOL
-        _label_check(g["label"].cpu().numpy(), r["score"])
+        _label_check(g["label"].cpu().numpy(), r["score"], g["score"].cpu())
         assert torch.equal(g["label"], g["label_output"])      # fused argmax == argmax of the emitted volume
 
 
@@ -158,7 +154,7 @@ def test_r_head_fold_on_and_off_agree_with_oracle(version, frames, monkeypatch):
         label = torch.empty(H, W, dtype=torch.uint8, device=dev)
         eng.cur_forward(frames[1].to(dev), frames[0].to(dev), rk["res5c_relu_output"].to(dev), None, score, label)
         assert (score.cpu() - ref_score).abs().max().item() < SCORE_TOL
-        _label_check(label.cpu().numpy(), ref_score)
+        _label_check(label.cpu().numpy(), ref_score, score.cpu())
         scores[fold] = score.cpu()
         eng.close()
     assert (scores["1"] - scores["0"]).abs().max().item() < 2e-4
