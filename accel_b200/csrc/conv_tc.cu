@@ -16,6 +16,8 @@
 //   mainloop of tile i+1.  Small maps use deterministic split-K through an fp32 workspace.
 #include <cuda.h>
 #include <stdio.h>
+
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 
@@ -56,6 +58,13 @@ struct alignas(64) TcParams {
   int tma_out;     // 1: the main output leaves through shared memory + TMA tensor stores (3-D map), 2: 5-D map (transposed-conv phase)
   int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = no TMA stores
   int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
+  // A-slab reuse (stride-1 multi-tap layers whose tile is one full 128-pixel row segment): the taps of one filter row
+  // (same dy, dx = dxmin .. dxmax) read the SAME source pixels shifted by whole pixels, so ONE TMA box of
+  // slab_w = 128 + dxmax - dxmin pixels x 64 channels serves all ndx of them: the MMA of tap dx starts
+  // (dx - dxmin) rows (128 bytes each) into the slab, the descriptor's base-offset field carrying the swizzle phase.
+  // A bytes through L2 -> SM drop by ndx (3 for a 3x3); the weights keep their own ring.
+  int aslab, ndx, dxmin, slab_w, slab_pl, sa_stages, slab_bo;
+  unsigned ring_bytes;   // operand rings in front of the epilogue staging area
   int kchains;     // 2: the K slices of a tile alternate between the two TMEM accumulator buffers and the epilogue sums
                    // them in fp32 (round-to-nearest): the tensor core's own accumulation truncates, so its error grows
                    // with the number of accumulation steps per accumulator; long-K layers only
@@ -66,6 +75,14 @@ struct alignas(64) TcParams {
   int8_t dx[kMaxTaps];
 };
 
+
+// Descriptor of a SWIZZLE_128B K-major operand that starts a whole number of 128-byte rows into a 1024-byte swizzle
+// atom: bits [49,52) = (start address >> 7) & 7 tell the tensor core the swizzle phase of the first row.
+__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t saddr, int mode) {
+  if (mode == 0) return tc::umma_desc(saddr);                                                   // address only
+  if (mode == 2) return tc::umma_desc(saddr & ~1023u) | ((uint64_t)((saddr >> 7) & 7u) << 49);   // atom address + phase
+  return tc::umma_desc(saddr) | ((uint64_t)((saddr >> 7) & 7u) << 49);
+}
 
 // NCAT: hi*hi and hi*lo issued as ONE MMA over [B_hi ; B_lo] (N = 2*BN <= 256), see the MMA issuer.
 // FUSED: in-kernel split-K tail (TcParams::fused); a template parameter so that the default instantiations keep their
@@ -83,7 +100,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = BM * 128u, b_bytes = (uint32_t)P.BN * 128u;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  const uint32_t stg0 = smem0 + (uint32_t)P.stages * stage_bytes;   // epilogue staging (1024-byte aligned)
+  const uint32_t stg0 = smem0 + P.ring_bytes;                       // epilogue staging (1024-byte aligned)
+  // A-slab mode: [sa_stages x (slab hi | slab lo)] [stages x (B_hi | B_lo)]
+  __shared__ __align__(8) uint64_t abars[8];
+  const uint32_t afull0 = smem_u32(&abars[0]), aempty0 = smem_u32(&abars[4]);
+  const uint32_t bring0 = smem0 + (uint32_t)P.sa_stages * 2u * (uint32_t)P.slab_pl;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
@@ -99,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(tempty0 + 8 * a, kEpiWarps);
     }
     for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&res_bars[a]), 1);
+    for (int a = 0; a < 8; ++a) mbar_init(smem_u32(&abars[a]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -120,7 +142,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (lane == 0 && P.aslab) {
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      const uint32_t slab_tx = 2u * (uint32_t)P.slab_w * 128u;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % P.splits, tile = item / P.splits;
+        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
+        const int kb = (int)(((long long)P.kiters * split) / P.splits);
+        const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
+        for (int it = kb; it < ke; ++it) {
+          // K order: filter row j, channel chunk kc, then the ndx taps of the row (they share one slab)
+          const int outer = it / P.ndx, i = it - outer * P.ndx;
+          const int j = outer / P.chunks, kc = outer - j * P.chunks;
+          const int t = j * P.ndx + i;
+          if (i == 0 || it == kb) {
+            mbar_wait(aempty0 + 8 * as, aph ^ 1);
+            const uint32_t fa = afull0 + 8 * as;
+            mbar_arrive_expect_tx(fa, slab_tx);
+            const uint32_t dst = smem0 + (uint32_t)as * 2u * (uint32_t)P.slab_pl;
+            tma_load_3d(dst, &P.a_hi, fa, kc * BK, x0 + P.dxmin, y0 + P.dy[t]);
+            tma_load_3d(dst + (uint32_t)P.slab_pl, &P.a_lo, fa, kc * BK, x0 + P.dxmin, y0 + P.dy[t]);
+            if (++as == P.sa_stages) { as = 0; aph ^= 1; }
+          }
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t fb = full0 + 8 * s;
+          mbar_arrive_expect_tx(fb, 2 * b_bytes);
+          const uint32_t sb = bring0 + (uint32_t)s * 2u * b_bytes;
+          const int kcol = t * P.Cin_pad + kc * BK;
+          tma_load_2d(sb, &P.b_hi, fb, kcol, nt * P.BN);
+          tma_load_2d(sb + b_bytes, &P.b_lo, fb, kcol, nt * P.BN);
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -162,6 +218,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool two = P.kchains == 2;
       int s = 0, acc = 0;
       uint32_t ph = 0, accph = 0;
+      int nas = 0, cur = 0;                               // A-slab ring: next slot to consume, slot in use
+      uint32_t aphc = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int split = item % P.splits;
         const int kb = (int)(((long long)P.kiters * split) / P.splits);
@@ -175,11 +233,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         int q = 0;                                        // K slice counter of this item
         for (int it = kb; it < ke; ++it) {
-          mbar_wait(full0 + 8 * s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem0 + s * stage_bytes;
-          const uint64_t ah = umma_desc(sa), al = umma_desc(sa + a_bytes);
-          const uint64_t bh = umma_desc(sa + 2 * a_bytes), bl = umma_desc(sa + 2 * a_bytes + b_bytes);
+          uint64_t ah, al, bh, bl;
+          bool slab_done = false;
+          if (P.aslab) {
+            const int outer = it / P.ndx, i = it - outer * P.ndx;
+            const int t = (outer / P.chunks) * P.ndx + i;
+            if (i == 0 || it == kb) {
+              cur = nas;
+              mbar_wait(afull0 + 8 * cur, aphc);
+              if (++nas == P.sa_stages) { nas = 0; aphc ^= 1; }
+            }
+            slab_done = i == P.ndx - 1 || it == ke - 1;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = smem0 + (uint32_t)cur * 2u * (uint32_t)P.slab_pl + (uint32_t)(P.dx[t] - P.dxmin) * 128u;
+            const uint32_t sb = bring0 + (uint32_t)s * 2u * b_bytes;
+            ah = umma_desc_rows(a0, P.slab_bo); al = umma_desc_rows(a0 + (uint32_t)P.slab_pl, P.slab_bo);
+            bh = umma_desc(sb); bl = umma_desc(sb + b_bytes);
+          } else {
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem0 + s * stage_bytes;
+            ah = umma_desc(sa); al = umma_desc(sa + a_bytes);
+            bh = umma_desc(sa + 2 * a_bytes); bl = umma_desc(sa + 2 * a_bytes + b_bytes);
+          }
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k, ++q) {
             const uint64_t adv = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes along K inside the swizzle atom
@@ -201,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
           }
           umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
+          if (slab_done) umma_commit(aempty0 + 8 * cur);  // ... and the A slab after the last tap that reads it
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
         if (two) {
@@ -851,7 +929,37 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   int stages = (int)((kSmemBudget - (want_stage ? kStageOut : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   P.stages = stages;
-  plan->smem = stages * stage_bytes + 1024 + (want_stage ? kStageOut : 0);
+  P.ring_bytes = (unsigned)(stages * stage_bytes);
+  // A-slab reuse (TcParams::aslab): stride 1, one-row tiles (BW = 128), taps on a regular ndy x ndx grid.
+  // MEASURED SLOWER and therefore off unless ACCEL_TC_ASLAB=1 (profiles/r02_layer_slab_sweep.txt): a third less operand
+  // traffic from L2, yet res4 3x3 35 -> 44 us -- the mainloop is bound by shared-memory bandwidth (tensor-core operand
+  // reads + TMA writes), and row-shifted operands cost the tensor core more shared-memory wavefronts than they save.
+  P.aslab = 0;
+  P.sa_stages = 1; P.slab_pl = 0; P.ndx = 1; P.dxmin = 0; P.slab_w = 0;
+  if (!P.stride2 && !P.pair && P.BH == 1 && P.ntaps > 1 && env_int("ACCEL_TC_ASLAB", 0) != 0) {
+    int ndx = 1;
+    while (ndx < P.ntaps && P.dy[ndx] == P.dy[0]) ++ndx;
+    bool grid_ok = ndx >= 2 && P.ntaps % ndx == 0;
+    int dxmin = P.dx[0], dxmax = P.dx[0];
+    for (int i = 0; grid_ok && i < ndx; ++i) { dxmin = std::min(dxmin, (int)P.dx[i]); dxmax = std::max(dxmax, (int)P.dx[i]); }
+    for (int t = 0; grid_ok && t < P.ntaps; ++t)
+      grid_ok = P.dy[t] == P.dy[(t / ndx) * ndx] && P.dx[t] == P.dx[t % ndx];
+    const int slab_w = P.BW + dxmax - dxmin;
+    const size_t slab_pl = ((size_t)slab_w * 128 + 1023) / 1024 * 1024;
+    int sa = env_int("ACCEL_TC_ASLAB_SA", 2);
+    if (sa < 1 || sa > 4) sa = 2;
+    const size_t b_stage = 2 * (size_t)bn * 128;
+    const long long left = (long long)kSmemBudget - (want_stage ? kStageOut : 0) - (long long)sa * 2 * slab_pl;
+    int sb = left > 0 ? (int)(left / (long long)b_stage) : 0;
+    if (sb > kMaxStages) sb = kMaxStages;
+    if (grid_ok && slab_w <= 256 && sb >= 3) {
+      P.slab_bo = env_int("ACCEL_TC_ASLAB_BO", 0);
+      P.aslab = 1; P.ndx = ndx; P.dxmin = dxmin; P.slab_w = slab_w; P.slab_pl = (int)slab_pl; P.sa_stages = sa;
+      P.stages = stages = sb;
+      P.ring_bytes = (unsigned)(sa * 2 * slab_pl + sb * b_stage);
+    }
+  }
+  plan->smem = P.ring_bytes + 1024 + (want_stage ? kStageOut : 0);
   // hi*hi and hi*lo as one N = 2*BN MMA (see the MMA issuer): needs 4*BN TMEM columns, i.e. BN <= 128.
   // ACCEL_TC_NCAT: -1 auto (on whenever it fits), 0 off, 1 on.
   {
@@ -880,7 +988,11 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     // 2 always, unset = when a split walks at least ACCEL_TC_CHAINS_MIN (6) K stages, i.e. 24 slices of 16.
     const int mode = env_int("ACCEL_TC_CHAINS", -1);
     const int kps = (P.kiters + splits - 1) / splits;
-    const bool want = mode == 2 || (mode < 0 && kps >= env_int("ACCEL_TC_CHAINS_MIN", 6));
+    // ACCEL_TC_CHAINS_MULTI=0: only where every CTA holds a single item (nothing to overlap an epilogue with anyway)
+    const bool single_wave = (long long)tiles * splits <= (long long)num_sms;
+    const bool want = mode == 2 || (mode < 0 && kps >= env_int("ACCEL_TC_CHAINS_MIN", 6) &&
+                                    (single_wave || kps >= env_int("ACCEL_TC_CHAINS_MULTI_MIN", 32) ||
+                                     env_int("ACCEL_TC_CHAINS_MULTI", 0) != 0));
     P.kchains = (want && !P.pair && mode != 0 && mode != 1) ? 2 : 1;
   }
   {
@@ -891,7 +1003,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     if (E.res_hi) v = v && al32(E.res_hi) && al32(E.res_lo) && E.res_ld % 16 == 0;
     if (E.out2_hi) v = v && al32(E.out2_hi) && al32(E.out2_lo) && E.out2_ld % 16 == 0;
     P.vec32 = v ? 1 : 0;
-    P.krot = env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
+    P.krot = P.aslab ? 0 : env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
     P.debug = env_int("ACCEL_TC_DEBUG", 0);
   }
 
@@ -901,7 +1013,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   if (!P.stride2) {
     cuuint64_t dims[3] = {(cuuint64_t)C.Cin, (cuuint64_t)C.Win, (cuuint64_t)C.Hin};
     cuuint64_t str[2] = {(cuuint64_t)C.in_ld * e, (cuuint64_t)C.in_ld * C.Win * e};
-    cuuint32_t box[3] = {BK, (cuuint32_t)P.BW, (cuuint32_t)P.BH};
+    cuuint32_t box[3] = {BK, (cuuint32_t)(P.aslab ? P.slab_w : P.BW), (cuuint32_t)P.BH};
     ok = ok && encode(&P.a_hi, C.in_hi, 3, dims, str, box, err, errlen);
     ok = ok && encode(&P.a_lo, C.in_lo, 3, dims, str, box, err, errlen);
   } else {

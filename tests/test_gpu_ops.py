@@ -149,6 +149,47 @@ def test_conv_layer_matches_torch(case, engine):
     assert (out - ref).abs().max().item() < _tol(ref)
 
 
+# Wide maps (W >= 128): one-row tiles, where the taps of a filter row share one TMA slab (TcParams::aslab, tap-shifted
+# shared-memory descriptors) -- incl. a right border that is not a multiple of the tile, dilation 2 (the offset convs of
+# res5), few and many output channels, a long K (two accumulation chains) and a transposed-conv phase set.
+WIDE_CASES = [
+    # cin, cout, h, w, k, pad, dil
+    (64, 64, 6, 128, 3, 1, 1),
+    (256, 256, 4, 128, 3, 1, 1),
+    (128, 128, 3, 256, 3, 1, 1),
+    (96, 40, 5, 160, 3, 1, 1),
+    (512, 72, 3, 128, 3, 2, 2),
+    (194, 2, 4, 256, 3, 1, 1),
+    (512, 512, 2, 128, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("slab", ["0", "1"])
+@pytest.mark.parametrize("case", WIDE_CASES)
+def test_conv_layer_wide_rows_slab_reuse(case, slab, monkeypatch):
+    monkeypatch.setenv("ACCEL_TC_ASLAB", slab)          # 1 = the tap-shifted slab mode (measured slower: off by default)
+    cin, cout, h, w, k, p, d = case
+    x = _rand(1, cin, h, w, seed=20)
+    wt = _rand(cout, cin, k, k, seed=21, scale=(2.0 / (cin * k * k)) ** 0.5)
+    scale, shift = torch.rand(cout, generator=torch.Generator().manual_seed(22)) + 0.5, _rand(cout, seed=23, scale=0.1)
+    ref = F.conv2d(x, wt, None, 1, p, d) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = _rand(*ref.shape, seed=24)
+    ref = F.relu(ref + res)
+    out = E.conv_layer(x.to(DEV), wt, "conv", 1, p, d, scale, shift, act=1, residual=res.to(DEV), engine=2).cpu()
+    assert (out - ref).abs().max().item() < _tol(ref)
+
+
+@pytest.mark.parametrize("slab", ["0", "1"])
+@pytest.mark.parametrize("cin,cout,h,w", [(256, 128, 3, 128), (130, 64, 2, 192)])
+def test_deconv_layer_wide_rows_slab_reuse(cin, cout, h, w, slab, monkeypatch):
+    monkeypatch.setenv("ACCEL_TC_ASLAB", slab)
+    x = _rand(1, cin, h, w, seed=30)
+    wt = _rand(cin, cout, 4, 4, seed=31, scale=(2.0 / (cin * 4)) ** 0.5)
+    ref = F.conv_transpose2d(x, wt, None, 2, 1)
+    out = E.conv_layer(x.to(DEV), wt, "deconv", engine=2).cpu()
+    assert out.shape == ref.shape and (out - ref).abs().max().item() < _tol(ref)
+
+
 @pytest.mark.parametrize("case", [(2048, 1024, 8, 16, 1, 1, 0, 1), (512, 512, 2, 4, 3, 1, 1, 1), (1026, 2, 2, 4, 3, 1, 1, 1)])
 def test_fused_splitk_tail_is_bit_identical(case, monkeypatch):
     """ACCEL_TC_FUSED_SPLITK=1 (the CTA that delivers a tile's last partial slab sums the slabs and runs the epilogue

@@ -28,6 +28,8 @@ LAYERS = {
     "res5_2a": (2048, 512, 64, 128, 1, 1, 0, 1, False),
     "res5_2c": (512, 2048, 64, 128, 1, 1, 0, 1, True),
     "fc6": (2048, 1024, 64, 128, 1, 1, 0, 1, False),
+    "res5_off": (512, 18, 64, 128, 3, 1, 1, 1, False),
+    "flow_conv3_1": (256, 256, 128, 256, 3, 1, 1, 1, False),
     "flow_conv3": (128, 256, 128, 256, 5, 2, 2, 1, False),
     "flow_conv4_1": (512, 512, 32, 64, 3, 1, 1, 1, False),
     "flow_conv6_1": (1024, 1024, 8, 16, 3, 1, 1, 1, False),
@@ -51,6 +53,14 @@ PAIR_SWEEP = [
     {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "256", "ACCEL_TC_SPLITS": "2"},
     {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "256", "ACCEL_TC_SPLITS": "3"},
     {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "128", "ACCEL_TC_SPLITS": "2"},
+]
+
+R02_SWEEP = [
+    {"ACCEL_TC_ASLAB": "0"},
+    {},
+    {"ACCEL_TC_ASLAB_SA": "3"},
+    {"ACCEL_TC_ASLAB_SA": "1"},
+    {"ACCEL_TC_ASLAB_BO": "1"},
 ]
 
 DEBUG_SWEEP = [
@@ -86,8 +96,9 @@ def main():
         ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
         wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
         r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
-        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP}.get(a.sweep, SWEEP):
-            for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR"):
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP}.get(a.sweep, SWEEP):
+            for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR", "ACCEL_TC_ASLAB",
+                       "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO"):
                 os.environ.pop(kk, None)
             os.environ.update(knobs)
             sys.stderr.write("%-14s %-44s " % (name, knobs))
