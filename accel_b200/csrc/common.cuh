@@ -31,7 +31,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // True the first time it is called for (slot, current device): cudaFuncSetAttribute is per device, and one process may
 // drive several GPUs (pred_eval_multiprocess uses one predictor pair per GPU from threads).
 bool first_time_on_device(int slot);
-enum { ONCE_CONV_TC = 0, ONCE_STEM_TC, ONCE_STEM, ONCE_WARP_STAGED_0, ONCE_WARP_STAGED_1, ONCE_WARP_STAGED_2, ONCE_WARP_STAGED_3, ONCE_SLOTS };
+enum { ONCE_CONV_TC = 0, ONCE_STEM_TC, ONCE_STEM, ONCE_WARP_STAGED_0, ONCE_WARP_STAGED_1, ONCE_WARP_STAGED_2, ONCE_WARP_STAGED_3, ONCE_WARP_FUSED, ONCE_WARP_FUSED_1, ONCE_SLOTS };
 
 bool pdl_enabled();   // graph.cu: ACCEL_PDL=1 turns it on (measured neutral on B200 for these plans, so off by default)
 
@@ -181,7 +181,21 @@ struct Epilogue {
   int osy, osx, ooy, oox;
   int OHf, OWf;
   int Cout;
+  // Batched plans stack their frames along H (OHf = frames * per-frame height): the split NHWC tensors are then
+  // simply taller, but fp32 planar outputs stay per frame, [frame][Cout][nchw_hw]:
+  int nchw_hw;               // pixels of ONE frame of the full output map (0 = OHf * OWf: a single frame)
+  int nchw_nb;               // only the first nchw_nb frames receive the fp32 copy (0 = all)
 };
+
+// Offset of channel 0 of full-map pixel `pix` in an fp32 planar output (channel c sits c * hw further); false = this
+// frame gets no fp32 copy.
+__device__ __forceinline__ bool nchw_base(const Epilogue& e, int pix, size_t& base, size_t& hw) {
+  hw = e.nchw_hw ? (size_t)e.nchw_hw : (size_t)e.OHf * e.OWf;
+  const int b = (int)((size_t)pix / hw);
+  if (e.nchw_nb && b >= e.nchw_nb) return false;
+  base = (size_t)b * e.Cout * hw + ((size_t)pix - (size_t)b * hw);
+  return true;
+}
 
 // Applies the epilogue to NV (4 or 8) consecutive channels [c0, c0+NV) of full-map pixel `pix`.
 template <int NV>
@@ -198,7 +212,10 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& e, int pix, int c
     if (c < e.Cout) {
       float s = e.scale ? e.scale[c] : 1.f;
       float b = e.shift ? e.shift[c] : 0.f;
-      if (e.raw_nchw) e.raw_nchw[(size_t)c * ((size_t)e.OHf * e.OWf) + pix] = v[i] * s;
+      if (e.raw_nchw) {
+        size_t nb_, hw_;
+        if (nchw_base(e, pix, nb_, hw_)) e.raw_nchw[nb_ + (size_t)c * hw_] = v[i] * s;
+      }
       x = fmaf(v[i], s, b);
       if (e.res_hi) x += r[i];
       x = apply_act(x, e.act);
@@ -210,10 +227,12 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& e, int pix, int c
     else store4(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
   }
   if (e.out_nchw) {
-    size_t plane = (size_t)e.OHf * e.OWf;
+    size_t base, plane;
+    if (nchw_base(e, pix, base, plane)) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (c0 + i < e.Cout) e.out_nchw[(size_t)(c0 + i) * plane + pix] = v[i];
+      for (int i = 0; i < NV; ++i)
+        if (c0 + i < e.Cout) e.out_nchw[base + (size_t)(c0 + i) * plane] = v[i];
+    }
   }
   if (e.out2_hi) {
     float w[NV];
@@ -244,7 +263,8 @@ struct ConvParams {
   int8_t dy[kMaxTaps];
   int8_t dx[kMaxTaps];
   int stride;
-  int Ho, Wo;          // loop space (== output size except for transposed-conv phases)
+  int Ho, Wo;          // loop space (== output size except for transposed-conv phases), ONE frame
+  int nb;              // frames (0/1 = one): input, outputs and residual hold `nb` frames stacked densely along H
   int splits;          // split-K factor (1 = epilogue in-kernel)
   float* partial;      // [splits][Ho*Wo][Cout_pad] fp32 when splits > 1
   Epilogue epi;

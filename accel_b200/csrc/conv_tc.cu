@@ -51,7 +51,9 @@ struct alignas(64) TcParams {
   float* partial;
   int BW, BH, BN, stages;
   int tiles_x, tiles_y, n_tiles, splits, kiters, chunks, ntaps;
-  int stride2, Cin_pad, Ho, Wo, Cout_pad, tmem_cols;
+  int stride2, Cin_pad, Ho, Wo, Cout_pad, tmem_cols;   // Ho: the loop space's height over ALL frames (nb * Hof)
+  int nb, Hof;     // batched plans: nb frames stacked along H, Hof output rows each; tiles never straddle two frames and
+                   // the A operand's 4-D tensor map (channel, x, y, frame) keeps the conv padding per frame
   int krot;
   int pair;        // 1: conv_tc2_kernel (cta_group::2 pairs)
   int ncat;        // 1: hi*hi and hi*lo issued as ONE MMA over [B_hi ; B_lo] (N = 2*BN, two accumulator halves summed in the epilogue)
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
         const int kb = (int)(((long long)P.kiters * split) / P.splits);
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
+        const int fr = y0 / P.Hof, yl = y0 - fr * P.Hof;         // frame of the tile and its first row inside that frame
         for (int it = kb; it < ke; ++it) {
           // K order: filter row j, channel chunk kc, then the ndx taps of the row (they share one slab)
           const int outer = it / P.ndx, i = it - outer * P.ndx;
@@ -162,8 +165,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t fa = afull0 + 8 * as;
             mbar_arrive_expect_tx(fa, slab_tx);
             const uint32_t dst = smem0 + (uint32_t)as * 2u * (uint32_t)P.slab_pl;
-            tma_load_3d(dst, &P.a_hi, fa, kc * BK, x0 + P.dxmin, y0 + P.dy[t]);
-            tma_load_3d(dst + (uint32_t)P.slab_pl, &P.a_lo, fa, kc * BK, x0 + P.dxmin, y0 + P.dy[t]);
+            tma_load_4d(dst, &P.a_hi, fa, kc * BK, x0 + P.dxmin, yl + P.dy[t], fr);
+            tma_load_4d(dst + (uint32_t)P.slab_pl, &P.a_lo, fa, kc * BK, x0 + P.dxmin, yl + P.dy[t], fr);
             if (++as == P.sa_stages) { as = 0; aph ^= 1; }
           }
           mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
         const int kb = (int)(((long long)P.kiters * split) / P.splits);
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
+        const int fr = y0 / P.Hof, yl = y0 - fr * P.Hof;         // frame of the tile and its first row inside that frame
         const int rot = P.krot ? (int)(((unsigned)item * 5u) % (unsigned)(ke - kb)) : 0;
         for (int i = kb; i < ke; ++i) {
           int it = i + rot;                               // each CTA walks K from its own offset: neighbours do not
@@ -199,8 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
             tma_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
           } else {
-            tma_load_3d(sa, &P.a_hi, fb, kc * BK, x0 + dx, y0 + dy);
-            tma_load_3d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, y0 + dy);
+            tma_load_4d(sa, &P.a_hi, fb, kc * BK, x0 + dx, yl + dy, fr);
+            tma_load_4d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, yl + dy, fr);
           }
           const int kcol = t * P.Cin_pad + kc * BK;
           tma_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nt * P.BN);
@@ -856,6 +860,23 @@ bool tc_supported(const ConvParams& P) {
   return true;
 }
 
+// Can `C.nb` frames share one launch?  Tiles are BH x BW boxes of the frames stacked along H: no tile may straddle two
+// frames, and a stride-2 layer (5-D view, frames folded into H/2) must not reach outside its frame vertically.
+bool tc_batchable(const ConvParams& C) {
+  if (C.nb <= 1) return true;
+  if (!tc_supported(C)) return false;
+  if (env_int("ACCEL_TC_PAIR", 0) != 0) return false;
+  int bw = 1;
+  while (bw * 2 <= C.Wo && bw * 2 <= BM) bw *= 2;
+  const int bh = BM / bw;
+  if (C.Ho % bh) return false;
+  if (C.stride == 2) {
+    for (int t = 0; t < C.ntaps; ++t)
+      if (C.dy[t] < 0 || (C.dy[t] >> 1) + C.Ho > C.Hin / 2) return false;
+  }
+  return true;
+}
+
 TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) {
   if (!tc_supported(C)) {
     snprintf(err, errlen, "shape not supported by the tcgen05 engine");
@@ -870,7 +891,10 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   memcpy(P.dx, C.dx, sizeof(P.dx));
   P.stride2 = C.stride == 2;
   P.Cin_pad = C.Cin_pad;
-  P.Ho = C.Ho; P.Wo = C.Wo; P.Cout_pad = C.Cout_pad;
+  const int nb = C.nb > 1 ? C.nb : 1;
+  const int HoT = C.Ho * nb;                    // frames stacked along H: the loop space is simply taller
+  P.nb = nb; P.Hof = C.Ho;
+  P.Ho = HoT; P.Wo = C.Wo; P.Cout_pad = C.Cout_pad;
   P.chunks = (C.Cin + BK - 1) / BK;            // channel chunks that hold real data (padding chunks are all-zero)
   P.kiters = P.ntaps * P.chunks;
 
@@ -879,7 +903,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   while (bw * 2 <= C.Wo && bw * 2 <= BM) bw *= 2;
   P.BW = bw; P.BH = BM / bw;
   P.tiles_x = (C.Wo + P.BW - 1) / P.BW;
-  P.tiles_y = (C.Ho + P.BH - 1) / P.BH;
+  P.tiles_y = (HoT + P.BH - 1) / P.BH;
   // Tile width / split-K from a small cost model (cycles per CTA).  Measured on B200 (tools/bench_layer.py):
   // the fp16x3 mainloop is bound by shared-memory bandwidth -- per 64-channel K step the tensor core reads
   // 12 x (4 KB of A + 32*BN bytes of B) and TMA writes 32 KB + 256*BN bytes, at ~88 B/cycle effective --
@@ -900,7 +924,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
       const long long work = (long long)tiles * sp;
       const int waves = (int)((work + num_sms - 1) / num_sms);
       double cost = (double)waves * (kps * per_k + 10.0 * bn) + 6000.0;
-      if (sp > 1) cost += 8000.0 + 2.0 * sp * (double)C.Ho * C.Wo * C.Cout_pad * 4.0 / 3000.0;
+      if (sp > 1) cost += 8000.0 + 2.0 * sp * (double)HoT * C.Wo * C.Cout_pad * 4.0 / 3000.0;
       if (cost < best_cost) { best_cost = cost; best_bn = bn; best_splits = sp; }
     }
   }
@@ -972,7 +996,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
 
   const int tiles = tiles_m * P.n_tiles;
   P.splits = splits;
-  plan->partial_bytes = splits > 1 ? (size_t)splits * C.Ho * C.Wo * C.Cout_pad * sizeof(float) : 0;
+  plan->partial_bytes = splits > 1 ? (size_t)splits * HoT * C.Wo * C.Cout_pad * sizeof(float) : 0;
   P.fused = (splits > 1 && !P.pair && env_int("ACCEL_TC_FUSED_SPLITK", 0) != 0) ? 1 : 0;
   if (P.fused) plan->partial_bytes += (size_t)tiles * sizeof(unsigned);          // arrival counters behind the slabs
   int items = tiles * splits;
@@ -1010,14 +1034,24 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   // tensor maps ------------------------------------------------------------------------------------
   bool ok = true;
   const cuuint64_t e = sizeof(__half);
-  if (!P.stride2) {
+  if (!P.stride2 && P.pair) {
     cuuint64_t dims[3] = {(cuuint64_t)C.Cin, (cuuint64_t)C.Win, (cuuint64_t)C.Hin};
     cuuint64_t str[2] = {(cuuint64_t)C.in_ld * e, (cuuint64_t)C.in_ld * C.Win * e};
-    cuuint32_t box[3] = {BK, (cuuint32_t)(P.aslab ? P.slab_w : P.BW), (cuuint32_t)P.BH};
+    cuuint32_t box[3] = {BK, (cuuint32_t)P.BW, (cuuint32_t)P.BH};
     ok = ok && encode(&P.a_hi, C.in_hi, 3, dims, str, box, err, errlen);
     ok = ok && encode(&P.a_lo, C.in_lo, 3, dims, str, box, err, errlen);
+  } else if (!P.stride2) {
+    // (channel, x, y, frame): out-of-image rows / columns are zero-filled per frame, so the conv padding stays right
+    // when several frames share one launch
+    cuuint64_t dims[4] = {(cuuint64_t)C.Cin, (cuuint64_t)C.Win, (cuuint64_t)C.Hin, (cuuint64_t)nb};
+    cuuint64_t str[3] = {(cuuint64_t)C.in_ld * e, (cuuint64_t)C.in_ld * C.Win * e, (cuuint64_t)C.in_ld * C.Win * C.Hin * e};
+    cuuint32_t box[4] = {BK, (cuuint32_t)(P.aslab ? P.slab_w : P.BW), (cuuint32_t)P.BH, 1};
+    ok = ok && encode(&P.a_hi, C.in_hi, 4, dims, str, box, err, errlen);
+    ok = ok && encode(&P.a_lo, C.in_lo, 4, dims, str, box, err, errlen);
   } else {
-    cuuint64_t dims[5] = {(cuuint64_t)C.Cin, 2, (cuuint64_t)C.Win / 2, 2, (cuuint64_t)C.Hin / 2};
+    // stride 2: [H/2][2][W/2][2][C]; the frames fold into the outermost dimension (tc_batchable() only admits layers
+    // whose taps never leave the frame vertically: the 1x1 / stride-2 convs of the bottleneck nets)
+    cuuint64_t dims[5] = {(cuuint64_t)C.Cin, 2, (cuuint64_t)C.Win / 2, 2, (cuuint64_t)C.Hin / 2 * nb};
     cuuint64_t str[4] = {(cuuint64_t)C.in_ld * e, 2 * (cuuint64_t)C.in_ld * e, (cuuint64_t)C.in_ld * C.Win * e,
                          2 * (cuuint64_t)C.in_ld * C.Win * e};
     cuuint32_t box[5] = {BK, 1, (cuuint32_t)P.BW, 1, (cuuint32_t)P.BH};

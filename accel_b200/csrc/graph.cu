@@ -36,8 +36,11 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 Graph::~Graph() {
   for (auto& kv : seqs_)
-    for (auto& op : kv.second)
+    for (auto& op : kv.second) {
       if (op.tc) tc_plan_destroy(op.tc);
+      for (TcPlan* p : op.frame_tc)
+        if (p) tc_plan_destroy(p);
+    }
   for (auto& kv : seqs_)
     for (auto& op : kv.second)
       if (op.stem_tc) stem_tc_plan_destroy(op.stem_tc);
@@ -64,13 +67,14 @@ int Graph::num_sms_hint() const {
   return 148;
 }
 
-int Graph::new_tensor(int C, int H, int W, bool f32) {
+int Graph::new_tensor(int C, int H, int W, bool f32, int nb) {
   Buffer b;
   Tensor t;
   t.C = C; t.H = H; t.W = W; t.f32 = f32;
+  t.nb = nb < 1 ? 1 : nb;
   t.ld = f32 ? C : round_up(C, 16);   // 32-byte pixel rows: the conv epilogues move 256-bit sectors
   b.f32 = f32;
-  b.elems = (size_t)H * W * t.ld;
+  b.elems = (size_t)H * W * t.ld * t.nb;
   bufs_.push_back(b);
   t.buf = (int)bufs_.size() - 1;
   tensors_.push_back(t);
@@ -81,6 +85,14 @@ int Graph::new_view(int base, int coff, int C) {
   Tensor t = tensors_[base];
   t.coff = tensors_[base].coff + coff;
   t.C = C;
+  tensors_.push_back(t);
+  return (int)tensors_.size() - 1;
+}
+
+int Graph::frame_view(int base, int first_frame, int nb) {
+  Tensor t = tensors_[base];
+  t.foff = tensors_[base].foff + first_frame;
+  t.nb = nb;
   tensors_.push_back(t);
   return (int)tensors_.size() - 1;
 }
@@ -107,7 +119,7 @@ static void register_epi_params(Graph& g, const EpiSpec& e, int cout) {
 }
 
 int Graph::stem(std::vector<Op>& s, const std::string& stage, int ext0, int ext1, int Hs, int Ws, bool pool,
-                float in_mul, const std::string& bn_in, const std::string& wname, int cin, EpiSpec e) {
+                float in_mul, const std::string& bn_in, const std::string& wname, int cin, EpiSpec e, int out, int frame) {
   Op op{};
   op.type = OP_STEM;
   op.stage = stage;
@@ -129,7 +141,8 @@ int Graph::stem(std::vector<Op>& s, const std::string& stage, int ext0, int ext1
   op.in = cin;            // stems carry the channel count here
   op.stem.Hs = Hs;
   op.stem.Ws = Ws;
-  op.out = new_tensor(64, Ho, Wo);
+  op.out = out >= 0 ? out : new_tensor(64, Ho, Wo);
+  op.frame = frame;
   op.flops = 2.0 * 64 * cin * 49 * Ho * Wo;
   s.push_back(op);
   return op.out;
@@ -150,10 +163,10 @@ int Graph::conv(std::vector<Op>& s, const std::string& stage, int in, const std:
   register_epi_params(*this, e, cout);
   const int Ho = (ti.H + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;
   const int Wo = (ti.W + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;
-  if (out < 0 && !e.no_split_out) out = new_tensor(cout, Ho, Wo);
+  if (out < 0 && !e.no_split_out) out = new_tensor(cout, Ho, Wo, false, ti.nb);
   op.out = out;
   op.epi = e;
-  op.flops = 2.0 * cout * ti.C * k * k * Ho * Wo;
+  op.flops = 2.0 * cout * ti.C * k * k * Ho * Wo * ti.nb;
   op.conv.Ho = Ho;
   op.conv.Wo = Wo;
   s.push_back(op);
@@ -176,7 +189,7 @@ int Graph::deconv4(std::vector<Op>& s, const std::string& stage, int in, const s
     if (!seen) folds_.push_back({wname + "_weight", wname_in + "_weight", fold_1x1 + "_weight", ti.C, mid, cout});
   }
   register_epi_params(*this, e, cout);
-  if (out < 0) out = new_tensor(cout, 2 * ti.H, 2 * ti.W);
+  if (out < 0) out = new_tensor(cout, 2 * ti.H, 2 * ti.W, false, ti.nb);
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       Op op{};
@@ -190,7 +203,7 @@ int Graph::deconv4(std::vector<Op>& s, const std::string& stage, int in, const s
       op.weight = wname + "_weight";
       op.cout = cout; op.ksize = 4; op.stride = 1;
       op.epi = e;
-      op.flops = 2.0 * cout * ti.C * 4 * ti.H * ti.W;
+      op.flops = 2.0 * cout * ti.C * 4 * ti.H * ti.W * ti.nb;
       op.conv.Ho = ti.H;
       op.conv.Wo = ti.W;
       s.push_back(op);
@@ -201,7 +214,7 @@ int Graph::deconv4(std::vector<Op>& s, const std::string& stage, int in, const s
 int Graph::dcn(std::vector<Op>& s, const std::string& stage, int in, int offset_f32, const std::string& wname,
                int cout, int dg, EpiSpec e) {
   const Tensor ti = tensors_[in];
-  const int col = new_tensor(9 * ti.C, ti.H, ti.W);
+  const int col = new_tensor(9 * ti.C, ti.H, ti.W, false, ti.nb);
   Op g{};
   g.type = OP_DCN_COL;
   g.stage = stage;
@@ -218,9 +231,9 @@ int Graph::dcn(std::vector<Op>& s, const std::string& stage, int in, int offset_
   op.cout = cout; op.ksize = 3; op.stride = 1;
   add_param(op.weight, {cout, ti.C, 3, 3});
   register_epi_params(*this, e, cout);
-  op.out = new_tensor(cout, ti.H, ti.W);
+  op.out = new_tensor(cout, ti.H, ti.W, false, ti.nb);
   op.epi = e;
-  op.flops = 2.0 * cout * ti.C * 9 * ti.H * ti.W;
+  op.flops = 2.0 * cout * ti.C * 9 * ti.H * ti.W * ti.nb;
   op.conv.Ho = ti.H;
   op.conv.Wo = ti.W;
   s.push_back(op);
@@ -249,7 +262,7 @@ int Graph::pool(std::vector<Op>& s, const std::string& stage, int in, int k, int
   op.ksize = k; op.stride = stride; op.pad = pad; op.pool_max = is_max ? 1 : 0;
   op.epi = post;
   register_epi_params(*this, post, ti.C);
-  op.out = new_tensor(ti.C, osz(ti.H), osz(ti.W));
+  op.out = new_tensor(ti.C, osz(ti.H), osz(ti.W), false, ti.nb);
   s.push_back(op);
   return op.out;
 }
@@ -524,8 +537,8 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
   const int Ho = P.Ho, Wo = P.Wo;
   P = ConvParams{};
   P.Ho = Ho; P.Wo = Wo;
-  P.in_hi = bufs_[ti.buf].hi + ti.coff;
-  P.in_lo = bufs_[ti.buf].lo + ti.coff;
+  P.in_hi = hi_ptr(ti);
+  P.in_lo = lo_ptr(ti);
   P.in_ld = ti.ld; P.Hin = ti.H; P.Win = ti.W; P.Cin = ti.C;
   P.stride = op.stride;
   int wcin = ti.C;            // channel count in the weight tensor
@@ -587,14 +600,14 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
   E.scale = sc; E.shift = sh; E.act = op.epi.act; E.Cout = op.cout;
   if (op.epi.res >= 0) {
     const Tensor& tr = tensors_[op.epi.res];
-    E.res_hi = bufs_[tr.buf].hi + tr.coff;
-    E.res_lo = bufs_[tr.buf].lo + tr.coff;
+    E.res_hi = hi_ptr(tr);
+    E.res_lo = lo_ptr(tr);
     E.res_ld = tr.ld;
   }
   if (op.out >= 0) {
     const Tensor& to = tensors_[op.out];
-    E.out_hi = bufs_[to.buf].hi + to.coff;
-    E.out_lo = bufs_[to.buf].lo + to.coff;
+    E.out_hi = hi_ptr(to);
+    E.out_lo = lo_ptr(to);
     E.out_ld = to.ld;
   }
   if (op.epi.out2 >= 0) {
@@ -602,17 +615,31 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
     float *s2 = nullptr, *h2 = nullptr;
     if (!make_scale_shift2(op.epi, op.cout, &s2, &h2, err)) return false;
     E.scale2 = s2; E.shift2 = h2; E.act2 = op.epi.act2;
-    E.out2_hi = bufs_[t2.buf].hi + t2.coff;
-    E.out2_lo = bufs_[t2.buf].lo + t2.coff;
+    E.out2_hi = hi_ptr(t2);
+    E.out2_lo = lo_ptr(t2);
     E.out2_ld = t2.ld;
   }
-  if (op.epi.out_f32 >= 0) E.out_nchw = bufs_[tensors_[op.epi.out_f32].buf].f;
+  if (op.epi.out_f32 >= 0) E.out_nchw = f_ptr(tensors_[op.epi.out_f32]);
   if (op.kind == 1) {
     E.osy = E.osx = 2; E.ooy = op.phase_y; E.oox = op.phase_x;
     E.OHf = 2 * ti.H; E.OWf = 2 * ti.W;
   } else {
     E.osy = E.osx = 1; E.ooy = E.oox = 0;
     E.OHf = Ho; E.OWf = Wo;
+  }
+  E.nchw_hw = E.OHf * E.OWf;
+  E.nchw_nb = op.epi.f32_frames;
+
+  // frames of a batched plan: every operand holds the same number of frames, stacked densely
+  const int nb = ti.nb;
+  {
+    bool same = true;
+    if (op.out >= 0) same = same && tensors_[op.out].nb == nb;
+    if (op.epi.res >= 0) same = same && tensors_[op.epi.res].nb == nb;
+    if (op.epi.out2 >= 0) same = same && tensors_[op.epi.out2].nb == nb;
+    if (op.epi.out_f32 >= 0) same = same && (tensors_[op.epi.out_f32].nb == nb || (op.epi.f32_frames > 0 && tensors_[op.epi.out_f32].nb >= op.epi.f32_frames));
+    if (!same) { *err = "operands of '" + op.name + "' disagree on the number of frames"; return false; }
+    if (nb > 1 && (op.epi.ext_out != X_NONE || op.epi.ext_raw != X_NONE)) { *err = "batched layer '" + op.name + "' cannot write a caller tensor"; return false; }
   }
 
   // engine
@@ -622,28 +649,57 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
     else if (op.cout <= 8) eng = ENG_NARROW;
     else eng = ENG_FFMA;
   }
-  if (eng == ENG_TC) {
-    char msg[256] = {0};
-    const int sm_budget = op.sm_budget > 0 ? std::min(op.sm_budget, num_sms_)
-                          : (op.par_group && op.par_width > 1 && branches_enabled()) ? std::max(8, num_sms_ / op.par_width) : num_sms_;
-    op.tc = tc_plan_create(P, sm_budget, msg, sizeof(msg));
-    if (!op.tc) { *err = std::string("tcgen05 plan failed for ") + op.name + ": " + msg; return false; }
-    const size_t pb = tc_plan_partial_bytes(op.tc);
-    if (pb) {
-      float* part = (float*)dev_alloc(pb);
-      if (!part) { *err = "out of device memory (split-K workspace)"; return false; }
-      tc_plan_set_partial(op.tc, part);
-    }
-  } else if (eng == ENG_FFMA) {
-    P.splits = ffma_pick_splits(P, num_sms_);
-    if (P.splits > 1) {
-      P.partial = (float*)dev_alloc(ffma_partial_bytes(P, P.splits));
-      if (!P.partial) { *err = "out of device memory (split-K workspace)"; return false; }
-    }
-  } else {
-    P.splits = 1;
-  }
   op.engine = eng;
+  const int sm_budget = op.sm_budget > 0 ? std::min(op.sm_budget, num_sms_)
+                        : (op.par_group && op.par_width > 1 && branches_enabled()) ? std::max(8, num_sms_ / op.par_width) : num_sms_;
+  auto plan_one = [&](ConvParams& Q, TcPlan** plan) -> bool {
+    if (eng == ENG_TC) {
+      char msg[256] = {0};
+      *plan = tc_plan_create(Q, sm_budget, msg, sizeof(msg));
+      if (!*plan) { *err = std::string("tcgen05 plan failed for ") + op.name + ": " + msg; return false; }
+      const size_t pb = tc_plan_partial_bytes(*plan);
+      if (pb) {
+        float* part = (float*)dev_alloc(pb);
+        if (!part) { *err = "out of device memory (split-K workspace)"; return false; }
+        tc_plan_set_partial(*plan, part);
+      }
+    } else if (eng == ENG_FFMA) {
+      Q.splits = ffma_pick_splits(Q, num_sms_);
+      if (Q.splits > 1) {
+        Q.partial = (float*)dev_alloc(ffma_partial_bytes(Q, Q.splits));
+        if (!Q.partial) { *err = "out of device memory (split-K workspace)"; return false; }
+      }
+    } else {
+      Q.splits = 1;
+    }
+    return true;
+  };
+  P.nb = nb;
+  static const bool no_batch = [] { const char* e = getenv("ACCEL_TC_BATCH"); return e && e[0] == '0'; }();
+  if (nb > 1 && eng == ENG_TC && tc_batchable(P) && !no_batch) {
+    // ONE launch over all frames: the loop space is the frames stacked along H
+    E.OHf *= nb;
+    return plan_one(P, &op.tc);
+  }
+  if (nb == 1) return plan_one(P, &op.tc);
+  // frame by frame (a layer the batched kernel cannot take: padded stride-2 convs, partial tiles, CUDA-core engines)
+  P.nb = 1;
+  op.frame_convs.assign(nb, P);
+  op.frame_tc.assign(nb, nullptr);
+  for (int b = 0; b < nb; ++b) {
+    ConvParams& Q = op.frame_convs[b];
+    Q.in_hi += (size_t)b * frame_elems(ti); Q.in_lo += (size_t)b * frame_elems(ti);
+    Epilogue& F = Q.epi;
+    if (op.out >= 0) { const size_t fs = frame_elems(tensors_[op.out]); F.out_hi += b * fs; F.out_lo += b * fs; }
+    if (op.epi.res >= 0) { const size_t fs = frame_elems(tensors_[op.epi.res]); F.res_hi += b * fs; F.res_lo += b * fs; }
+    if (op.epi.out2 >= 0) { const size_t fs = frame_elems(tensors_[op.epi.out2]); F.out2_hi += b * fs; F.out2_lo += b * fs; }
+    if (F.out_nchw) {
+      if (op.epi.f32_frames > 0 && b >= op.epi.f32_frames) F.out_nchw = nullptr;
+      else F.out_nchw += (size_t)b * op.cout * F.nchw_hw;
+    }
+    F.nchw_nb = 0;
+    if (!plan_one(Q, &op.frame_tc[b])) return false;
+  }
   return true;
 }
 
@@ -754,7 +810,9 @@ bool Graph::finalize(std::string* err) {
           if (!make_scale_shift(op.epi, 64, prescale, &sc, &sh, err)) return false;
           Epilogue& E = S.epi;
           E.scale = sc; E.shift = sh; E.act = op.epi.act; E.Cout = 64;
-          E.out_hi = bufs_[to.buf].hi + to.coff; E.out_lo = bufs_[to.buf].lo + to.coff; E.out_ld = to.ld;
+          E.out_hi = hi_ptr(to) + (size_t)op.frame * frame_elems(to);
+          E.out_lo = lo_ptr(to) + (size_t)op.frame * frame_elems(to);
+          E.out_ld = to.ld;
           E.osy = E.osx = 1; E.OHf = to.H; E.OWf = to.W;
           if (use_tc) {
             char msg[256] = {0};
@@ -767,9 +825,9 @@ bool Graph::finalize(std::string* err) {
           const Tensor& ti = tensors_[op.in];
           const Tensor& to = tensors_[op.out];
           PoolParams& Q = op.pool;
-          Q.in_hi = bufs_[ti.buf].hi + ti.coff; Q.in_lo = bufs_[ti.buf].lo + ti.coff;
+          Q.in_hi = hi_ptr(ti); Q.in_lo = lo_ptr(ti);
           Q.in_ld = ti.ld; Q.Hin = ti.H; Q.Win = ti.W; Q.C = ti.C;
-          Q.out_hi = bufs_[to.buf].hi + to.coff; Q.out_lo = bufs_[to.buf].lo + to.coff;
+          Q.out_hi = hi_ptr(to); Q.out_lo = lo_ptr(to);
           Q.out_ld = to.ld; Q.Ho = to.H; Q.Wo = to.W;
           Q.kernel = op.ksize; Q.stride = op.stride; Q.pad = op.pad; Q.is_max = op.pool_max;
           Q.scale = Q.shift = nullptr; Q.act = op.epi.act;
@@ -785,11 +843,11 @@ bool Graph::finalize(std::string* err) {
           const Tensor& tf = tensors_[op.in2];
           const Tensor& to = tensors_[op.out];
           DcnColParams& D = op.dcn;
-          D.in_hi = bufs_[ti.buf].hi + ti.coff; D.in_lo = bufs_[ti.buf].lo + ti.coff;
+          D.in_hi = hi_ptr(ti); D.in_lo = lo_ptr(ti);
           D.in_ld = ti.ld; D.H = ti.H; D.W = ti.W; D.C = ti.C;
-          D.offset = bufs_[tf.buf].f;
+          D.offset = f_ptr(tf);
           D.dg = op.dg; D.dilate = op.dilate; D.pad = op.pad;
-          D.col_hi = bufs_[to.buf].hi; D.col_lo = bufs_[to.buf].lo; D.col_ld = to.ld;
+          D.col_hi = hi_ptr(to); D.col_lo = lo_ptr(to); D.col_ld = to.ld;
           if (ti.C % (8 * op.dg) != 0) { *err = "deformable conv needs C % (8*dg) == 0"; return false; }
           break;
         }
@@ -798,9 +856,9 @@ bool Graph::finalize(std::string* err) {
           WarpParams& Wp = op.warp;
           if (op.src_f32 >= 0) {                               // whole-interval plan: internal fp32 source / destination
             const Tensor& ts = tensors_[op.src_f32];
-            Wp.feat = bufs_[ts.buf].f;
-            Wp.out_nchw = bufs_[tensors_[op.dst_f32].buf].f;
-            Wp.flow = bufs_[tf.buf].f;
+            Wp.feat = f_ptr(ts);
+            Wp.out_nchw = f_ptr(tensors_[op.dst_f32]);
+            Wp.flow = f_ptr(tf);
             Wp.C = ts.C; Wp.H = tf.H; Wp.W = tf.W;
             break;
           }
@@ -809,7 +867,7 @@ bool Graph::finalize(std::string* err) {
             warp_scratch_ = (float*)dev_alloc((size_t)to.C * to.H * to.W * sizeof(float));
             if (!warp_scratch_) { *err = "out of device memory"; return false; }
           }
-          Wp.flow = bufs_[tf.buf].f;
+          Wp.flow = f_ptr(tf);
           Wp.H = tf.H; Wp.W = tf.W;
           if (op.out >= 0) Wp.C = tensors_[op.out].C;
           break;
@@ -818,19 +876,19 @@ bool Graph::finalize(std::string* err) {
           const Tensor& tf = tensors_[op.in];
           const Tensor& to = tensors_[op.out];
           UpflowParams& U = op.upflow;
-          U.flow = bufs_[tf.buf].f; U.H = tf.H; U.W = tf.W;
+          U.flow = f_ptr(tf); U.H = tf.H; U.W = tf.W;
           const std::vector<float>* w = host_param(op.weight, err);
           const std::vector<float>* b = w ? host_param(op.weight2, err) : nullptr;
           if (!w || !b) return false;
           memcpy(U.weight, w->data(), sizeof(U.weight));
           memcpy(U.bias, b->data(), sizeof(U.bias));
-          U.out_hi = bufs_[to.buf].hi + to.coff; U.out_lo = bufs_[to.buf].lo + to.coff; U.out_ld = to.ld;
+          U.out_hi = hi_ptr(to); U.out_lo = lo_ptr(to); U.out_ld = to.ld;
           break;
         }
         case OP_FUSE: {
           const Tensor& ta = tensors_[op.in];
           FuseParams& F = op.fuse;
-          F.a = bufs_[ta.buf].f; F.b = bufs_[tensors_[op.in2].buf].f; F.out = bufs_[tensors_[op.out].buf].f;
+          F.a = f_ptr(ta); F.b = f_ptr(tensors_[op.in2]); F.out = f_ptr(tensors_[op.out]);
           F.K = ta.C; F.h = ta.H; F.w_ = ta.W;
           const std::vector<float>* w = host_param(op.weight, err);
           if (!w) return false;
@@ -840,7 +898,7 @@ bool Graph::finalize(std::string* err) {
         case OP_TAIL: {
           const Tensor& ts = tensors_[op.in];
           TailParams& T = op.tail;
-          T.score = bufs_[ts.buf].f; T.K = ts.C; T.h = ts.H; T.w = ts.W; T.factor = 16;
+          T.score = f_ptr(ts); T.K = ts.C; T.h = ts.H; T.w = ts.W; T.factor = 16;
           T.bias = nullptr;
           if (!op.weight2.empty()) {
             const std::vector<float>* b = host_param(op.weight2, err);
@@ -876,6 +934,24 @@ bool Graph::finalize(std::string* err) {
           t.tail.fuse_a = f.fuse.a; t.tail.fuse_b = f.fuse.b; t.tail.fuse_w = f.fuse.w;
         }
       }
+  }
+  // warp followed by the layout conversion of its own output: the fused warp kernel writes the split NHWC copy itself
+  // (decided per launch: the source pointer is the caller's)
+  for (auto& kv : seqs_) {
+    std::vector<Op>& ops = kv.second;
+    for (size_t i = 0; i + 1 < ops.size(); ++i) {
+      Op &wp = ops[i], &cv = ops[i + 1];
+      if (wp.type != OP_WARP || cv.type != OP_TO_SPLIT) continue;
+      if (!(cv.src_warp || (cv.src_f32 >= 0 && cv.src_f32 == wp.dst_f32))) continue;
+      const Tensor& to = tensors_[cv.out];
+      wp.warp.out_hi = hi_ptr(to);
+      wp.warp.out_lo = lo_ptr(to);
+      wp.warp.out_ld = to.ld;
+      wp.warp.bias = cv.split_bias_dev;
+      wp.warp.act = cv.split_act;
+      if (wp.warp.C == 0) wp.warp.C = to.C;
+      wp.fuse_split = true;
+    }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) {
     *err = std::string("CUDA error during finalize: ") + cudaGetErrorString(cudaGetLastError());
@@ -1005,6 +1081,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
     if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, lane_join_ev_, 0);
     return e;
   };
+  const Op* skip_split = nullptr;
   for (auto& op : ops) {
     cudaStream_t stream = main_stream;
     if (use_branches && op.lane == 1 && lane_open) {
@@ -1047,51 +1124,86 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
       case OP_CONV: {
         float* ext_nchw = op.epi.ext_out != X_NONE ? (float*)ext[op.epi.ext_out] : nullptr;
         float* ext_raw = op.epi.ext_raw != X_NONE ? (float*)ext[op.epi.ext_raw] : nullptr;
-        if (op.engine == ENG_TC) {
-          ce = launch_conv_tc_ext(op.tc, ext_nchw, ext_raw, stream);
-          launches += tc_plan_launches(op.tc);
-        } else {
-          ConvParams P = op.conv;
-          if (ext_nchw) P.epi.out_nchw = ext_nchw;
-          P.epi.raw_nchw = ext_raw;
-          if (op.engine == ENG_NARROW) {
-            ce = launch_conv_narrow(P, stream);
-            ++launches;
+        const int nf = op.frame_convs.empty() ? 1 : (int)op.frame_convs.size();     // > 1: batched tensor, frame by frame
+        for (int b = 0; b < nf && ce == cudaSuccess; ++b) {
+          TcPlan* plan = op.frame_convs.empty() ? op.tc : op.frame_tc[b];
+          if (op.engine == ENG_TC) {
+            ce = launch_conv_tc_ext(plan, ext_nchw, ext_raw, stream);
+            launches += tc_plan_launches(plan);
           } else {
-            ce = launch_conv_ffma(P, stream);
-            launches += P.splits > 1 ? 2 : 1;
+            ConvParams P = op.frame_convs.empty() ? op.conv : op.frame_convs[b];
+            if (ext_nchw) P.epi.out_nchw = ext_nchw;
+            P.epi.raw_nchw = ext_raw;
+            if (op.engine == ENG_NARROW) {
+              ce = launch_conv_narrow(P, stream);
+              ++launches;
+            } else {
+              ce = launch_conv_ffma(P, stream);
+              launches += P.splits > 1 ? 2 : 1;
+            }
           }
         }
         break;
       }
-      case OP_POOL:
-        ce = launch_pool(op.pool, stream);
-        ++launches;
+      case OP_POOL: {
+        const Tensor& ti = tensors_[op.in];
+        const Tensor& to = tensors_[op.out];
+        for (int b = 0; b < ti.nb && ce == cudaSuccess; ++b) {       // frame by frame (window clipping is per frame)
+          PoolParams Q = op.pool;
+          Q.in_hi += (size_t)b * frame_elems(ti); Q.in_lo += (size_t)b * frame_elems(ti);
+          Q.out_hi += (size_t)b * frame_elems(to); Q.out_lo += (size_t)b * frame_elems(to);
+          ce = launch_pool(Q, stream);
+          ++launches;
+        }
         break;
-      case OP_DCN_COL:
-        ce = launch_dcn_col(op.dcn, stream);
-        ++launches;
+      }
+      case OP_DCN_COL: {
+        const Tensor& ti = tensors_[op.in];
+        const Tensor& tf = tensors_[op.in2];
+        const Tensor& to = tensors_[op.out];
+        for (int b = 0; b < ti.nb && ce == cudaSuccess; ++b) {       // frame by frame (sampling bounds are per frame)
+          DcnColParams D = op.dcn;
+          D.in_hi += (size_t)b * frame_elems(ti); D.in_lo += (size_t)b * frame_elems(ti);
+          D.offset += (size_t)b * frame_elems(tf);
+          D.col_hi += (size_t)b * frame_elems(to); D.col_lo += (size_t)b * frame_elems(to);
+          ce = launch_dcn_col(D, stream);
+          ++launches;
+        }
         break;
+      }
       case OP_WARP: {
         WarpParams Wp = op.warp;
-        if (op.src_f32 >= 0) {
-          ce = launch_warp(Wp, stream);
-          ++launches;
-          break;
+        if (op.src_f32 < 0) {
+          Wp.feat = (const float*)ext[op.ext_in0];
+          Wp.out_nchw = op.ext_out != X_NONE ? (float*)ext[op.ext_out] : nullptr;
+          if (!Wp.feat) { *err = "missing feat_key"; return false; }
+          if (Wp.out_nchw == Wp.feat) { *err = "feat_out must not alias feat_key"; return false; }
         }
-        Wp.feat = (const float*)ext[op.ext_in0];
-        Wp.out_nchw = op.ext_out != X_NONE ? (float*)ext[op.ext_out] : nullptr;
-        if (!Wp.feat) { *err = "missing feat_key"; return false; }
-        if (Wp.out_nchw == Wp.feat) { *err = "feat_out must not alias feat_key"; return false; }
-        if (!Wp.out_nchw) Wp.out_nchw = warp_scratch_;          // caller does not keep `warping_feat_output`
+        // one pass for both copies when the fused kernel takes this shape; the conversion op that follows is then skipped
+        const bool with_split = op.fuse_split && warp_fused_supported(Wp);
+        if (with_split) {
+          skip_split = &op + 1;
+        } else {
+          Wp.out_hi = Wp.out_lo = nullptr;
+          Wp.bias = nullptr;
+          if (!Wp.out_nchw) Wp.out_nchw = warp_scratch_;        // caller does not keep `warping_feat_output`
+        }
         ce = launch_warp(Wp, stream);
         ++launches;
         break;
       }
-      case OP_UPFLOW:
-        ce = launch_upflow(op.upflow, stream);
-        ++launches;
+      case OP_UPFLOW: {
+        const Tensor& tf = tensors_[op.in];
+        const Tensor& to = tensors_[op.out];
+        for (int b = 0; b < tf.nb && ce == cudaSuccess; ++b) {
+          UpflowParams U = op.upflow;
+          U.flow += (size_t)b * frame_elems(tf);
+          U.out_hi += (size_t)b * frame_elems(to); U.out_lo += (size_t)b * frame_elems(to);
+          ce = launch_upflow(U, stream);
+          ++launches;
+        }
         break;
+      }
       case OP_FUSE:
         if (op.skip) break;                                  // evaluated inside the tail kernel that follows
         ce = launch_fuse_lowres(op.fuse, stream);
@@ -1106,11 +1218,12 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
         break;
       }
       case OP_TO_SPLIT: {
+        if (&op == skip_split) break;                        // written by the fused warp kernel
         const Tensor& to = tensors_[op.out];
-        const float* src = op.src_f32 >= 0 ? bufs_[tensors_[op.src_f32].buf].f : (const float*)ext[op.ext_in0];
+        const float* src = op.src_f32 >= 0 ? f_ptr(tensors_[op.src_f32]) : (const float*)ext[op.ext_in0];
         if (!src && op.src_warp) src = warp_scratch_;
         if (!src) { *err = "missing input tensor"; return false; }
-        ce = launch_nchw_to_split(src, to.C, to.H, to.W, bufs_[to.buf].hi + to.coff, bufs_[to.buf].lo + to.coff, to.ld,
+        ce = launch_nchw_to_split(src, to.C, to.H, to.W, hi_ptr(to), lo_ptr(to), to.ld,
                                   stream, op.split_bias_dev, op.split_act);
         ++launches;
         break;
@@ -1119,7 +1232,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
         const Tensor& to = tensors_[op.out];
         const void* src = ext[op.ext_in0];
         if (!src) { *err = "missing input tensor"; return false; }
-        ce = cudaMemcpyAsync(bufs_[to.buf].f, src, (size_t)to.C * to.H * to.W * sizeof(float), cudaMemcpyDeviceToDevice,
+        ce = cudaMemcpyAsync(f_ptr(to), src, (size_t)to.C * to.H * to.W * sizeof(float), cudaMemcpyDeviceToDevice,
                              stream);
         break;
       }
@@ -1127,7 +1240,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
         const Tensor& ti = tensors_[op.in];
         float* dst = (float*)ext[op.ext_out];
         if (dst) {
-          ce = launch_split_to_nchw(bufs_[ti.buf].hi + ti.coff, bufs_[ti.buf].lo + ti.coff, ti.ld, ti.C, ti.H, ti.W, dst,
+          ce = launch_split_to_nchw(hi_ptr(ti), lo_ptr(ti), ti.ld, ti.C, ti.H, ti.W, dst,
                                     stream);
           ++launches;
         }
@@ -1149,7 +1262,7 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
       cudaStreamSynchronize(stream);
       const Tensor& to = tensors_[op.out];
       std::vector<__half> hbuf((size_t)to.H * to.W * to.ld);
-      cudaMemcpy(hbuf.data(), bufs_[to.buf].hi, hbuf.size() * sizeof(__half), cudaMemcpyDeviceToHost);
+      cudaMemcpy(hbuf.data(), hi_ptr(to) - to.coff, hbuf.size() * sizeof(__half), cudaMemcpyDeviceToHost);
       double sum = 0.0, asum = 0.0;
       for (size_t px = 0; px < (size_t)to.H * to.W; ++px)
         for (int c = 0; c < to.C; ++c) {

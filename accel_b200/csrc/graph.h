@@ -26,6 +26,8 @@ struct Tensor {
   int buf = -1;      // buffer index
   int coff = 0;      // channel offset inside the buffer (zero-copy concat views)
   bool f32 = false;  // fp32 planar (C,H,W) instead of split NHWC
+  int nb = 1;        // frames stacked densely in the buffer ([nb][H][W][ld] / [nb][C][H][W]): batched plans
+  int foff = 0;      // first frame of this view inside the buffer
 };
 
 struct Buffer {
@@ -53,6 +55,7 @@ struct EpiSpec {
   int act2 = ACT_RELU;
   int out2 = -1;
   int out_f32 = -1;          // also/only write fp32 planar tensor
+  int f32_frames = 0;        // batched plans: only the first f32_frames frames get the fp32 copy (0 = all)
   int ext_out = X_NONE;      // also write an external fp32 NCHW output when the caller passed one
   int ext_raw = X_NONE;      // external fp32 NCHW copy of the LINEAR part (acc * scale: no bias, no activation)
   bool no_split_out = false;
@@ -82,6 +85,7 @@ struct Op {
   int src_warp = 0;          // OP_TO_SPLIT: read the warp op's fp32 output (caller's feat_out or the scratch)
   int src_f32 = -1;          // OP_WARP / OP_TO_SPLIT: internal fp32 planar source tensor (instead of an external pointer)
   int dst_f32 = -1;          // OP_WARP: internal fp32 planar destination tensor (whole-interval plan: the chained features)
+  bool fuse_split = false;   // OP_WARP: the OP_TO_SPLIT that follows is done by the fused warp kernel when the shape allows
   int sm_budget = 0;         // > 0: plan this op's persistent kernels for that many SMs (a chain of the whole-interval plan)
   std::string split_bias;    // OP_TO_SPLIT: per-channel bias added + `split_act` applied during the conversion
   int split_act = 0;
@@ -97,6 +101,9 @@ struct Op {
   FuseParams fuse{};
   TailParams tail{};
   TcPlan* tc = nullptr;
+  std::vector<ConvParams> frame_convs;   // a batched tensor run frame by frame (layers the batched kernel cannot take)
+  std::vector<TcPlan*> frame_tc;
+  int frame = 0;             // OP_STEM of a batched plan: which frame of the output tensor this launch writes
   StemTcPlan* stem_tc = nullptr;
   int partial_buf = -1;
   double flops = 0.0;
@@ -121,13 +128,14 @@ class Graph {
   ~Graph();
 
   // ---- building ----
-  int new_tensor(int C, int H, int W, bool f32 = false);
+  int new_tensor(int C, int H, int W, bool f32 = false, int nb = 1);
   int new_view(int base, int coff, int C);
+  int frame_view(int base, int first_frame, int nb);     // frames [first_frame, first_frame + nb) of a batched tensor
   int add_param(const std::string& name, std::vector<int64_t> shape);
   std::vector<Op>& seq(const std::string& which) { return seqs_[which]; }
 
   int stem(std::vector<Op>& s, const std::string& stage, int ext0, int ext1, int Hs, int Ws, bool pool,
-           float in_mul, const std::string& bn_in, const std::string& wname, int cin, EpiSpec e);
+           float in_mul, const std::string& bn_in, const std::string& wname, int cin, EpiSpec e, int out = -1, int frame = 0);
   int conv(std::vector<Op>& s, const std::string& stage, int in, const std::string& wname, int cout, int k, int stride,
            int pad, int dil, EpiSpec e, int out = -1);
   // fold_1x1: name of a 1x1 convolution (weight (cout, mid, 1, 1)) that follows the transposed conv (weight
@@ -166,6 +174,10 @@ class Graph {
   const std::vector<std::pair<std::string, float>>& stage_times();
   std::vector<OpTime> op_times();   // per launch group of the last profiled run
   const Tensor& tensor(int id) const { return tensors_[id]; }
+  size_t frame_elems(const Tensor& t) const { return t.f32 ? (size_t)t.ld * t.H * t.W : (size_t)t.H * t.W * t.ld; }
+  __half* hi_ptr(const Tensor& t) const { return bufs_[t.buf].hi + (size_t)t.foff * frame_elems(t) + t.coff; }
+  __half* lo_ptr(const Tensor& t) const { return bufs_[t.buf].lo + (size_t)t.foff * frame_elems(t) + t.coff; }
+  float* f_ptr(const Tensor& t) const { return bufs_[t.buf].f + (size_t)t.foff * frame_elems(t); }
   int flags() const { return flags_; }
   int num_sms() const { return num_sms_; }
   int num_sms_hint() const;            // SM count of the handle's device when one is visible (before finalize), else 148

@@ -16,6 +16,7 @@ cudaError_t launch_conv_narrow(const ConvParams& P, cudaStream_t stream);
 // tcgen05 / TMEM / TMA implicit-GEMM (conv_tc.cu)
 struct TcPlan;   // opaque: tensor maps + tiling chosen at plan time
 bool tc_supported(const ConvParams& P);
+bool tc_batchable(const ConvParams& P);   // P.nb frames in one launch (frames stacked along H)?
 TcPlan* tc_plan_create(const ConvParams& P, int num_sms, char* err, int errlen);
 void tc_plan_destroy(TcPlan* plan);
 size_t tc_plan_partial_bytes(const TcPlan* plan);
@@ -89,8 +90,15 @@ struct WarpParams {
   __half* out_hi;            // split NHWC copy feeding the task head, or nullptr
   __half* out_lo;
   int out_ld;
+  const float* bias;         // split copy only: + bias[c], then `act` (commuted L head: relu(warp(W*F) + fc6_bias)); or nullptr
+  int act;
 };
+// Writes the fp32 NCHW warped feature (when out_nchw is set) and the split NHWC copy (when out_hi is set).  Shapes the
+// fused kernel supports do both in ONE pass over the source (warp_kernel_fused, warp_staged.cu); others run the staged /
+// gather kernel and, for the split copy, nchw_to_split_kernel over its output (out_nchw is then required).
 cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream);
+bool warp_fused_supported(const WarpParams& P);
+cudaError_t launch_warp_fused(const WarpParams& P, cudaStream_t stream);
 // shared-memory staged variant (warp_staged.cu); cudaErrorNotSupported = shape unsuitable, use the gather kernel
 cudaError_t launch_warp_staged(const WarpParams& P, cudaStream_t stream);
 

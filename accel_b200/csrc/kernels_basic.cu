@@ -668,14 +668,20 @@ static bool env_gather_only() {
 }
 
 cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
-  // The warped feature always lands as fp32 NCHW (`warping_feat_output`, or the handle's scratch when the
-  // caller does not want it); the split NHWC copy the task head consumes is a second, L2-fed pass.
+  // One pass for both consumers where the fused kernel fits (warp_staged.cu: fp32 NCHW `warping_feat_output` and / or
+  // the split NHWC copy the task head loads); otherwise the warped feature lands as fp32 NCHW first and the split
+  // copy is a second, L2-fed pass.
+  if (!env_gather_only() && warp_fused_supported(P)) {
+    cudaError_t e = launch_warp_fused(P, stream);
+    if (e != cudaErrorNotSupported) return e;
+    cudaGetLastError();
+  }
   if (!P.out_nchw) return cudaErrorInvalidValue;
   const int npix = P.H * P.W;
   cudaError_t e = env_gather_only() ? cudaErrorNotSupported : launch_warp_staged(P, stream);
   if (e == cudaSuccess) {
     if (!P.out_hi) return e;
-    return launch_nchw_to_split(P.out_nchw, P.C, P.H, P.W, P.out_hi, P.out_lo, P.out_ld, stream);
+    return launch_nchw_to_split(P.out_nchw, P.C, P.H, P.W, P.out_hi, P.out_lo, P.out_ld, stream, P.bias, P.act);
   }
   if (e != cudaErrorNotSupported) return e;
   cudaGetLastError();
@@ -683,7 +689,7 @@ cudaError_t launch_warp(const WarpParams& P, cudaStream_t stream) {
   else if (npix == 32 * 64) e = launch_warp_t<32 * 64>(P, stream);       // 512 x 1024
   else e = launch_warp_t<0>(P, stream);
   if (e != cudaSuccess || !P.out_hi) return e;
-  return launch_nchw_to_split(P.out_nchw, P.C, P.H, P.W, P.out_hi, P.out_lo, P.out_ld, stream);
+  return launch_nchw_to_split(P.out_nchw, P.C, P.H, P.W, P.out_hi, P.out_lo, P.out_ld, stream, P.bias, P.act);
 }
 
 cudaError_t launch_nchw_to_split(const float* src, int C, int H, int W, __half* hi, __half* lo, int ld,

@@ -36,16 +36,20 @@ EpiSpec bias_epi(const std::string& conv, int act) {
 // ---- FlowNet-S -----------------------------------------------------------------------------------
 // ext_cur / ext_ref: external slots of the frame pair; inner_branches = false: the refinement levels stay one chain
 // (whole-interval plan: the chain itself is a branch next to the other frames' chains)
+// nb > 1: the pairs (ext_cur + b, ext_ref + b), b < nb, go through the net as ONE batch (one stem launch per pair, every
+// other layer one launch over all frames where the batched kernel takes it)
 int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out, int ext_cur = X_DATA, int ext_ref = X_DATA_KEY,
-            bool inner_branches = true) {
+            bool inner_branches = true, int nb = 1) {
   const std::string st = "flownet";
-  int r1 = g.stem(s, st, ext_cur, ext_ref, H, W, true, 1.0f / 255.0f, "", "flow_conv1", 6,
-                  bias_epi("flow_conv1", ACT_LEAKY));
+  int r1 = nb > 1 ? g.new_tensor(64, H / 4, W / 4, false, nb) : -1;
+  for (int b = 0; b < nb; ++b)
+    r1 = g.stem(s, st, ext_cur + b, ext_ref + b, H, W, true, 1.0f / 255.0f, "", "flow_conv1", 6,
+                bias_epi("flow_conv1", ACT_LEAKY), r1, b);
   const Tensor t1 = g.tensor(r1);                                   // (64, H/4, W/4)
-  const int c5 = g.new_tensor(128 + 64 + 2, t1.H / 2, t1.W / 2);     // Concat5
-  const int c4 = g.new_tensor(256 + 128 + 2, t1.H / 4, t1.W / 4);    // Concat4
-  const int c3 = g.new_tensor(512 + 256 + 2, t1.H / 8, t1.W / 8);    // Concat3
-  const int c2 = g.new_tensor(512 + 512 + 2, t1.H / 16, t1.W / 16);  // Concat2
+  const int c5 = g.new_tensor(128 + 64 + 2, t1.H / 2, t1.W / 2, false, nb);     // Concat5
+  const int c4 = g.new_tensor(256 + 128 + 2, t1.H / 4, t1.W / 4, false, nb);    // Concat4
+  const int c3 = g.new_tensor(512 + 256 + 2, t1.H / 8, t1.W / 8, false, nb);    // Concat3
+  const int c2 = g.new_tensor(512 + 512 + 2, t1.H / 16, t1.W / 16, false, nb);  // Concat2
   int r2 = g.conv(s, st, r1, "conv2", 128, 5, 2, 2, 1, bias_epi("conv2", ACT_LEAKY), g.new_view(c5, 0, 128));
   int r3 = g.conv(s, st, r2, "conv3", 256, 5, 2, 2, 1, bias_epi("conv3", ACT_LEAKY));
   int r4 = g.conv(s, st, r3, "conv3_1", 256, 3, 1, 1, 1, bias_epi("conv3_1", ACT_LEAKY), g.new_view(c4, 0, 256));
@@ -60,7 +64,7 @@ int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out, int ext_cur = X_DA
   auto refine = [&](int feat, int cat, int skip_c, int deconv_c, const char* flow_name, const char* deconv_name,
                     const char* up_name) {
     const Tensor tf = g.tensor(feat);
-    const int f = g.new_tensor(2, tf.H, tf.W, true);
+    const int f = g.new_tensor(2, tf.H, tf.W, true, nb);
     EpiSpec fe = bias_epi(flow_name, ACT_NONE);
     fe.out_f32 = f;
     fe.no_split_out = true;
@@ -99,7 +103,7 @@ int flownet(Graph& g, Seq& s, int H, int W, int ext_flow_out, int ext_cur = X_DA
   if (ext_flow_out != X_NONE) {
     fe.ext_out = ext_flow_out;
   } else {
-    flow = g.new_tensor(2, tp.H, tp.W, true);
+    flow = g.new_tensor(2, tp.H, tp.W, true, nb);
     fe.out_f32 = flow;
   }
   g.conv(s, st, p5, "Convolution5", 2, 3, 1, 1, 1, fe);
@@ -112,10 +116,13 @@ struct DeformCfg {
 };
 
 // ext_data: external slot of the frame; final_f32 >= 0: the last layer also writes that internal fp32 planar tensor
+// nb > 1: frames ext_data .. ext_data + nb - 1 as one batch; final_f32_frames: how many leading frames get the fp32 copy
 int bottleneck_net(Graph& g, Seq& s, const std::string& st, int H, int W, const std::string& prefix,
                    const std::vector<std::vector<std::string>>& stage_units, DeformCfg d, int ext_feat_out,
-                   int final_out_view, int ext_data = X_DATA, int final_f32 = -1) {
-  int x = g.stem(s, st, ext_data, X_NONE, H, W, false, 1.f, "", prefix + "conv1", 3, bn_epi(prefix + "bn_conv1", ACT_RELU));
+                   int final_out_view, int ext_data = X_DATA, int final_f32 = -1, int nb = 1, int final_f32_frames = 0) {
+  int x = nb > 1 ? g.new_tensor(64, H / 2, W / 2, false, nb) : -1;
+  for (int b = 0; b < nb; ++b)
+    x = g.stem(s, st, ext_data + b, X_NONE, H, W, false, 1.f, "", prefix + "conv1", 3, bn_epi(prefix + "bn_conv1", ACT_RELU), x, b);
   x = g.pool(s, st, x, 3, 2, 0, true, true);                        // pool1: 3x3/s2, pooling_convention='full'
   const int mids[4] = {64, 128, 256, 512};
   for (int si = 0; si < 4; ++si) {
@@ -132,7 +139,7 @@ int bottleneck_net(Graph& g, Seq& s, const std::string& st, int H, int W, const 
       int m;
       if (stage == 5) {
         const Tensor ta = g.tensor(a);
-        const int off = g.new_tensor(d.off_ch, ta.H, ta.W, true);
+        const int off = g.new_tensor(d.off_ch, ta.H, ta.W, true, nb);
         EpiSpec oe = bias_epi(r + "_branch2b_offset", ACT_NONE);
         oe.out_f32 = off;
         oe.no_split_out = true;
@@ -144,7 +151,7 @@ int bottleneck_net(Graph& g, Seq& s, const std::string& st, int H, int W, const 
       EpiSpec ce = bn_epi(b + "_branch2c", ACT_RELU);
       ce.res = sc;
       if (last) ce.ext_out = ext_feat_out;
-      if (last && final_f32 >= 0) ce.out_f32 = final_f32;
+      if (last && final_f32 >= 0) { ce.out_f32 = final_f32; ce.f32_frames = final_f32_frames; }
       x = g.conv(s, st, m, r + "_branch2c", 4 * mid, 1, 1, 0, 1, ce, last ? final_out_view : -1);
     }
   }
@@ -163,10 +170,12 @@ std::vector<std::vector<std::string>> units_50() {
 
 // ---- pre-activation basic-block trunk + deformable conv5 (Accel-18 / Accel-34 R branch) ----------------
 int preact_branch(Graph& g, Seq& s, const std::string& st, int H, int W, const std::string& pre,
-                  const std::vector<int>& units, const std::string& letters, bool fold_fc6, int ext_data = X_DATA) {
+                  const std::vector<int>& units, const std::string& letters, bool fold_fc6, int ext_data = X_DATA, int nb = 1) {
   const float eps = 2e-5f;
-  int x = g.stem(s, st, ext_data, X_NONE, H, W, false, 1.f, pre + "bn_data", pre + "conv0", 3,
-                 bn_epi(pre + "bn0", ACT_RELU, eps));
+  int x = nb > 1 ? g.new_tensor(64, H / 2, W / 2, false, nb) : -1;
+  for (int b = 0; b < nb; ++b)
+    x = g.stem(s, st, ext_data + b, X_NONE, H, W, false, 1.f, pre + "bn_data", pre + "conv0", 3,
+               bn_epi(pre + "bn0", ACT_RELU, eps), x, b);
   // max pool, then stage1_unit1's bn1 + relu on the pooled map (unit 1 never reads the raw input:
   // its shortcut conv also takes act1, :80-81)
   int act = g.pool(s, st, x, 3, 2, 1, true, false, bn_epi(pre + "stage1_unit1_bn1", ACT_RELU, eps));
@@ -199,7 +208,7 @@ int preact_branch(Graph& g, Seq& s, const std::string& st, int H, int W, const s
         e.bn2 = next + "_bn1";
         e.eps2 = eps;
         e.act2 = ACT_RELU;
-        e.out2 = g.new_tensor(c, t1.H, t1.W);
+        e.out2 = g.new_tensor(c, t1.H, t1.W, false, nb);
       }
       e.no_split_out = !next_needs_raw;
       raw = g.conv(s, st, c1, name + "_conv2", c, 3, 1, 1, 1, e);
@@ -216,7 +225,7 @@ int preact_branch(Graph& g, Seq& s, const std::string& st, int H, int W, const s
     int a = g.conv(s, st, xx, pre + "res5" + L + "_branch2a", 512, 3, first ? 2 : 1, 1, 1,
                    bn_epi(pre + "bn5" + L + "_branch2a", ACT_RELU));
     const Tensor ta = g.tensor(a);
-    const int off = g.new_tensor(72, ta.H, ta.W, true);
+    const int off = g.new_tensor(72, ta.H, ta.W, true, nb);
     EpiSpec oe = bias_epi(pre + "res5" + L + "_branch2b_offset", ACT_NONE);
     oe.out_f32 = off;
     oe.no_split_out = true;
@@ -245,7 +254,7 @@ int head(Graph& g, Seq& s, const std::string& st, int feat, const std::string& f
     x = g.conv(s, st, feat, fc6, 1024, 1, 1, 0, 1, fe);
   }
   const Tensor tx = g.tensor(x);
-  const int sc = g.new_tensor(K, tx.H, tx.W, true);
+  const int sc = g.new_tensor(K, tx.H, tx.W, true, tx.nb);
   EpiSpec e = bias_epi(score, ACT_NONE);
   e.out_f32 = sc;
   e.no_split_out = true;
@@ -256,14 +265,14 @@ int head(Graph& g, Seq& s, const std::string& st, int feat, const std::string& f
 
 // The correction ("R") network of Accel-18/34/50 with its own DeepLab head: returns the low-res fp32 score map
 // (accel_18.py:199-221, accel_50.py:195-216).  On its own it is the plain DeepLab-<v> segmentation net (BASELINE config 1).
-int rbranch_scores(Graph& g, Seq& s, int version, int H, int W, int K, bool fold_fc6, int ext_data = X_DATA) {
+int rbranch_scores(Graph& g, Seq& s, int version, int H, int W, int K, bool fold_fc6, int ext_data = X_DATA, int nb = 1) {
   if (version == 50) {
-    int f = bottleneck_net(g, s, "rbranch", H, W, "50_", units_50(), DeformCfg{72, 2, 2, 4}, X_NONE, -1, ext_data);
+    int f = bottleneck_net(g, s, "rbranch", H, W, "50_", units_50(), DeformCfg{72, 2, 2, 4}, X_NONE, -1, ext_data, -1, nb);
     return head(g, s, "rhead", f, "curr_fc6", "curr_score", "curr_upsampling", K);
   }
   const std::string pre = std::to_string(version) + "_";
   int f = preact_branch(g, s, "rbranch", H, W, pre, version == 18 ? std::vector<int>{2, 2, 2} : std::vector<int>{3, 4, 6},
-                        version == 18 ? "ab" : "abc", fold_fc6, ext_data);
+                        version == 18 ? "ab" : "abc", fold_fc6, ext_data, nb);
   return head(g, s, "rhead", f, pre + "fc6", pre + "score", pre + "upsampling", K, X_NONE, fold_fc6);
 }
 
@@ -294,9 +303,50 @@ bool build_interval(Graph& g, int version, int H, int W, int K, int interval, st
   std::vector<Chain> chains;
   auto close_chain = [&](size_t b) { chains.push_back({b, s.size()}); };
 
-  // chain 0: key frame -- R101-DCN, its head and its tail (get_key_test_symbol)
+  // Frames that go through the same network with the same weights share ONE launch per layer (ACCEL_IVL_BATCH=0: one chain
+  // per frame instead): R101 over all I frames in Accel-101 (the key net and the correction net are the same network,
+  // accel_101.py:161), FlowNet over the I-1 frame pairs, the correction network over the I-1 cur frames.
+  const char* be = getenv("ACCEL_IVL_BATCH");
+  const bool batched = !(be && be[0] == '0') && !(g.flags() & 1);
   std::vector<int> feat(I);                                  // fp32 planar features: F_0 = res5c_relu, F_t = warp_t(F_{t-1})
   for (int t = 0; t < I; ++t) feat[t] = g.new_tensor(2048, h, w, true);
+  std::vector<int> flow(I, -1), cat(I, -1), sr(I, -1), warped(I, -1);
+  int cat_all = -1, flow_all = -1, sr_all = -1, warped_all = -1;
+  if (batched) {
+    {
+      const size_t b = s.size();
+      int f0;
+      if (version == 101) {
+        cat_all = g.new_tensor(4096, h, w, false, I);          // frame t: [warp_t(F_{t-1}) | R101(frame t)]
+        const int upper = g.new_view(cat_all, 2048, 2048);
+        bottleneck_net(g, s, "backbone", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_NONE, upper, X_FRAME0, feat[0], I, 1);
+        f0 = g.frame_view(upper, 0, 1);
+        for (int t = 1; t < I; ++t) cat[t] = g.frame_view(cat_all, t, 1);
+      } else {
+        f0 = bottleneck_net(g, s, "backbone", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_NONE, -1, X_FRAME0, feat[0]);
+      }
+      int sc = head(g, s, "head", f0, "fc6", "score", "upsampling", K);
+      g.tail(s, sc, "", X_LABEL0, X_SCORE0);
+      close_chain(b);
+    }
+    {
+      const size_t b = s.size();
+      flow_all = flownet(g, s, H, W, X_NONE, X_FRAME0 + 1, X_FRAME0, false, I - 1);
+      for (int t = 1; t < I; ++t) flow[t] = g.frame_view(flow_all, t - 1, 1);
+      close_chain(b);
+    }
+    if (version != 0 && version != 101) {
+      const size_t b = s.size();
+      sr_all = rbranch_scores(g, s, version, H, W, K, fold_fc6, X_FRAME0 + 1, I - 1);
+      for (int t = 1; t < I; ++t) sr[t] = g.frame_view(sr_all, t - 1, 1);
+      close_chain(b);
+    }
+    if (version != 101) {
+      warped_all = g.new_tensor(2048, h, w, false, I - 1);
+      for (int t = 1; t < I; ++t) warped[t] = g.frame_view(warped_all, t - 1, 1);
+    }
+  } else {
+  // chain 0: key frame -- R101-DCN, its head and its tail (get_key_test_symbol)
   {
     const size_t b = s.size();
     int f0 = bottleneck_net(g, s, "backbone", H, W, "", units_101(), DeformCfg{18, 1, 1, 1}, X_NONE, -1, X_FRAME0, feat[0]);
@@ -305,14 +355,12 @@ bool build_interval(Graph& g, int version, int H, int W, int K, int interval, st
     close_chain(b);
   }
   // FlowNet of every frame pair
-  std::vector<int> flow(I, -1);
   for (int t = 1; t < I; ++t) {
     const size_t b = s.size();
     flow[t] = flownet(g, s, H, W, X_NONE, X_FRAME0 + t, X_FRAME0 + t - 1, false);
     close_chain(b);
   }
   // correction network of every cur frame
-  std::vector<int> cat(I, -1), sr(I, -1);
   for (int t = 1; t < I && version != 0; ++t) {
     const size_t b = s.size();
     if (version == 101) {
@@ -323,6 +371,7 @@ bool build_interval(Graph& g, int version, int H, int W, int K, int interval, st
       sr[t] = rbranch_scores(g, s, version, H, W, K, fold_fc6, X_FRAME0 + t);
     }
     close_chain(b);
+  }
   }
   // SM shares proportional to the chains' flops
   {
@@ -362,6 +411,28 @@ bool build_interval(Graph& g, int version, int H, int W, int K, int interval, st
       }
   }
   // sequential part: the chained warps and what consumes them
+  if (batched) {
+    for (int t = 1; t < I; ++t)
+      g.warp_internal(s, feat[t - 1], flow[t], feat[t], version == 101 ? g.new_view(cat[t], 0, 2048) : warped[t]);
+    int sl_all;
+    if (version == 101) {
+      int fused = g.conv(s, "fusion", g.frame_view(cat_all, 1, I - 1), "corr", 2048, 1, 1, 0, 1, bias_epi("corr", ACT_NONE));
+      sl_all = head(g, s, "head", fused, "fc6", "score", "upsampling", K);
+    } else {
+      sl_all = head(g, s, "head", warped_all, "fc6", "score", "upsampling", K);
+    }
+    for (int t = 1; t < I; ++t) {
+      const int sl = g.frame_view(sl_all, t - 1, 1);
+      if (version == 0 || version == 101) {
+        g.tail(s, sl, "", X_LABEL0 + t, X_SCORE0 + t);
+      } else {
+        const int fused = g.new_tensor(K, h, w, true);
+        g.fuse(s, sl, sr[t], "corr", fused);
+        g.tail(s, fused, "corr_bias", X_LABEL0 + t, X_SCORE0 + t);
+      }
+    }
+    return true;
+  }
   for (int t = 1; t < I; ++t) {
     if (version == 101) {
       g.warp_internal(s, feat[t - 1], flow[t], feat[t], g.new_view(cat[t], 0, 2048));
@@ -369,9 +440,9 @@ bool build_interval(Graph& g, int version, int H, int W, int K, int interval, st
       int sc = head(g, s, "head", fused, "fc6", "score", "upsampling", K);
       g.tail(s, sc, "", X_LABEL0 + t, X_SCORE0 + t);
     } else {
-      const int warped = g.new_tensor(2048, h, w);
-      g.warp_internal(s, feat[t - 1], flow[t], feat[t], warped);
-      const int sl = head(g, s, "head", warped, "fc6", "score", "upsampling", K);
+      const int wt = g.new_tensor(2048, h, w);
+      g.warp_internal(s, feat[t - 1], flow[t], feat[t], wt);
+      const int sl = head(g, s, "head", wt, "fc6", "score", "upsampling", K);
       if (version == 0) {
         g.tail(s, sl, "", X_LABEL0 + t, X_SCORE0 + t);
       } else {

@@ -58,6 +58,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -208,9 +215,11 @@ __device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int
       b = e.shift ? __ldg(reinterpret_cast<const float4*>(e.shift + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (e.raw_nchw) {                       // the linear part alone (key frame `fc6`: W*F for the commuted L head)
-      const size_t plane = (size_t)e.OHf * e.OWf;
-      float* rp = e.raw_nchw + (size_t)(c0 + 4 * q) * plane + pix;
-      rp[0] = v[4 * q + 0] * s.x; rp[plane] = v[4 * q + 1] * s.y; rp[2 * plane] = v[4 * q + 2] * s.z; rp[3 * plane] = v[4 * q + 3] * s.w;
+      size_t base, plane;
+      if (nchw_base(e, pix, base, plane)) {
+        float* rp = e.raw_nchw + base + (size_t)(c0 + 4 * q) * plane;
+        rp[0] = v[4 * q + 0] * s.x; rp[plane] = v[4 * q + 1] * s.y; rp[2 * plane] = v[4 * q + 2] * s.z; rp[3 * plane] = v[4 * q + 3] * s.w;
+      }
     }
     v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, b.x);
     v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, b.y);
@@ -230,9 +239,11 @@ __device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int
   for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
   if (e.out_hi && store_main) store_split32(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
   if (e.out_nchw) {
-    const size_t plane = (size_t)e.OHf * e.OWf;
+    size_t base, plane;
+    if (nchw_base(e, pix, base, plane)) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) e.out_nchw[(size_t)(c0 + i) * plane + pix] = v[i];
+      for (int i = 0; i < 32; ++i) e.out_nchw[base + (size_t)(c0 + i) * plane] = v[i];
+    }
   }
   if (e.out2_hi) {
     float v2[32];

@@ -31,7 +31,23 @@ LAYERS = {
     "res5_off": (512, 18, 64, 128, 3, 1, 1, 1, False),
     "flow_conv3_1": (256, 256, 128, 256, 3, 1, 1, 1, False),
     "flow_conv3": (128, 256, 128, 256, 5, 2, 2, 1, False),
+    # the same layers over 5 frames stacked along H: what batching an interval's frames through one launch would give
+    "res2_2a_x5": (256, 64, 1280, 512, 1, 1, 0, 1, False),
+    "res2_2a": (256, 64, 256, 512, 1, 1, 0, 1, False),
+    "res3_2a_x5": (512, 128, 640, 256, 1, 1, 0, 1, False),
+    "res3_2a": (512, 128, 128, 256, 1, 1, 0, 1, False),
+    "res3_2b_x5": (128, 128, 640, 256, 3, 1, 1, 1, False),
+    "res4_2a_x5": (1024, 256, 320, 128, 1, 1, 0, 1, False),
+    "res4_2b_x5": (256, 256, 320, 128, 3, 1, 1, 1, False),
+    "res4_2c_x5": (256, 1024, 320, 128, 1, 1, 0, 1, True),
+    "res5_2a_x5": (2048, 512, 320, 128, 1, 1, 0, 1, False),
+    "res5_2c_x5": (512, 2048, 320, 128, 1, 1, 0, 1, True),
+    "fc6_x5": (2048, 1024, 320, 128, 1, 1, 0, 1, False),
     "flow_conv4_1": (512, 512, 32, 64, 3, 1, 1, 1, False),
+    "flow_conv4_1_x4": (512, 512, 128, 64, 3, 1, 1, 1, False),
+    "flow_conv5_1": (512, 512, 16, 32, 3, 1, 1, 1, False),
+    "flow_conv5_1_x4": (512, 512, 64, 32, 3, 1, 1, 1, False),
+    "flow_conv6_1_x4": (1024, 1024, 32, 16, 3, 1, 1, 1, False),
     "flow_conv6_1": (1024, 1024, 8, 16, 3, 1, 1, 1, False),
 }
 SWEEP = [
@@ -54,6 +70,8 @@ PAIR_SWEEP = [
     {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "256", "ACCEL_TC_SPLITS": "3"},
     {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "128", "ACCEL_TC_SPLITS": "2"},
 ]
+
+ONE = [{}]
 
 R02_SWEEP = [
     {"ACCEL_TC_ASLAB": "0"},
@@ -96,7 +114,7 @@ def main():
         ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
         wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
         r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
-        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP}.get(a.sweep, SWEEP):
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE}.get(a.sweep, SWEEP):
             for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR", "ACCEL_TC_ASLAB",
                        "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO"):
                 os.environ.pop(kk, None)
