@@ -402,7 +402,9 @@ bool build_interval(Graph& g, int version, int H, int W, int K, int interval, st
       if (worst == chains.size()) break;
       --share[worst]; --used;
     }
-    for (size_t c = 0; c < chains.size(); ++c)
+    const char* se = getenv("ACCEL_IVL_SERIAL");           // 1: the chains one after the other, each on all SMs
+    const bool serial = se && se[0] == '1';
+    for (size_t c = 0; c < chains.size() && !serial; ++c)
       for (size_t i = chains[c].begin; i < chains[c].end; ++i) {
         s[i].par_group = grp;
         s[i].par_branch = (int)c + 1;

@@ -86,13 +86,16 @@ def make_params(version, seed=0):
 
 
 def _smooth_noise(h, w, gen, octaves=5):
-    """Sum of bilinearly upsampled uniform noise at `octaves` scales -> (3,h,w) in [0,1]."""
-    img = torch.zeros(1, 3, h, w)
+    """Sum of bilinearly upsampled uniform noise at `octaves` scales -> (3,h,w) in [0,1].
+    Interpolated and summed in float64: the uint8 frames derived from it must not depend on how many threads (or which
+    vector ISA) the CPU interpolation kernel runs with -- in float32 a few pixels per frame flip at .5 boundaries
+    between a 1-thread torchrun rank and a 16-thread single process, and with them the per-stream label CRCs."""
+    img = torch.zeros(1, 3, h, w, dtype=torch.float64)
     amp_sum = 0.0
     for o in range(octaves):
         cells = 2 ** (o + 2)
         amp = 0.5 ** o
-        coarse = torch.rand(1, 3, max(2, cells * h // w) + 1, cells + 1, generator=gen)
+        coarse = torch.rand(1, 3, max(2, cells * h // w) + 1, cells + 1, generator=gen).double()
         img += amp * torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)
         amp_sum += amp
     return (img / amp_sum)[0]
