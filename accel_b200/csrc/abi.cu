@@ -223,6 +223,14 @@ extern "C" int accel_interval_forward(AccelHandle* h, const float* const* frames
   ACCEL_CATCH(h)
 }
 
+extern "C" int accel_debug_fetch(AccelHandle* h, const char* plan, const char* op_name, float* out, int64_t shape[4], void* stream) {
+  if (!h) return 1;
+  ACCEL_TRY
+  if (!plan || !op_name || !shape) { h->err = "null argument"; return 1; }
+  return h->graph->fetch_op_output(plan, op_name, out, shape, (cudaStream_t)stream, &h->err) ? 0 : 1;
+  ACCEL_CATCH(h)
+}
+
 extern "C" int accel_graph_cache_stats(const AccelHandle* h, uint64_t* hits, uint64_t* misses) {
   if (!h || !hits || !misses) return 1;
   unsigned long long a = 0, b = 0;

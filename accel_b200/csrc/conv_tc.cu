@@ -912,8 +912,15 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   int best_bn = 64, best_splits = 1;
   double best_cost = 1e30;
   const int split_opts[10] = {1, 2, 3, 4, 5, 6, 8, 9, 12, 16};
+  // Accuracy first: a 256-wide tile has no room in TMEM for the N-concatenated layout, so its three
+  // MMAs per K slice (hi*hi, hi*lo, lo*hi) all add into ONE accumulator and the small cross terms are truncated at the big
+  // sum's ulp; measured at 1024x2048 (tools/interval_parity.py) that alone put Accel-101's score error at 0.8-1.5e-3
+  // against 2.4-4.0e-4 with every long-K layer on N <= 128.  Layers that walk >= ACCEL_TC_WIDE_KMAX (16) K stages
+  // therefore never take BN = 256.
+  const int wide_kmax = env_int("ACCEL_TC_WIDE_KMAX", 16);
   for (int bn = 256; bn >= 64; bn >>= 1) {
     if (bn > C.Cout_pad && bn != 64) continue;
+    if (bn == 256 && P.kiters >= wide_kmax) continue;
     const int n_tiles = (C.Cout_pad + bn - 1) / bn;
     const int tiles = tiles_m * n_tiles;
     const double per_k = (12.0 * (4096.0 + 32.0 * bn) + 32768.0 + 256.0 * bn) / 88.0;
@@ -1015,7 +1022,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     // ACCEL_TC_CHAINS_MULTI=0: only where every CTA holds a single item (nothing to overlap an epilogue with anyway)
     const bool single_wave = (long long)tiles * splits <= (long long)num_sms;
     const bool want = mode == 2 || (mode < 0 && kps >= env_int("ACCEL_TC_CHAINS_MIN", 6) &&
-                                    (single_wave || kps >= env_int("ACCEL_TC_CHAINS_MULTI_MIN", 32) ||
+                                    (single_wave || kps >= env_int("ACCEL_TC_CHAINS_MULTI_MIN", 16) ||
                                      env_int("ACCEL_TC_CHAINS_MULTI", 0) != 0));
     P.kchains = (want && !P.pair && mode != 0 && mode != 1) ? 2 : 1;
   }

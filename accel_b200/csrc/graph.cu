@@ -1278,6 +1278,26 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
   return true;
 }
 
+bool Graph::fetch_op_output(const std::string& which, const std::string& op_name, float* dst, int64_t shape[4],
+                            cudaStream_t stream, std::string* err) {
+  auto it = seqs_.find(which);
+  if (it == seqs_.end()) { *err = "no such graph: " + which; return false; }
+  if (!finalized_) { *err = "not finalized"; return false; }
+  const Op* found = nullptr;
+  for (const Op& op : it->second)
+    if (op.name == op_name && op.out >= 0 && !tensors_[op.out].f32) found = &op;      // the last op of that name
+  if (!found) { *err = "no op '" + op_name + "' with a split output in plan '" + which + "'"; return false; }
+  const Tensor& t = tensors_[found->out];
+  shape[0] = t.nb; shape[1] = t.C; shape[2] = t.H; shape[3] = t.W;
+  if (!dst) return true;
+  for (int b = 0; b < t.nb; ++b) {
+    cudaError_t ce = launch_split_to_nchw(hi_ptr(t) + (size_t)b * frame_elems(t), lo_ptr(t) + (size_t)b * frame_elems(t), t.ld, t.C,
+                                          t.H, t.W, dst + (size_t)b * t.C * t.H * t.W, stream);
+    if (ce != cudaSuccess) { *err = std::string("split_to_nchw: ") + cudaGetErrorString(ce); return false; }
+  }
+  return true;
+}
+
 const std::vector<std::pair<std::string, float>>& Graph::stage_times() {
   times_.clear();
   if (event_stage_.empty()) return times_;

@@ -168,6 +168,10 @@ class Graph {
   bool finalized() const { return finalized_; }
   bool run(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err);
   bool run_eager(const std::string& which, void* const ext[X_COUNT], cudaStream_t stream, std::string* err);
+  // Debugging / per-layer parity aid: the split NHWC output of op `op_name` of plan `which` (as left by the last run) as
+  // fp32 NCHW into `dst` (device); shape receives (frames, C, H, W).
+  bool fetch_op_output(const std::string& which, const std::string& op_name, float* dst, int64_t shape[4], cudaStream_t stream,
+                       std::string* err);
   int last_launches() const { return last_launches_; }
   void cache_stats(unsigned long long* hits, unsigned long long* misses) const { *hits = cache_hits_; *misses = cache_misses_; }
   void set_profiling(bool on) { profiling_ = on; }

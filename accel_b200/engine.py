@@ -219,6 +219,19 @@ class Engine:
         if rc != 0:
             raise RuntimeError("accel_interval_forward failed: %s" % self._err())
 
+    def fetch_layer(self, plan, op_name):
+        """accel_debug_fetch: the internal output of layer `op_name` of `plan` after the last forward, as an fp32
+        (frames, C, H, W) CUDA tensor (per-layer parity tests, debugging)."""
+        shape = (C.c_int64 * 4)()
+        if self.lib.accel_debug_fetch(self._h, plan.encode(), op_name.encode(), None, shape, None) != 0:
+            raise RuntimeError(self._err())
+        out = torch.empty(tuple(int(x) for x in shape), device=self.torch_device)
+        with torch.cuda.device(self.torch_device):
+            rc = self.lib.accel_debug_fetch(self._h, plan.encode(), op_name.encode(), _ptr(out), shape, self._stream())
+        if rc != 0:
+            raise RuntimeError(self._err())
+        return out
+
     def graph_cache_stats(self):
         """(hits, misses) of the handle's CUDA-graph cache: a miss = one stream capture + instantiate."""
         a, b = C.c_uint64(), C.c_uint64()

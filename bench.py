@@ -156,7 +156,7 @@ def cpu_oracle_fps(a, steps, warmup, budget_s=None, frames=None, keep_outputs=Fa
     first key frame's and first cur frame's oracle outputs stay in detail["key_out"] / detail["cur_out"]."""
     import torch
     from accel_b200 import synthetic
-    from oracle import nets
+    from oracle import nets, ops
     torch.set_num_threads(os.cpu_count() or 1)
     p = synthetic.make_params(a.version)
     if frames is None:
@@ -170,6 +170,9 @@ def cpu_oracle_fps(a, steps, warmup, budget_s=None, frames=None, keep_outputs=Fa
         total = warmup + steps
         for i in range(total):
             idx = i % a.interval
+            # the kept frames also record where DCNv1's border rule makes the reference itself discontinuous
+            tracing = keep_outputs and ((idx == 0 and "key_out" not in detail) or (idx != 0 and "cur_out" not in detail))
+            ops.DCN_TRACE = [] if tracing else None
             t0 = time.perf_counter()
             if idx == 0 or feat is None:
                 out = nets.key_forward(p, frames[idx])
@@ -184,7 +187,8 @@ def cpu_oracle_fps(a, steps, warmup, budget_s=None, frames=None, keep_outputs=Fa
             score.argmax(dim=1)
             dt = time.perf_counter() - t0
             if keep_outputs and (kind + "_out") not in detail:
-                detail[kind + "_out"] = {"score": score, "feat": feat, "index": idx}
+                detail[kind + "_out"] = {"score": score, "feat": feat, "index": idx, "dcn_trace": ops.DCN_TRACE or []}
+            ops.DCN_TRACE = None
             if i >= warmup:
                 (t_key if kind == "key" else t_cur).append(dt)
                 t_all.append(dt)
@@ -540,7 +544,7 @@ def run_native(a):
         cpu_base = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
                     "sample": "%d frames of the same workload on the CPU oracle (%.2fs/key, %.2fs/cur), "
                               "~%ds budget" % (d["frames_timed"], d["key_s"], d["cur_s"], int(budget))}
-        parity = oracle_parity(eng, frames, d, torch, a.version)
+        parity = oracle_parity(eng, frames, d, torch, a.version, use_batched, I)
         del d, host_frames
 
     # ---- the other north-star workloads, same K steps and warm-up, one object each -------------------------------
@@ -705,44 +709,85 @@ def _xor(vals):
     return x
 
 
-def oracle_parity(eng, frames, d, torch, version):
+def oracle_parity(eng, frames, d, torch, version, batched=False, interval=5):
     """GPU outputs of the workload's first key frame and first cur frame (through the C ABI, score volume on) against
     the CPU oracle's outputs of the same frames kept by the cpu_baseline leg: the north-star's parity bar at the
-    benchmark's own size."""
+    benchmark's own size, in the issue order of `value` (the whole-interval plan when that is the headline) and, as
+    `frame_by_frame`, through accel_key_forward / accel_cur_forward."""
     from oracle import nets, ops  # noqa: F401  (checker only)
     dev = eng.torch_device
     H, W = eng.height, eng.width
     feat = [torch.empty(eng.feat_shape, device=dev) for _ in range(2)]
     score = torch.empty(1, eng.num_classes, H, W, device=dev)
     label = torch.empty(H, W, dtype=torch.uint8, device=dev)
-    out = {"size": "%dx%d" % (H, W), "score_tolerance": 1e-3}
 
-    def compare(tag, ref_score):
-        err = (score.cpu() - ref_score).abs().max().item()
+    def critical(*traces):
+        """Frame pixels in the footprint (12 px of the stride-16 grid) of a deformable-conv tap that lies within 2e-4 of the
+        image border in the ORACLE's run: DCNv1's `0 unless 0 <= p < H` rule is discontinuous there, the reference operator
+        itself moves by O(|x|) under rounding-noise changes of its offsets, so those pixels are
+        reported separately and not held to the tolerance."""
+        import torch.nn.functional as F
+        h, w = H // 16, W // 16
+        m = torch.zeros(1, 1, h, w)
+        for tr in traces:
+            for t in tr:
+                t = t.float().reshape(1, 1, t.shape[-2], t.shape[-1])
+                m = torch.maximum(m, t if t.shape[-2:] == (h, w) else F.interpolate(t, size=(h, w), mode="nearest"))
+        if m.sum() == 0:
+            return torch.zeros(H, W, dtype=torch.bool)
+        return F.interpolate(F.max_pool2d(m, 25, 1, 12), size=(H, W), mode="nearest")[0, 0] > 0
+
+    def compare(out, tag, ref_score, score, label, excl):
+        emap = (score.cpu() - ref_score).abs()[0].max(dim=0).values
+        keep = ~excl
+        err = emap[keep].max().item()
         ref_label = torch.from_numpy(ops.argmax_channel(ref_score)[0].astype("uint8"))
         top2 = ref_score.topk(2, dim=1).values
         margin = (top2[:, 0] - top2[:, 1])[0]
-        diff = label.cpu() != ref_label
+        diff = (label.cpu() != ref_label) & keep
         out[tag] = {"score_max_abs": err, "label_mismatch": int(diff.sum()), "pixels": H * W,
                     "label_mismatch_where_margin_gt_2x_measured_err": int((diff & (margin > 2 * err)).sum()),
-                    "undecided_px_margin_le_2x_measured_err": int((margin <= 2 * err).sum()),
-                    "undecided_px_margin_le_2e-3": int((margin <= 2e-3).sum())}
+                    "undecided_px_margin_le_2x_measured_err": int(((margin <= 2 * err) & keep).sum()),
+                    "undecided_px_margin_le_2e-3": int(((margin <= 2e-3) & keep).sum()),
+                    "dcn_border_critical_px_excluded": int(excl.sum()), "score_max_abs_incl_excluded": emap.max().item()}
 
+    def totals(out):
+        ks = [k for k in ("key", "cur") if k in out]
+        out["score_max_abs"] = max(out[k]["score_max_abs"] for k in ks)
+        out["label_mismatch"] = sum(out[k]["label_mismatch"] for k in ks)
+        out["undecided_px"] = sum(out[k]["undecided_px_margin_le_2x_measured_err"] for k in ks)
+        out["label_mismatch_decided"] = sum(out[k]["label_mismatch_where_margin_gt_2x_measured_err"] for k in ks)
+        out["dcn_border_critical_px_excluded"] = sum(out[k]["dcn_border_critical_px_excluded"] for k in ks)
+        return out
+
+    i = d["cur_out"]["index"] if "cur_out" in d else 0
+    ex_key = critical(d["key_out"]["dcn_trace"])
+    ex_cur = critical(d["key_out"]["dcn_trace"], d["cur_out"]["dcn_trace"]) if i else ex_key
+    fbf = {"size": "%dx%d" % (H, W), "score_tolerance": 1e-3, "issue_order": "frame by frame"}
     eng.key_forward(frames[0], feat[0], score, label)
-    compare("key", d["key_out"]["score"])
-    if "cur_out" in d:
-        i = d["cur_out"]["index"]
-        # chained schedule, as in the timed loop: frames 1..i on the GPU's own key feature
-        src = 0
+    compare(fbf, "key", d["key_out"]["score"], score, label, ex_key)
+    if i:
+        src = 0                                   # chained schedule, as in the timed loop: frames 1..i on the GPU's own key feature
         for t in range(1, i + 1):
             eng.cur_forward(frames[t], frames[t - 1], feat[src], feat[src ^ 1], score, label)
             src ^= 1
-        compare("cur", d["cur_out"]["score"])
-        out["cur"]["feat_max_abs"] = (feat[src].cpu() - d["cur_out"]["feat"]).abs().max().item()
-    out["score_max_abs"] = max(out[k]["score_max_abs"] for k in ("key", "cur") if k in out)
-    out["label_mismatch"] = sum(out[k]["label_mismatch"] for k in ("key", "cur") if k in out)
-    out["undecided_px"] = sum(out[k]["undecided_px_margin_le_2x_measured_err"] for k in ("key", "cur") if k in out)
-    out["label_mismatch_decided"] = sum(out[k]["label_mismatch_where_margin_gt_2x_measured_err"] for k in ("key", "cur") if k in out)
+        compare(fbf, "cur", d["cur_out"]["score"], score, label, ex_cur)
+        fbf["cur"]["feat_max_abs"] = (feat[src].cpu() - d["cur_out"]["feat"]).abs().max().item()
+    totals(fbf)
+    if not batched:
+        return fbf
+    out = {"size": "%dx%d" % (H, W), "score_tolerance": 1e-3, "issue_order": "whole-interval plan"}
+    labels = torch.empty(interval, H, W, dtype=torch.uint8, device=dev)
+    scores = [None] * interval
+    scores[0] = score
+    if i:
+        scores[i] = torch.empty_like(score)
+    eng.interval_forward(frames[:interval], labels, scores)
+    compare(out, "key", d["key_out"]["score"], scores[0], labels[0], ex_key)
+    if i:
+        compare(out, "cur", d["cur_out"]["score"], scores[i], labels[i], ex_cur)
+    totals(out)
+    out["frame_by_frame"] = fbf
     return out
 
 

@@ -118,6 +118,11 @@ int accel_plan_interval(AccelHandle* h, int interval);
 int accel_interval_forward(AccelHandle* h, const float* const* frames, float* const* score_out, uint8_t* const* label_out,
                            void* stream);
 
+/* Per-layer parity / debugging aid: the internal (split fp16 NHWC) output that layer `op_name` (the reference's layer
+ * name, e.g. "res4b7_branch2c", "conv3_1", "fc6") of plan `plan` ("key", "cur", "flow", "interval", ...) holds after the
+ * last forward, converted to fp32 NCHW into `out` (DEVICE memory; NULL = only report the shape (frames, C, H, W)). */
+int accel_debug_fetch(AccelHandle* h, const char* plan, const char* op_name, float* out, int64_t shape[4], void* stream);
+
 /* CUDA-graph cache of the handle: every distinct set of caller pointers is captured once (a miss costs a stream
  * capture + instantiate, ~100x a replay); callers that see `misses` grow per frame are passing fresh temporaries. */
 int accel_graph_cache_stats(const AccelHandle* h, uint64_t* hits, uint64_t* misses);

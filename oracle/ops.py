@@ -105,6 +105,14 @@ def bilinear_sampler(data, grid):
     return out
 
 
+# DCNv1's "zero outside" rule is DISCONTINUOUS in the sampling position: a tap at p = -1e-6 contributes 0, at p = +1e-6 the
+# full border value (same at p = H / W).  When DCN_TRACE is a list, every call appends a boolean (N, Ho, Wo) map of the
+# output pixels that have a tap within DCN_TRACE_TAU of such a jump: there, any two implementations whose offset inputs
+# differ by rounding noise may legitimately disagree by O(|x|) (tests/test_oracle_ops.py::test_dcn_border_rule_is_discontinuous).
+DCN_TRACE = None
+DCN_TRACE_TAU = 2e-4
+
+
 def deformable_convolution(x, offset, weight, stride, pad, dilate, num_deformable_group):
     """mx.contrib.symbol.DeformableConvolution, DCNv1 (...flownet_deeplab.py:146-148,1235-1237)
     [MXNet-ext].  offset is (N, dg*2*kh*kw, Ho, Wo); inside deformable group g channel
@@ -123,6 +131,7 @@ def deformable_convolution(x, offset, weight, stride, pad, dilate, num_deformabl
     base_x = (torch.arange(wo, dtype=torch.float32) * stride - pad).view(1, 1, wo)
     cols = torch.zeros(n, c, kh * kw, ho * wo, dtype=x.dtype)
     flat = x.reshape(n, c, h * w)
+    critical = torch.zeros(n, ho, wo, dtype=torch.bool) if DCN_TRACE is not None else None
     for g in range(num_deformable_group):
         xs = flat[:, g * cpg:(g + 1) * cpg]
         for i in range(kh):
@@ -133,6 +142,11 @@ def deformable_convolution(x, offset, weight, stride, pad, dilate, num_deformabl
                 py = base_y + float(i * dilate) + oy
                 px = base_x + float(j * dilate) + ox
                 inside = (py >= 0) & (px >= 0) & (py < h) & (px < w)
+                if critical is not None:
+                    t = DCN_TRACE_TAU
+                    near_y = (py.abs() < t) | ((py - h).abs() < t)
+                    near_x = (px.abs() < t) | ((px - w).abs() < t)
+                    critical |= (near_y & (px > -t) & (px < w + t)) | (near_x & (py > -t) & (py < h + t))
                 y0 = torch.floor(py)
                 x0 = torch.floor(px)
                 top = y0 >= h - 1
@@ -152,6 +166,8 @@ def deformable_convolution(x, offset, weight, stride, pad, dilate, num_deformabl
                     idx = (yy.clamp(0, h - 1) * w + xx.clamp(0, w - 1)).long().view(n, 1, -1).expand(n, cpg, -1)
                     acc = acc + torch.gather(xs, 2, idx) * (wgt * inside).view(n, 1, -1)
                 cols[:, g * cpg:(g + 1) * cpg, k] = acc
+    if critical is not None:
+        DCN_TRACE.append(critical)
     out = torch.einsum("ok,nkp->nop", weight.reshape(cout, c * kh * kw), cols.reshape(n, c * kh * kw, ho * wo))
     return out.view(n, cout, ho, wo)
 

@@ -9,8 +9,11 @@ margin is <= 2*err.  The tests therefore
   * bound the TOTAL number of mismatching pixels (MAX_MISMATCH_FRAC), reporting the counts.
 Scaling the synthetic `score_weight` cannot tighten this further: the score error is fp32 re-association noise of the
 100-layer trunk, relative to the score magnitude, so margins and error scale together."""
+import contextlib
+
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from oracle import ops
 
@@ -19,21 +22,58 @@ MIN_DECIDED = 0.998
 MAX_MISMATCH_FRAC = 2e-4
 
 
+@contextlib.contextmanager
+def dcn_trace(store):
+    """Runs oracle code with ops.DCN_TRACE on and appends the flagged maps to `store` (a list)."""
+    ops.DCN_TRACE = []
+    try:
+        yield
+    finally:
+        store.extend(ops.DCN_TRACE)
+        ops.DCN_TRACE = None
+
+
+def critical_mask(trace_maps, H, W, radius=12):
+    """(H, W) bool mask of the frame pixels inside the footprint of a border-critical deformable sample
+    (oracle/ops.py DCN_TRACE): DCNv1's `0 unless 0 <= p < H` rule is discontinuous, so where a tap lies within 2e-4 of the
+    image border the reference operator itself changes by O(|x|) under rounding-noise-sized changes of its offset input
+    (test_dcn_border_rule_is_discontinuous; measured on the oracle: offsets shifted by 1e-4 move res5c by 2.4-3.6 in
+    20-80 feature pixels).  Footprint = the flagged feature pixel dilated by `radius` pixels of the stride-16 grid
+    (two more deformable 3x3/dil-2 convs and their offset convs, the heads, the x16 bilinear upsampling)."""
+    h, w = H // 16, W // 16
+    m = torch.zeros(1, 1, h, w)
+    for t in trace_maps:
+        t = t.float().reshape(1, 1, t.shape[-2], t.shape[-1])
+        if t.shape[-2:] != (h, w):
+            t = F.interpolate(t, size=(h, w), mode="nearest")
+        m = torch.maximum(m, t)
+    if m.sum() == 0:
+        return np.zeros((H, W), dtype=bool)
+    m = F.max_pool2d(m, 2 * radius + 1, 1, radius)
+    return F.interpolate(m, size=(H, W), mode="nearest")[0, 0].numpy() > 0
+
+
 def label_report(label, gpu_score, ref_score, min_decided=MIN_DECIDED, max_mismatch_frac=MAX_MISMATCH_FRAC,
-                 score_tol=SCORE_TOL):
-    """label: (H,W) uint8 array/tensor from the CUDA path; gpu_score / ref_score: (1,K,H,W) CPU tensors.
-    Asserts the rule above and returns the counts."""
+                 score_tol=SCORE_TOL, exclude=None):
+    """label: (H,W) uint8 array/tensor from the CUDA path; gpu_score / ref_score: (1,K,H,W) CPU tensors; exclude: optional
+    (H,W) bool mask from critical_mask() -- pixels where the reference operator itself is discontinuous are reported
+    (`excluded_px`, `score_max_abs_incl_excluded`) but not held to the tolerance.  Asserts the rule above and returns the counts."""
     label = label.cpu().numpy() if isinstance(label, torch.Tensor) else np.asarray(label)
-    err = (gpu_score - ref_score).abs().max().item()
-    assert err < score_tol, "score volume max-abs error %.3e exceeds %.0e" % (err, score_tol)
+    emap = (gpu_score - ref_score).abs()[0].max(dim=0).values.numpy()
+    keep = np.ones_like(emap, dtype=bool) if exclude is None else ~exclude
+    err = float(emap[keep].max())
+    assert err < score_tol, "score volume max-abs error %.3e exceeds %.0e (outside %d excluded px)" % (err, score_tol, int((~keep).sum()))
     ref_label = ops.argmax_channel(ref_score)[0]
     top2 = ref_score.topk(2, dim=1).values
     margin = (top2[:, 0] - top2[:, 1])[0].numpy()
-    diff = label != ref_label
-    decided = margin > 2.0 * err
+    diff = (label != ref_label) & keep
+    decided = (margin > 2.0 * err) | ~keep
     n = label.size
     rep = {"score_max_abs": err, "pixels": n, "mismatch": int(diff.sum()), "mismatch_decided": int((diff & decided).sum()),
-           "undecided": int((~decided).sum()), "undecided_at_2e-3": int((margin <= 2 * score_tol).sum())}
+           "undecided": int((~decided).sum()), "undecided_at_2e-3": int(((margin <= 2 * score_tol) & keep).sum())}
+    if exclude is not None:
+        rep["excluded_px"] = int((~keep).sum())
+        rep["score_max_abs_incl_excluded"] = float(emap.max())
     assert rep["mismatch_decided"] == 0, "label differs from the oracle outside the score error band: %r" % rep
     assert decided.mean() >= min_decided, "only %.5f of the pixels are decided: %r" % (decided.mean(), rep)
     assert rep["mismatch"] <= max(1, int(max_mismatch_frac * n)), "too many flipped labels: %r" % rep

@@ -135,3 +135,27 @@ def test_fast_hist_and_iu():
     assert h.tolist() == [[1, 0, 0], [0, 1, 0], [0, 1, 2]]
     iu = ops.per_class_iu(h)
     assert np.allclose(iu, [1.0, 0.5, 2.0 / 3.0])
+
+
+def test_dcn_border_rule_is_discontinuous():
+    """DCNv1's `0 unless 0 <= p < H` rule jumps at the image border: shifting one tap's offset by 2e-6 across p = 0 changes
+    the output by O(|x|), and ops.DCN_TRACE flags exactly that output pixel.  This is why graph-level parity is stated
+    away from `border-critical` deformable samples (tests/parity_util.py)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 8, 6, 7, generator=g) + 1.0
+    w = torch.rand(4, 8, 3, 3, generator=g)
+    off = torch.full((1, 18, 6, 7), 0.37)                      # generic positions: no other tap sits on a border
+    # tap (i=1, j=0) of output pixel (2, 1): base x = 1 - 2 + 0 = -1; dx = 1 +- 1e-6 puts it just inside / outside x = 0
+    outs = []
+    for d in (1.0 + 1e-6, 1.0 - 1e-6):
+        o = off.clone()
+        o[0, 2 * 3 + 1, 2, 1] = d
+        ops.DCN_TRACE = []
+        outs.append(ops.deformable_convolution(x, o, w, 1, 2, 2, 1))
+        trace = ops.DCN_TRACE
+        ops.DCN_TRACE = None
+        assert trace[0].sum().item() == 1 and bool(trace[0][0, 2, 1])
+    diff = (outs[0] - outs[1]).abs()
+    assert diff[0, :, 2, 1].max().item() > 0.5                 # an O(1) jump for a 2e-6 change of the offset ...
+    diff[0, :, 2, 1] = 0
+    assert diff.max().item() == 0.0                             # ... at that pixel only
