@@ -301,18 +301,20 @@ __global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restric
       }
 #pragma unroll
       for (int k = 0; k < WP_UNROLL; ++k) {
-        float v = __fmul_rn(a[k], w00);
-        v = __fadd_rn(v, __fmul_rn(b[k], w01));
-        v = __fadd_rn(v, __fmul_rn(c[k], w10));
-        v = __fadd_rn(v, __fmul_rn(d[k], w11));
+        // taps with a zero weight (out of range, as MXNet's BilinearSampler skips them) contribute by VALUE zero: an Inf /
+        // NaN in the clamped neighbour must not become NaN here
+        float v = __fmul_rn(w00 != 0.f ? a[k] : 0.f, w00);
+        v = __fadd_rn(v, __fmul_rn(w01 != 0.f ? b[k] : 0.f, w01));
+        v = __fadd_rn(v, __fmul_rn(w10 != 0.f ? c[k] : 0.f, w10));
+        v = __fadd_rn(v, __fmul_rn(w11 != 0.f ? d[k] : 0.f, w11));
         po[(size_t)k * npix] = v;
       }
     } else {
       for (int k = 0; c0 + k < C; ++k) {
-        float v = __fmul_rn(__ldg(p00 + (size_t)k * npix), w00);
-        v = __fadd_rn(v, __fmul_rn(__ldg(p01 + (size_t)k * npix), w01));
-        v = __fadd_rn(v, __fmul_rn(__ldg(p10 + (size_t)k * npix), w10));
-        v = __fadd_rn(v, __fmul_rn(__ldg(p11 + (size_t)k * npix), w11));
+        float v = __fmul_rn(w00 != 0.f ? __ldg(p00 + (size_t)k * npix) : 0.f, w00);
+        v = __fadd_rn(v, __fmul_rn(w01 != 0.f ? __ldg(p01 + (size_t)k * npix) : 0.f, w01));
+        v = __fadd_rn(v, __fmul_rn(w10 != 0.f ? __ldg(p10 + (size_t)k * npix) : 0.f, w10));
+        v = __fadd_rn(v, __fmul_rn(w11 != 0.f ? __ldg(p11 + (size_t)k * npix) : 0.f, w11));
         po[(size_t)k * npix] = v;
       }
     }

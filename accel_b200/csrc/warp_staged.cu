@@ -156,19 +156,19 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
             }
 #pragma unroll
             for (int ch = 0; ch < WS_CB; ++ch) {
-              float v = __fmul_rn(a[ch], t.w00);
-              v = __fadd_rn(v, __fmul_rn(b[ch], t.w01));
-              v = __fadd_rn(v, __fmul_rn(c[ch], t.w10));
-              v = __fadd_rn(v, __fmul_rn(d[ch], t.w11));
+              float v = __fmul_rn(t.w00 != 0.f ? a[ch] : 0.f, t.w00);      // zero-weight (out-of-range) taps: skipped by value
+              v = __fadd_rn(v, __fmul_rn(t.w01 != 0.f ? b[ch] : 0.f, t.w01));
+              v = __fadd_rn(v, __fmul_rn(t.w10 != 0.f ? c[ch] : 0.f, t.w10));
+              v = __fadd_rn(v, __fmul_rn(t.w11 != 0.f ? d[ch] : 0.f, t.w11));
               po[(size_t)ch * npix] = v;
             }
           } else {
             for (int ch = 0; ch < nc; ++ch) {
               const float* sp = st + ch * slot + t.o00;
-              float v = __fmul_rn(sp[0], t.w00);
-              v = __fadd_rn(v, __fmul_rn(sp[t.dx1], t.w01));
-              v = __fadd_rn(v, __fmul_rn(sp[t.dyw], t.w10));
-              v = __fadd_rn(v, __fmul_rn(sp[t.dyw + t.dx1], t.w11));
+              float v = __fmul_rn(t.w00 != 0.f ? sp[0] : 0.f, t.w00);
+              v = __fadd_rn(v, __fmul_rn(t.w01 != 0.f ? sp[t.dx1] : 0.f, t.w01));
+              v = __fadd_rn(v, __fmul_rn(t.w10 != 0.f ? sp[t.dyw] : 0.f, t.w10));
+              v = __fadd_rn(v, __fmul_rn(t.w11 != 0.f ? sp[t.dyw + t.dx1] : 0.f, t.w11));
               po[(size_t)ch * npix] = v;
             }
           }
@@ -197,19 +197,19 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
             }
 #pragma unroll
             for (int ch = 0; ch < WS_CB; ++ch) {
-              float v = __fmul_rn(a[ch], t.w00);
-              v = __fadd_rn(v, __fmul_rn(b[ch], t.w01));
-              v = __fadd_rn(v, __fmul_rn(c[ch], t.w10));
-              v = __fadd_rn(v, __fmul_rn(d[ch], t.w11));
+              float v = __fmul_rn(t.w00 != 0.f ? a[ch] : 0.f, t.w00);      // zero-weight (out-of-range) taps: skipped by value
+              v = __fadd_rn(v, __fmul_rn(t.w01 != 0.f ? b[ch] : 0.f, t.w01));
+              v = __fadd_rn(v, __fmul_rn(t.w10 != 0.f ? c[ch] : 0.f, t.w10));
+              v = __fadd_rn(v, __fmul_rn(t.w11 != 0.f ? d[ch] : 0.f, t.w11));
               po[(size_t)ch * npix] = v;
             }
           } else {
             for (int ch = 0; ch < nc; ++ch) {
               const float* sp = sp0 + (size_t)ch * npix;
-              float v = __fmul_rn(__ldg(sp), t.w00);
-              v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dx1), t.w01));
-              v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dyw), t.w10));
-              v = __fadd_rn(v, __fmul_rn(__ldg(sp + t.dyw + t.dx1), t.w11));
+              float v = __fmul_rn(t.w00 != 0.f ? __ldg(sp) : 0.f, t.w00);
+              v = __fadd_rn(v, __fmul_rn(t.w01 != 0.f ? __ldg(sp + t.dx1) : 0.f, t.w01));
+              v = __fadd_rn(v, __fmul_rn(t.w10 != 0.f ? __ldg(sp + t.dyw) : 0.f, t.w10));
+              v = __fadd_rn(v, __fmul_rn(t.w11 != 0.f ? __ldg(sp + t.dyw + t.dx1) : 0.f, t.w11));
               po[(size_t)ch * npix] = v;
             }
           }

@@ -52,6 +52,27 @@ def test_warp_mixed_band_heights():
     assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("gather", ["0", "1"])
+def test_warp_out_of_range_taps_are_skipped_by_value(gather, monkeypatch):
+    """MXNet's BilinearSampler skips out-of-range taps; a zero WEIGHT on a clamped neighbour is not the same thing when
+    that neighbour holds Inf (0 * Inf = NaN).  A pixel whose sample lies wholly outside the map must read 0 even if the
+    feature at its own location is Inf."""
+    monkeypatch.setenv("ACCEL_WARP_GATHER", gather)
+    c, h, w = 64, 16, 128
+    feat = _rand(1, c, h, w, seed=40)
+    feat[0, :, 5, 7] = float("inf")
+    flow = torch.zeros(1, 2, h, w)
+    flow[0, 0, 5, 7] = 1000.0                       # (5, 7) samples far outside; every other pixel is the identity
+    flow[0, 0, 5, 6] = 0.5                          # its left neighbour blends (5,6) and (5,7): Inf, legitimately
+    out = E.warp(feat.to(DEV), flow.to(DEV)).cpu()
+    ref = ops.bilinear_sampler(feat, ops.grid_generator_warp(flow))
+    assert torch.isfinite(ref[0, :, 5, 7]).all() and (ref[0, :, 5, 7] == 0).all()
+    assert (out[0, :, 5, 7] == 0).all()
+    assert torch.isinf(out[0, :, 5, 6]).all()
+    fin = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(out), fin) and torch.equal(out[fin], ref[fin])
+
+
 def test_warp_zero_flow_identity_and_integer_shift():
     feat = _rand(1, 32, 16, 32, seed=3)
     zero = torch.zeros(1, 2, 16, 32)
