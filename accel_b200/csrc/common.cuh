@@ -79,6 +79,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Flow-guided warp: an out-of-range tap carries the weight -0.0f, which no in-range tap can have (its weights are products
+// of values in [0, 1]).  Out-of-range taps are skipped by VALUE, as MXNet's BilinearSampler skips them -- the clamped
+// neighbour they point at may hold Inf -- while an in-range tap whose weight happens to be +0 still multiplies, as it does
+// there (0 * Inf = NaN in both).
+constexpr float kSkipTap = -0.0f;
+__device__ __forceinline__ bool keep_tap(float w) { return __float_as_uint(w) != 0x80000000u; }
+
 // Two values at a time: hi2 = rn16x2(v), lo2 = rn16x2(v - hi2), both saturating to +-65504 (one packed convert each
 // instead of clamp + scalar converts: 3 instructions per element instead of 7 -- the split is on the critical path
 // of every epilogue).  For |v| <= 65504 this is exactly hi = rn16(v), lo = rn16(v - hi).

@@ -1263,13 +1263,16 @@ bool Graph::run_eager(const std::string& which, void* const ext[X_COUNT], cudaSt
       const Tensor& to = tensors_[op.out];
       std::vector<__half> hbuf((size_t)to.H * to.W * to.ld);
       cudaMemcpy(hbuf.data(), hi_ptr(to) - to.coff, hbuf.size() * sizeof(__half), cudaMemcpyDeviceToHost);
-      double sum = 0.0, asum = 0.0;
+      double sum = 0.0, asum = 0.0, amax = 0.0;
       for (size_t px = 0; px < (size_t)to.H * to.W; ++px)
         for (int c = 0; c < to.C; ++c) {
           const double v = (double)__half2float(hbuf[px * to.ld + to.coff + c]);
-          sum += v; asum += fabs(v);
+          sum += v; asum += fabs(v); amax = std::max(amax, fabs(v));
         }
-      fprintf(stderr, "ACCEL_SUM %s/%s C=%d coff=%d ld=%d sum=%.6e abs=%.6e\n", op.stage.c_str(), op.name.c_str(), to.C, to.coff, to.ld, sum, asum);
+      // |hi| == 65504: the split format clamped an activation (cvt.rn.satfinite) -- a checkpoint whose activations leave
+      // the fp16 range would silently lose them; this is where to look for it
+      fprintf(stderr, "ACCEL_SUM %s/%s C=%d coff=%d ld=%d sum=%.6e abs=%.6e max=%.6e%s\n", op.stage.c_str(), op.name.c_str(), to.C,
+              to.coff, to.ld, sum, asum, amax, amax >= 65504.0 ? "  SATURATED (fp16 range)" : "");
     }
   }
   if (cur_group && (ce = join_all()) != cudaSuccess) { *err = std::string("join failed: ") + cudaGetErrorString(ce); return false; }

@@ -276,10 +276,10 @@ __global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restric
     const int yi0 = min(max((int)yf, 0), H - 1), yi1 = min(max((int)yf + 1, 0), H - 1);
     i00 = yi0 * W + xi0; i01 = yi0 * W + xi1; i10 = yi1 * W + xi0; i11 = yi1 * W + xi1;
   }
-  const float w00 = (sane && y0ok && x0ok) ? __fmul_rn(wy0, wx0) : 0.f;
-  const float w01 = (sane && y0ok && x1ok) ? __fmul_rn(wy0, wx1) : 0.f;
-  const float w10 = (sane && y1ok && x0ok) ? __fmul_rn(wy1, wx0) : 0.f;
-  const float w11 = (sane && y1ok && x1ok) ? __fmul_rn(wy1, wx1) : 0.f;
+  const float w00 = (sane && y0ok && x0ok) ? __fmul_rn(wy0, wx0) : kSkipTap;
+  const float w01 = (sane && y0ok && x1ok) ? __fmul_rn(wy0, wx1) : kSkipTap;
+  const float w10 = (sane && y1ok && x0ok) ? __fmul_rn(wy1, wx0) : kSkipTap;
+  const float w11 = (sane && y1ok && x1ok) ? __fmul_rn(wy1, wx1) : kSkipTap;
 
   const int nbatch = (C + WP_UNROLL - 1) / WP_UNROLL;
   for (int bt = blockIdx.y; bt < nbatch; bt += gridDim.y) {
@@ -303,18 +303,18 @@ __global__ void __launch_bounds__(WP_THREADS) warp_kernel(const float* __restric
       for (int k = 0; k < WP_UNROLL; ++k) {
         // taps with a zero weight (out of range, as MXNet's BilinearSampler skips them) contribute by VALUE zero: an Inf /
         // NaN in the clamped neighbour must not become NaN here
-        float v = __fmul_rn(w00 != 0.f ? a[k] : 0.f, w00);
-        v = __fadd_rn(v, __fmul_rn(w01 != 0.f ? b[k] : 0.f, w01));
-        v = __fadd_rn(v, __fmul_rn(w10 != 0.f ? c[k] : 0.f, w10));
-        v = __fadd_rn(v, __fmul_rn(w11 != 0.f ? d[k] : 0.f, w11));
+        float v = __fmul_rn(keep_tap(w00) ? a[k] : 0.f, w00);
+        v = __fadd_rn(v, __fmul_rn(keep_tap(w01) ? b[k] : 0.f, w01));
+        v = __fadd_rn(v, __fmul_rn(keep_tap(w10) ? c[k] : 0.f, w10));
+        v = __fadd_rn(v, __fmul_rn(keep_tap(w11) ? d[k] : 0.f, w11));
         po[(size_t)k * npix] = v;
       }
     } else {
       for (int k = 0; c0 + k < C; ++k) {
-        float v = __fmul_rn(w00 != 0.f ? __ldg(p00 + (size_t)k * npix) : 0.f, w00);
-        v = __fadd_rn(v, __fmul_rn(w01 != 0.f ? __ldg(p01 + (size_t)k * npix) : 0.f, w01));
-        v = __fadd_rn(v, __fmul_rn(w10 != 0.f ? __ldg(p10 + (size_t)k * npix) : 0.f, w10));
-        v = __fadd_rn(v, __fmul_rn(w11 != 0.f ? __ldg(p11 + (size_t)k * npix) : 0.f, w11));
+        float v = __fmul_rn(keep_tap(w00) ? __ldg(p00 + (size_t)k * npix) : 0.f, w00);
+        v = __fadd_rn(v, __fmul_rn(keep_tap(w01) ? __ldg(p01 + (size_t)k * npix) : 0.f, w01));
+        v = __fadd_rn(v, __fmul_rn(keep_tap(w10) ? __ldg(p10 + (size_t)k * npix) : 0.f, w10));
+        v = __fadd_rn(v, __fmul_rn(keep_tap(w11) ? __ldg(p11 + (size_t)k * npix) : 0.f, w11));
         po[(size_t)k * npix] = v;
       }
     }

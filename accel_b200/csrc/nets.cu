@@ -409,7 +409,8 @@ bool build_interval(Graph& g, int version, int H, int W, int K, int interval, st
         s[i].par_group = grp;
         s[i].par_branch = (int)c + 1;
         s[i].par_width = 1;
-        s[i].sm_budget = share[c];
+        static const bool full_width = [] { const char* e = getenv("ACCEL_IVL_FULLWIDTH"); return e && e[0] == '1'; }();
+        s[i].sm_budget = full_width ? 0 : share[c];       // 1: every chain plans for all SMs and the hardware interleaves them
       }
   }
   // sequential part: the chained warps and what consumes them

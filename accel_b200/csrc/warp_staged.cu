@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
   for (int k = 0; k < WS_PPT; ++k) {
     const int q = tid + k * WS_THREADS;
     Tap t;
-    t.o00 = 0; t.dx1 = 0; t.dyw = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+    t.o00 = 0; t.dx1 = 0; t.dyw = 0; t.w00 = t.w01 = t.w10 = t.w11 = kSkipTap;
     if (q < tile) {
       const int y = y0 + q / W, x = q - (q / W) * W;
       const int p = y * W + x;
@@ -83,10 +83,10 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
       if (sane && (x0ok || x1ok) && (y0ok || y1ok)) {
         xi0 = min(max((int)xf, 0), W - 1); xi1 = min(max((int)xf + 1, 0), W - 1);
         yi0 = min(max((int)yf, 0), H - 1); yi1 = min(max((int)yf + 1, 0), H - 1);
-        t.w00 = (y0ok && x0ok) ? __fmul_rn(wy0, wx0) : 0.f;
-        t.w01 = (y0ok && x1ok) ? __fmul_rn(wy0, wx1) : 0.f;
-        t.w10 = (y1ok && x0ok) ? __fmul_rn(wy1, wx0) : 0.f;
-        t.w11 = (y1ok && x1ok) ? __fmul_rn(wy1, wx1) : 0.f;
+        t.w00 = (y0ok && x0ok) ? __fmul_rn(wy0, wx0) : kSkipTap;
+        t.w01 = (y0ok && x1ok) ? __fmul_rn(wy0, wx1) : kSkipTap;
+        t.w10 = (y1ok && x0ok) ? __fmul_rn(wy1, wx0) : kSkipTap;
+        t.w11 = (y1ok && x1ok) ? __fmul_rn(wy1, wx1) : kSkipTap;
       }
       t.o00 = yi0 * W + xi0; t.dx1 = xi1 - xi0; t.dyw = (yi1 - yi0) * W;
       ymin = min(ymin, yi0); ymax = max(ymax, yi1);
@@ -156,19 +156,19 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
             }
 #pragma unroll
             for (int ch = 0; ch < WS_CB; ++ch) {
-              float v = __fmul_rn(t.w00 != 0.f ? a[ch] : 0.f, t.w00);      // zero-weight (out-of-range) taps: skipped by value
-              v = __fadd_rn(v, __fmul_rn(t.w01 != 0.f ? b[ch] : 0.f, t.w01));
-              v = __fadd_rn(v, __fmul_rn(t.w10 != 0.f ? c[ch] : 0.f, t.w10));
-              v = __fadd_rn(v, __fmul_rn(t.w11 != 0.f ? d[ch] : 0.f, t.w11));
+              float v = __fmul_rn(keep_tap(t.w00) ? a[ch] : 0.f, t.w00);      // zero-weight (out-of-range) taps: skipped by value
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w01) ? b[ch] : 0.f, t.w01));
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w10) ? c[ch] : 0.f, t.w10));
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w11) ? d[ch] : 0.f, t.w11));
               po[(size_t)ch * npix] = v;
             }
           } else {
             for (int ch = 0; ch < nc; ++ch) {
               const float* sp = st + ch * slot + t.o00;
-              float v = __fmul_rn(t.w00 != 0.f ? sp[0] : 0.f, t.w00);
-              v = __fadd_rn(v, __fmul_rn(t.w01 != 0.f ? sp[t.dx1] : 0.f, t.w01));
-              v = __fadd_rn(v, __fmul_rn(t.w10 != 0.f ? sp[t.dyw] : 0.f, t.w10));
-              v = __fadd_rn(v, __fmul_rn(t.w11 != 0.f ? sp[t.dyw + t.dx1] : 0.f, t.w11));
+              float v = __fmul_rn(keep_tap(t.w00) ? sp[0] : 0.f, t.w00);
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w01) ? sp[t.dx1] : 0.f, t.w01));
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w10) ? sp[t.dyw] : 0.f, t.w10));
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w11) ? sp[t.dyw + t.dx1] : 0.f, t.w11));
               po[(size_t)ch * npix] = v;
             }
           }
@@ -197,19 +197,19 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
             }
 #pragma unroll
             for (int ch = 0; ch < WS_CB; ++ch) {
-              float v = __fmul_rn(t.w00 != 0.f ? a[ch] : 0.f, t.w00);      // zero-weight (out-of-range) taps: skipped by value
-              v = __fadd_rn(v, __fmul_rn(t.w01 != 0.f ? b[ch] : 0.f, t.w01));
-              v = __fadd_rn(v, __fmul_rn(t.w10 != 0.f ? c[ch] : 0.f, t.w10));
-              v = __fadd_rn(v, __fmul_rn(t.w11 != 0.f ? d[ch] : 0.f, t.w11));
+              float v = __fmul_rn(keep_tap(t.w00) ? a[ch] : 0.f, t.w00);      // zero-weight (out-of-range) taps: skipped by value
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w01) ? b[ch] : 0.f, t.w01));
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w10) ? c[ch] : 0.f, t.w10));
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w11) ? d[ch] : 0.f, t.w11));
               po[(size_t)ch * npix] = v;
             }
           } else {
             for (int ch = 0; ch < nc; ++ch) {
               const float* sp = sp0 + (size_t)ch * npix;
-              float v = __fmul_rn(t.w00 != 0.f ? __ldg(sp) : 0.f, t.w00);
-              v = __fadd_rn(v, __fmul_rn(t.w01 != 0.f ? __ldg(sp + t.dx1) : 0.f, t.w01));
-              v = __fadd_rn(v, __fmul_rn(t.w10 != 0.f ? __ldg(sp + t.dyw) : 0.f, t.w10));
-              v = __fadd_rn(v, __fmul_rn(t.w11 != 0.f ? __ldg(sp + t.dyw + t.dx1) : 0.f, t.w11));
+              float v = __fmul_rn(keep_tap(t.w00) ? __ldg(sp) : 0.f, t.w00);
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w01) ? __ldg(sp + t.dx1) : 0.f, t.w01));
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w10) ? __ldg(sp + t.dyw) : 0.f, t.w10));
+              v = __fadd_rn(v, __fmul_rn(keep_tap(t.w11) ? __ldg(sp + t.dyw + t.dx1) : 0.f, t.w11));
               po[(size_t)ch * npix] = v;
             }
           }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
   const uint32_t full0 = smem_u32(&wf_bars[0]), empty0 = smem_u32(&wf_bars[WF_STAGES]);
 
   Tap t;
-  t.o00 = 0; t.dx1 = 0; t.dyw = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+  t.o00 = 0; t.dx1 = 0; t.dyw = 0; t.w00 = t.w01 = t.w10 = t.w11 = kSkipTap;
   int ymin = H, ymax = -1;
   const bool live = !producer && tid < tile;
   if (live) {
@@ -290,10 +290,10 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
     if (sane && (x0ok || x1ok) && (y0ok || y1ok)) {
       xi0 = min(max((int)xf, 0), W - 1); xi1 = min(max((int)xf + 1, 0), W - 1);
       yi0 = min(max((int)yf, 0), H - 1); yi1 = min(max((int)yf + 1, 0), H - 1);
-      t.w00 = (y0ok && x0ok) ? __fmul_rn(wy0, wx0) : 0.f;
-      t.w01 = (y0ok && x1ok) ? __fmul_rn(wy0, wx1) : 0.f;
-      t.w10 = (y1ok && x0ok) ? __fmul_rn(wy1, wx0) : 0.f;
-      t.w11 = (y1ok && x1ok) ? __fmul_rn(wy1, wx1) : 0.f;
+      t.w00 = (y0ok && x0ok) ? __fmul_rn(wy0, wx0) : kSkipTap;
+      t.w01 = (y0ok && x1ok) ? __fmul_rn(wy0, wx1) : kSkipTap;
+      t.w10 = (y1ok && x0ok) ? __fmul_rn(wy1, wx0) : kSkipTap;
+      t.w11 = (y1ok && x1ok) ? __fmul_rn(wy1, wx1) : kSkipTap;
     }
     t.o00 = yi0 * W + xi0; t.dx1 = xi1 - xi0; t.dyw = (yi1 - yi0) * W;
     ymin = yi0; ymax = yi1;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
 
   // ---------------------------------------------------------------- consumers
   if (staged) t.o00 -= r0 * W;
-  const bool n00 = t.w00 != 0.f, n01 = t.w01 != 0.f, n10 = t.w10 != 0.f, n11 = t.w11 != 0.f;
+  const bool n00 = keep_tap(t.w00), n01 = keep_tap(t.w01), n10 = keep_tap(t.w10), n11 = keep_tap(t.w11);
   int s = 0;
   uint32_t ph = 0;
   for (int g = blockIdx.y; g < ngroups; g += gridDim.y) {

@@ -147,6 +147,39 @@ def resnet_dcn_101(p, data):
     return _bottleneck_net(p, data, "", units, (18, 1, 1, 1))
 
 
+def resnet_dcn_101_layers(p, data):
+    """resnet_dcn_101 with every activation kept under the name of the layer that produces it (conv + BN [+ ReLU]
+    [+ shortcut] fused, i.e. what the CUDA plan's op of that name leaves behind): per-layer parity through
+    accel_debug_fetch (tests/test_gpu_layers.py, tools/layer_parity.py).  Same code path as _bottleneck_net."""
+    acts = {}
+    eps = 1e-5
+    x = torch.relu(_bn(p, _conv(p, data, "conv1", 2, 3), "bn_conv1", eps))
+    acts["conv1"] = x
+    x = ops.pooling(x, 3, 2, 0, "max", full=True)
+    acts["maxpool"] = x
+    units = (("a", "b", "c"), ("a", "b1", "b2", "b3"), ("a",) + tuple("b%d" % i for i in range(1, 23)), ("a", "b", "c"))
+    for stage, us in zip((2, 3, 4, 5), units):
+        for n, u in enumerate(us):
+            stride = 2 if (n == 0 and stage in (3, 4)) else 1
+            r, b = "res%d%s" % (stage, u), "bn%d%s" % (stage, u)
+            sc = x
+            if n == 0:
+                sc = _bn(p, _conv(p, x, r + "_branch1", stride, 0), b + "_branch1", eps)
+                acts[r + "_branch1"] = sc
+            a = torch.relu(_bn(p, _conv(p, x, r + "_branch2a", stride, 0), b + "_branch2a", eps))
+            acts[r + "_branch2a"] = a
+            if stage == 5:
+                off = _conv(p, a, r + "_branch2b_offset", 1, 1, 1, bias=True)
+                m = ops.deformable_convolution(a, off, p[r + "_branch2b_weight"], 1, 2, 2, 1)
+            else:
+                m = _conv(p, a, r + "_branch2b", 1, 1)
+            m = torch.relu(_bn(p, m, b + "_branch2b", eps))
+            acts[r + "_branch2b"] = m
+            x = torch.relu(sc + _bn(p, _conv(p, m, r + "_branch2c", 1, 0), b + "_branch2c", eps))
+            acts[r + "_branch2c"] = x
+    return acts
+
+
 # ----------------------------------------------------------------------------- heads and graphs
 def deeplab_head(p, feat, data, fc6, score, upsampling):
     """fc6 1x1 -> ReLU -> score 1x1 -> grouped 32x32/s16 deconv -> Crop(8,8)  (accel_18.py:177-197)."""

@@ -17,38 +17,6 @@ from accel_b200.engine import Engine  # noqa: E402
 from oracle import nets, ops  # noqa: E402
 
 
-def oracle_r101_layers(p, data):
-    """oracle/nets.py::_bottleneck_net for R101-DCN with every activation kept under the CUDA plan's op name."""
-    acts = {}
-    eps = 1e-5
-    x = torch.relu(nets._bn(p, nets._conv(p, data, "conv1", 2, 3), "bn_conv1", eps))
-    acts["conv1"] = x
-    x = ops.pooling(x, 3, 2, 0, "max", full=True)
-    acts["maxpool"] = x
-    units = (("a", "b", "c"), ("a", "b1", "b2", "b3"), ("a",) + tuple("b%d" % i for i in range(1, 23)), ("a", "b", "c"))
-    for stage, us in zip((2, 3, 4, 5), units):
-        for n, u in enumerate(us):
-            stride = 2 if (n == 0 and stage in (3, 4)) else 1
-            r, b = "res%d%s" % (stage, u), "bn%d%s" % (stage, u)
-            sc = x
-            if n == 0:
-                sc = nets._bn(p, nets._conv(p, x, r + "_branch1", stride, 0), b + "_branch1", eps)
-                acts[r + "_branch1"] = sc
-            a = torch.relu(nets._bn(p, nets._conv(p, x, r + "_branch2a", stride, 0), b + "_branch2a", eps))
-            acts[r + "_branch2a"] = a
-            if stage == 5:
-                off = nets._conv(p, a, r + "_branch2b_offset", 1, 1, 1, bias=True)
-                acts[r + "_branch2b_offset(f32)"] = off
-                m = ops.deformable_convolution(a, off, p[r + "_branch2b_weight"], 1, 2, 2, 1)
-            else:
-                m = nets._conv(p, a, r + "_branch2b", 1, 1)
-            m = torch.relu(nets._bn(p, m, b + "_branch2b", eps))
-            acts[r + "_branch2b"] = m
-            x = torch.relu(sc + nets._bn(p, nets._conv(p, m, r + "_branch2c", 1, 0), b + "_branch2c", eps))
-            acts[r + "_branch2c"] = x
-    return acts
-
-
 def main():
     H, W = 1024, 2048
     which = [int(a) for a in sys.argv[1:]] or [2]
@@ -60,14 +28,12 @@ def main():
     label = torch.empty(H, W, dtype=torch.uint8, device=dev)
     for t in which:
         with torch.no_grad():
-            acts = oracle_r101_layers(params, frames[t])
+            acts = nets.resnet_dcn_101_layers(params, frames[t])
         eng.key_forward(frames[t].to(dev), feat, None, label)
         torch.cuda.synchronize()
         print("==== frame %d" % t)
         reported = 0
         for name, ref in acts.items():
-            if name.endswith("(f32)"):
-                continue
             got = eng.fetch_layer("key", name)[0].cpu()
             e = (got - ref[0]).abs()
             scale = ref.abs().max().item()
