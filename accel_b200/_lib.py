@@ -14,7 +14,7 @@ SYMBOLS = (
     "accel_set_param", "accel_finalize", "accel_key_forward", "accel_cur_forward", "accel_key_forward_lin",
     "accel_cur_forward_lin", "accel_flownet", "accel_rbranch_forward", "accel_plan_interval", "accel_interval_forward",
     "accel_graph_cache_stats", "accel_debug_fetch",
-    "accel_warp", "accel_fuse_argmax", "accel_preprocess", "accel_confusion", "accel_conv_layer", "accel_head", "accel_last_launch_count",
+    "accel_warp", "accel_fuse_argmax", "accel_preprocess", "accel_resize_size", "accel_resize_bgr", "accel_confusion", "accel_conv_layer", "accel_head", "accel_last_launch_count",
     "accel_set_profiling", "accel_stage_times", "accel_op_times",
 )
 
@@ -63,6 +63,8 @@ def load():
     lib.accel_warp.argtypes = [vp, vp, vp, ip, ip, ip, vp]
     lib.accel_fuse_argmax.argtypes = [vp, vp, vp, vp, ip, ip, ip, u8p, vp, vp]
     lib.accel_preprocess.argtypes = [u8p, ip, ip, C.POINTER(C.c_double), vp, vp]
+    lib.accel_resize_size.argtypes = [ip, ip, C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.accel_resize_bgr.argtypes = [u8p, ip, ip, C.c_double, C.c_double, u8p, vp]
     lib.accel_confusion.argtypes = [u8p, u8p, C.c_size_t, ip, vp, vp]
     lib.accel_conv_layer.argtypes = [ip, vp, ip, ip, ip, vp, ip, ip, ip, ip, ip, ip, vp, vp, vp, ip, vp, ip, vp, ip,
                                      C.c_char_p, ip]

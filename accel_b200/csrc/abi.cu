@@ -348,6 +348,19 @@ extern "C" int accel_preprocess(const uint8_t* bgr_hwc, int height, int width, c
   return launch_preprocess(bgr_hwc, height, width, pixel_means_bgr, out, (cudaStream_t)stream) == cudaSuccess ? 0 : 5;
 }
 
+extern "C" int accel_resize_size(int src_height, int src_width, double fx, double fy, int* dst_height, int* dst_width) {
+  if (!dst_height || !dst_width || src_height < 1 || src_width < 1 || !(fx > 0.0) || !(fy > 0.0)) return 1;
+  resize_linear_size(src_height, src_width, fx, fy, dst_height, dst_width);
+  return 0;
+}
+
+extern "C" int accel_resize_bgr(const uint8_t* src_hwc, int src_height, int src_width, double fx, double fy, uint8_t* dst_hwc,
+                                void* stream) {
+  if (!src_hwc || !dst_hwc || src_height < 1 || src_width < 1 || !(fx > 0.0) || !(fy > 0.0)) return 1;
+  if (no_device(nullptr, 0)) return 6;
+  return launch_resize_linear(src_hwc, src_height, src_width, fx, fy, dst_hwc, (cudaStream_t)stream) == cudaSuccess ? 0 : 5;
+}
+
 extern "C" int accel_confusion(const uint8_t* pred, const uint8_t* label, size_t count, int num_classes, int64_t* hist,
                                void* stream) {
   if (!pred || !label || !hist || num_classes < 1 || num_classes > 32) return 1;

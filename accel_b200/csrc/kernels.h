@@ -157,6 +157,9 @@ cudaError_t launch_tail(const TailParams& P, cudaStream_t stream);
 // lib/utils/image.py:224-235 transform(): uint8 BGR HWC -> fp32 RGB NCHW minus PIXEL_MEANS (B, G, R order)
 cudaError_t launch_preprocess(const uint8_t* bgr_hwc, int H, int W, const double mean_bgr[3], float* out,
                               cudaStream_t stream);
+// lib/utils/image.py:211 cv2.resize(im, None, None, fx, fy, cv2.INTER_LINEAR) on (H, W, 3) uint8, bit-exact vs OpenCV
+void resize_linear_size(int sh, int sw, double fx, double fy, int* dh, int* dw);
+cudaError_t launch_resize_linear(const uint8_t* src, int sh, int sw, double fx, double fy, uint8_t* dst, cudaStream_t stream);
 // dff_deeplab/demo.py:50-53 fast_hist(): hist[label * K + pred] += 1 where label < K (device int64 K x K)
 cudaError_t launch_confusion(const uint8_t* pred, const uint8_t* label, size_t n, int K, unsigned long long* hist,
                              cudaStream_t stream);

@@ -54,6 +54,50 @@ __global__ void __launch_bounds__(256) preprocess_scalar_kernel(const uint8_t* _
   out[2 * npix + i] = (float)((double)src[3 * i] - mean_b);
 }
 
+// cv2.resize(im, None, None, fx, fy, INTER_LINEAR) for 8-bit BGR (lib/utils/image.py:211), bit for bit: OpenCV's fixed-point
+// separable bilinear.  Per destination column: fx = (float)((dx + 0.5) / fx_scale - 0.5), sx = floor, frac clamped to 0 at
+// both borders, coefficients rounded (half to even) to 11 bits; per destination row the same WITHOUT clamping the fraction
+// (both rows then clip to the border row, OpenCV's `clip(sy, 0, ssize.height)`); the horizontal pass keeps 11 fractional
+// bits and the vertical pass is ((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2.  An exact 2x decimation is
+// what OpenCV turns into INTER_AREA: the rounded mean of the 2x2 block.  Pinned against cv2 4.13 (tests/golden/
+// make_resize_vectors.py, tests/test_gpu_io.py).  One thread per destination pixel (3 bytes); HBM streaming.
+__global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst,
+                                                            int dh, int dw, double scale_x, double scale_y, int area2) {
+  pdl_trigger();
+  pdl_wait();
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+  if (dx >= dw || dy >= dh) return;
+  uint8_t* o = dst + ((size_t)dy * dw + dx) * 3;
+  if (area2) {
+    const uint8_t* p0 = src + ((size_t)(2 * dy) * sw + 2 * dx) * 3;
+    const uint8_t* p1 = p0 + (size_t)sw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = (uint8_t)((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
+    return;
+  }
+  // un-fused double multiply / subtract, as the host code OpenCV runs (an FMA here flips a coefficient now and then)
+  float fx = (float)__dsub_rn(__dmul_rn((double)dx + 0.5, scale_x), 0.5);
+  int sx = (int)floorf(fx);
+  fx -= (float)sx;
+  if (sx < 0) { fx = 0.f; sx = 0; }
+  if (sx >= sw - 1) { fx = 0.f; sx = sw - 1; }
+  const int a0 = __float2int_rn((1.f - fx) * 2048.f), a1 = __float2int_rn(fx * 2048.f);
+  const int sx1 = min(sx + 1, sw - 1);
+  float fy = (float)__dsub_rn(__dmul_rn((double)dy + 0.5, scale_y), 0.5);
+  const int sy = (int)floorf(fy);
+  fy -= (float)sy;
+  const int b0 = __float2int_rn((1.f - fy) * 2048.f), b1 = __float2int_rn(fy * 2048.f);
+  const int y0 = min(max(sy, 0), sh - 1), y1 = min(max(sy + 1, 0), sh - 1);
+  const uint8_t* r0 = src + (size_t)y0 * sw * 3;
+  const uint8_t* r1 = src + (size_t)y1 * sw * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
+    const int h1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+    o[c] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+  }
+}
+
 // fast_hist: hist[label * n + pred] += 1 for every pixel with label < n (labels are uint8, so `label >= 0`
 // always holds; 255 = Cityscapes "ignore").  pred >= n cannot come out of the argmax; such pixels are
 // dropped rather than corrupting a neighbouring bin.  Per-CTA histogram in shared memory (32-bit), 16
@@ -106,6 +150,22 @@ cudaError_t launch_preprocess(const uint8_t* bgr_hwc, int H, int W, const double
                     mean_bgr[0], mean_bgr[1], mean_bgr[2], out);
   }
   return cudaGetLastError();
+}
+
+void resize_linear_size(int sh, int sw, double fx, double fy, int* dh, int* dw) {
+  *dw = (int)nearbyint((double)sw * fx);          // saturate_cast<int>(ssize.width * inv_scale_x): round half to even
+  *dh = (int)nearbyint((double)sh * fy);
+}
+
+cudaError_t launch_resize_linear(const uint8_t* src, int sh, int sw, double fx, double fy, uint8_t* dst, cudaStream_t stream) {
+  int dh, dw;
+  resize_linear_size(sh, sw, fx, fy, &dh, &dw);
+  if (dh < 1 || dw < 1 || sh < 1 || sw < 1) return cudaErrorInvalidValue;
+  const double scale_x = 1.0 / fx, scale_y = 1.0 / fy;
+  // OpenCV: INTER_LINEAR with an exact integer 2x decimation in both directions is computed as INTER_AREA
+  const int area2 = (scale_x == 2.0 && scale_y == 2.0 && sw == 2 * dw && sh == 2 * dh) ? 1 : 0;
+  return launch_k(resize_linear_kernel, dim3((dw + 255) / 256, dh), dim3(256), 0, stream, src, sh, sw, dst, dh, dw, scale_x, scale_y,
+                  area2);
 }
 
 cudaError_t launch_confusion(const uint8_t* pred, const uint8_t* label, size_t n, int K, unsigned long long* hist,

@@ -342,6 +342,42 @@ def preprocess(frame_bgr_u8, out=None, pixel_means_bgr=None):
     return out
 
 
+def resize_scale(height, width, target_size, max_size):
+    """im_scale of lib/utils/image.py:204-210: the short side to target_size unless that pushes the long side past max_size."""
+    im_size_min, im_size_max = min(height, width), max(height, width)
+    im_scale = float(target_size) / float(im_size_min)
+    if np.round(im_scale * im_size_max) > max_size:
+        im_scale = float(max_size) / float(im_size_max)
+    return im_scale
+
+
+def resize(frame_bgr_u8, target_size, max_size, stride=0):
+    """lib/utils/image.py:194-222 `resize` on the device: (H,W,3) uint8 BGR CUDA tensor -> (resized tensor, im_scale);
+    cv2.INTER_LINEAR bit for bit (accel_resize_bgr); stride > 0 pads bottom / right with zeros to a multiple of it."""
+    lib = _lib.load()
+    if not (frame_bgr_u8.is_cuda and frame_bgr_u8.dtype == torch.uint8 and frame_bgr_u8.is_contiguous()
+            and frame_bgr_u8.dim() == 3 and frame_bgr_u8.shape[2] == 3):
+        raise TypeError("frame must be a contiguous CUDA uint8 tensor of shape (H, W, 3)")
+    h, w = int(frame_bgr_u8.shape[0]), int(frame_bgr_u8.shape[1])
+    im_scale = resize_scale(h, w, target_size, max_size)
+    dh, dw = C.c_int(), C.c_int()
+    if lib.accel_resize_size(h, w, im_scale, im_scale, C.byref(dh), C.byref(dw)) != 0:
+        raise RuntimeError("accel_resize_size failed")
+    out = torch.empty(dh.value, dw.value, 3, dtype=torch.uint8, device=frame_bgr_u8.device)
+    st = C.c_void_p(torch.cuda.current_stream(frame_bgr_u8.device).cuda_stream)
+    with torch.cuda.device(frame_bgr_u8.device):
+        rc = lib.accel_resize_bgr(_ptr(frame_bgr_u8), h, w, im_scale, im_scale, _ptr(out), st)
+    if rc != 0:
+        raise RuntimeError("accel_resize_bgr failed (%d)" % rc)
+    if stride:
+        ph = int(np.ceil(out.shape[0] / float(stride)) * stride)
+        pw = int(np.ceil(out.shape[1] / float(stride)) * stride)
+        padded = torch.zeros(ph, pw, 3, dtype=torch.uint8, device=out.device)
+        padded[:out.shape[0], :out.shape[1]] = out
+        out = padded
+    return out, im_scale
+
+
 def confusion(pred, label, hist=None, num_classes=NUM_CLASSES):
     """fast_hist(pred, label, n) of dff_deeplab/demo.py:50-53, accumulated into `hist` (n x n int64, CUDA)."""
     lib = _lib.load()

@@ -131,24 +131,25 @@ class TestLoader:
         im = torch.as_tensor(np.ascontiguousarray(im)) if not isinstance(im, torch.Tensor) else im
         if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3:
             raise ValueError("frames must be (H,W,3) uint8 BGR")
-        target, max_size = self.cfg.SCALES[0]
-        if min(im.shape[0], im.shape[1]) != target or max(im.shape[0], im.shape[1]) > max_size:
-            raise ValueError("frame size %s does not match SCALES %s: resizing (cv2.INTER_LINEAR, image.py:194-213) is not "
-                             "part of this path; decode at the configured scale" % (tuple(im.shape[:2]), (target, max_size)))
         return im
 
     def _ingest(self, rec, frameid):
-        """get_rpn_testbatch -> get_image -> transform (lib/utils/image.py:224-235) for one frame: the uint8 BGR
-        image goes to the device and `accel_preprocess` builds the fp32 `data` tensor there (no CPU path)."""
+        """get_rpn_testbatch -> get_image -> resize + transform (lib/utils/image.py:194-235) for one frame: the uint8
+        BGR image goes to the device, frames that do not arrive at config.SCALES are resized there (accel_resize_bgr:
+        cv2.INTER_LINEAR bit for bit) and `accel_preprocess` builds the fp32 `data` tensor (no CPU path)."""
         from . import engine as E
-        im = self._frame_u8(rec, frameid).to(self.device, non_blocking=True)
+        im = self._frame_u8(rec, frameid).to(self.device, non_blocking=True).contiguous()
+        target, max_size = self.cfg.SCALES[0]
+        self.im_scale = 1.0
+        if min(im.shape[0], im.shape[1]) != target or max(im.shape[0], im.shape[1]) > max_size:
+            im, self.im_scale = E.resize(im, target, max_size, stride=int(getattr(self.cfg.network, "IMAGE_STRIDE", 0) or 0))
         return E.preprocess(im.contiguous(), None, tuple(float(m) for m in self.cfg.network.PIXEL_MEANS))
 
     def get_batch(self):                                              # loader.py:278-303
         rec = self.roidb[self.cur_roidb_index]
         self.cur_seg_len = rec["frame_seg_len"]
         data = self._ingest(rec, self.cur_frameid)
-        im_info = torch.tensor([[data.shape[2], data.shape[3], 1.0]], dtype=torch.float32)
+        im_info = torch.tensor([[data.shape[2], data.shape[3], self.im_scale]], dtype=torch.float32)
         if self.key_frameid == self.cur_frameid:                      # key frame
             self.data_key = data.clone()
             self.key_frame_flag = 0 if self.key_frameid == 0 else 1

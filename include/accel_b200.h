@@ -155,6 +155,13 @@ int accel_fuse_argmax(const float* score_a, const float* score_b, const float* c
 int accel_preprocess(const uint8_t* bgr_hwc, int height, int width, const double pixel_means_bgr[3], float* out,
                      void* stream);
 
+/* cv2.resize(im, None, None, fx=im_scale, fy=im_scale, interpolation=cv2.INTER_LINEAR) of lib/utils/image.py:211 (the
+ * `resize()` every decoded frame goes through, demo.py:173), on the device, bit for bit (OpenCV's fixed-point separable
+ * bilinear; an exact 2x decimation is the rounded 2x2 mean, as in OpenCV).  src/dst: (H,W,3) uint8 BGR in DEVICE memory;
+ * accel_resize_size gives the destination size (round-half-even of size * scale, as OpenCV). */
+int accel_resize_size(int src_height, int src_width, double fx, double fy, int* dst_height, int* dst_width);
+int accel_resize_bgr(const uint8_t* src_hwc, int src_height, int src_width, double fx, double fy, uint8_t* dst_hwc, void* stream);
+
 /* fast_hist(pred, label, n) of dff_deeplab/demo.py:50-53 on the device: for every pixel with label < n,
  * hist[label * n + pred] += 1.  pred/label: `count` uint8 values (label 255 = ignore); hist: n*n int64 in
  * DEVICE memory, ACCUMULATED into (`hist += curr_hist`, demo.py:272) -- zero it before the first frame. */

@@ -125,3 +125,44 @@ def test_key_lookahead_equals_sequential_loop(schedule, interval):
         assert np.array_equal(lab.cpu().numpy(), ref_labels[i]), "frame %d" % i
         assert np.array_equal(st.feat_in.cpu().numpy(), ref_feats[i]), "frame %d" % i
     eng.close()
+
+
+# ----------------------------------------------------------------------------- cv2.resize ingest (lib/utils/image.py:194-222)
+def _resize_cases():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_vectors.npz"))
+    return [(g["src_%d" % i], float(g["fx_%d" % i]), g["dst_%d" % i]) for i in range(int(g["n"]))]
+
+
+def test_resize_matches_cv2_golden_vectors():
+    """accel_resize_bgr against outputs of the real cv2.resize(INTER_LINEAR) (tests/golden/make_resize_vectors.py)."""
+    from accel_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    for src, fx, dst in _resize_cases():
+        s = torch.from_numpy(src).cuda().contiguous()
+        dh, dw = C.c_int(), C.c_int()
+        assert lib.accel_resize_size(src.shape[0], src.shape[1], fx, fx, C.byref(dh), C.byref(dw)) == 0
+        assert (dh.value, dw.value) == dst.shape[:2], (src.shape, fx)
+        out = torch.empty(dh.value, dw.value, 3, dtype=torch.uint8, device="cuda")
+        assert lib.accel_resize_bgr(C.c_void_p(s.data_ptr()), src.shape[0], src.shape[1], fx, fx, C.c_void_p(out.data_ptr()), None) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), dst), (src.shape, fx)
+
+
+def test_resize_full_size_against_live_cv2_and_reference_scale_rule():
+    """Frame-sized inputs through engine.resize (the reference's scale rule, image.py:204-210) against cv2 itself where
+    it is installed: a 2048x4096 frame to 1024x2048 (exact 2x: OpenCV's INTER_AREA path), 1080x1920 (short side to
+    1024), 600x800 (long side capped)."""
+    cv2 = pytest.importorskip("cv2")
+    from accel_b200 import engine as E
+    rng = np.random.default_rng(5)
+    for (h, w), (target, max_size) in (((2048, 4096), (1024, 2048)), ((1080, 1920), (1024, 2048)), ((600, 800), (1024, 1280))):
+        im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        out, scale = E.resize(torch.from_numpy(im).cuda(), target, max_size)
+        ref_scale = E.resize_scale(h, w, target, max_size)
+        ref = cv2.resize(im, None, None, fx=ref_scale, fy=ref_scale, interpolation=cv2.INTER_LINEAR)
+        assert scale == ref_scale and tuple(out.shape) == ref.shape
+        assert np.array_equal(out.cpu().numpy(), ref), (h, w)
+    out, _ = E.resize(torch.from_numpy(im).cuda(), 1024, 1280, stride=32)          # IMAGE_STRIDE padding, image.py:215-222
+    assert out.shape[0] % 32 == 0 and out.shape[1] % 32 == 0 and int(out[ref.shape[0]:].sum()) == 0

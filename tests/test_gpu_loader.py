@@ -74,11 +74,28 @@ def test_loader_flags_and_pred_eval(tmp_path):
     assert np.array_equal(merged["hist"], want_hist) and merged["mIoU"] == oio.mean_iou(want_hist)
 
 
-def test_loader_rejects_wrong_scale():
+@pytest.mark.parametrize("factor", [2.0, 1.5])
+def test_loader_resizes_frames_like_the_reference(factor):
+    """Frames that do not arrive at config.SCALES go through `resize` (lib/utils/image.py:194-213: short side to the
+    target, cv2.INTER_LINEAR) before `transform`, on the device: TestLoader's `data` must equal transform(cv2.resize(frame))
+    bit for bit and im_info must carry the scale (get_image, image.py:40-44)."""
+    cv2 = pytest.importorskip("cv2")
     cfg = loader.default_config(key_frame_interval=2, scales=(H, W))
-    bad = [{"pattern": None, "frames": torch.zeros(2, 64, 64, 3, dtype=torch.uint8), "frame_seg_len": 2, "frame_id": 0}]
-    with pytest.raises(ValueError):
-        loader.TestLoader(bad, cfg, device="cuda:0")
+    hs, ws = int(H * factor), int(W * factor)
+    g = torch.Generator().manual_seed(9)
+    frames = torch.randint(0, 256, (2, hs, ws, 3), generator=g, dtype=torch.uint8)
+    roidb = [{"pattern": None, "frames": frames, "frame_seg_len": 2, "frame_id": 0}]
+    data = loader.TestLoader(roidb, cfg, device="cuda:0")
+    scale = float(H) / float(hs)
+    seen = 0
+    for t, (im_info, flag, batch) in enumerate(data):
+        ref_im = cv2.resize(frames[t].numpy(), None, None, fx=scale, fy=scale, interpolation=cv2.INTER_LINEAR)
+        want = oio.transform(ref_im, synthetic.PIXEL_MEANS_BGR)
+        got = batch.data[0][0]
+        assert tuple(got.shape) == (1, 3, H, W) and np.array_equal(got.cpu().numpy(), want)
+        assert abs(float(im_info[0][0, 2]) - scale) < 1e-7
+        seen += 1
+    assert seen == 2
 
 
 def test_pred_eval_multiprocess_two_gpus(tmp_path):

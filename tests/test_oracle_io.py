@@ -70,3 +70,16 @@ def test_torch_confusion_helper_matches_fast_hist():
     label[::7] = 255
     got = scheduler.confusion_matrix(pred, label, 19).numpy()
     assert np.array_equal(got, oio.fast_hist(pred.numpy().flatten(), label.numpy().flatten(), 19))
+
+
+def test_resize_golden_vectors_are_what_cv2_produces():
+    """tests/golden/resize_vectors.npz must stay what the installed cv2 computes (the GPU test compares against the file)."""
+    import os
+
+    import numpy as np
+    import pytest
+    cv2 = pytest.importorskip("cv2")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_vectors.npz"))
+    for i in range(int(g["n"])):
+        fx = float(g["fx_%d" % i])
+        assert np.array_equal(cv2.resize(g["src_%d" % i], None, None, fx=fx, fy=fx, interpolation=cv2.INTER_LINEAR), g["dst_%d" % i])

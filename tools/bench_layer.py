@@ -32,6 +32,9 @@ LAYERS = {
     "flow_conv3_1": (256, 256, 128, 256, 3, 1, 1, 1, False),
     "flow_conv3": (128, 256, 128, 256, 5, 2, 2, 1, False),
     # the same layers over 5 frames stacked along H: what batching an interval's frames through one launch would give
+    "res2_2c_x5": (64, 256, 1280, 512, 1, 1, 0, 1, True),
+    "res2_br1_x5": (64, 256, 1280, 512, 1, 1, 0, 1, False),
+    "res3_2c_x5": (128, 512, 640, 256, 1, 1, 0, 1, True),
     "res2_2a_x5": (256, 64, 1280, 512, 1, 1, 0, 1, False),
     "res2_2a": (256, 64, 256, 512, 1, 1, 0, 1, False),
     "res3_2a_x5": (512, 128, 640, 256, 1, 1, 0, 1, False),
@@ -72,6 +75,7 @@ PAIR_SWEEP = [
 ]
 
 ONE = [{}]
+EPI_SWEEP = [{}, {"ACCEL_TC_TMA_OUT": "0"}, {"ACCEL_TC_BN": "256"}, {"ACCEL_TC_BN": "256", "ACCEL_TC_TMA_OUT": "0"}, {"ACCEL_TC_BN": "64"}]
 
 R02_SWEEP = [
     {"ACCEL_TC_ASLAB": "0"},
@@ -114,7 +118,7 @@ def main():
         ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
         wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
         r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
-        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE}.get(a.sweep, SWEEP):
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP}.get(a.sweep, SWEEP):
             for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR", "ACCEL_TC_ASLAB",
                        "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO"):
                 os.environ.pop(kk, None)
