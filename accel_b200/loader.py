@@ -149,7 +149,7 @@ class TestLoader:
         rec = self.roidb[self.cur_roidb_index]
         self.cur_seg_len = rec["frame_seg_len"]
         data = self._ingest(rec, self.cur_frameid)
-        im_info = torch.tensor([[data.shape[2], data.shape[3], self.im_scale]], dtype=torch.float32)
+        im_info = torch.tensor([[data.shape[2], data.shape[3], getattr(self, "im_scale", 1.0)]], dtype=torch.float32)
         if self.key_frameid == self.cur_frameid:                      # key frame
             self.data_key = data.clone()
             self.key_frame_flag = 0 if self.key_frameid == 0 else 1
