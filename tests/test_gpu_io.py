@@ -127,6 +127,37 @@ def test_key_lookahead_equals_sequential_loop(schedule, interval):
     eng.close()
 
 
+@pytest.mark.parametrize("version", ["dff", "101"])
+def test_video_pipeline_whole_intervals(version):
+    """VideoPipeline.submit_interval (host uint8 frames of a whole key interval in, host label maps out, two buffer sets in
+    flight) == accel_interval_forward on resident fp32 frames, label for label, over several intervals."""
+    from accel_b200.engine import Engine
+    H, W, I, N = 128, 256, 3, 4
+    eng = Engine(version, H, W, params=synthetic.make_params(version), interval=I)
+    dev = eng.torch_device
+    frames_u8 = synthetic.make_frames_u8(N * I, H, W, stream=6)
+    host = [f.contiguous().pin_memory() for f in frames_u8]
+    out = [torch.empty(H, W, dtype=torch.uint8).pin_memory() for _ in range(N * I)]
+    pipe = scheduler.VideoPipeline(eng, I, "chained", batched=True)
+    evs = []
+    for k in range(N):
+        evs += pipe.submit_interval(host[k * I:(k + 1) * I], out[k * I:(k + 1) * I])
+    pipe.sync()
+    assert all(e.query() for e in evs)
+    st = scheduler.StreamState(eng)
+    labels = torch.empty(I, H, W, dtype=torch.uint8, device=dev)
+    for k in range(N):
+        fr = [synthetic.transform(f).to(dev) for f in frames_u8[k * I:(k + 1) * I]]
+        scheduler.segment_interval(eng, st, fr, labels)
+        for t in range(I):
+            assert np.array_equal(out[k * I + t].numpy(), labels[t].cpu().numpy()), "interval %d frame %d" % (k, t)
+    with pytest.raises(ValueError):
+        pipe.submit_interval(host[:2], out[:2])
+    with pytest.raises(ValueError):
+        scheduler.VideoPipeline(eng, I + 1, "chained", batched=True)
+    eng.close()
+
+
 # ----------------------------------------------------------------------------- cv2.resize ingest (lib/utils/image.py:194-222)
 def _resize_cases():
     import os
