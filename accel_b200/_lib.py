@@ -14,7 +14,7 @@ SYMBOLS = (
     "accel_set_param", "accel_finalize", "accel_key_forward", "accel_cur_forward", "accel_key_forward_lin",
     "accel_cur_forward_lin", "accel_flownet", "accel_rbranch_forward", "accel_plan_interval", "accel_interval_forward",
     "accel_graph_cache_stats", "accel_debug_fetch",
-    "accel_warp", "accel_fuse_argmax", "accel_preprocess", "accel_resize_size", "accel_resize_bgr", "accel_confusion", "accel_conv_layer", "accel_head", "accel_last_launch_count",
+    "accel_warp", "accel_warp_split", "accel_fuse_argmax", "accel_preprocess", "accel_resize_size", "accel_resize_bgr", "accel_confusion", "accel_conv_layer", "accel_head", "accel_last_launch_count",
     "accel_set_profiling", "accel_stage_times", "accel_op_times",
 )
 
@@ -61,6 +61,7 @@ def load():
     lib.accel_debug_fetch.argtypes = [vp, cp, cp, vp, C.POINTER(C.c_int64), vp]
     lib.accel_graph_cache_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.accel_warp.argtypes = [vp, vp, vp, ip, ip, ip, vp]
+    lib.accel_warp_split.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, vp]
     lib.accel_fuse_argmax.argtypes = [vp, vp, vp, vp, ip, ip, ip, u8p, vp, vp]
     lib.accel_preprocess.argtypes = [u8p, ip, ip, C.POINTER(C.c_double), vp, vp]
     lib.accel_resize_size.argtypes = [ip, ip, C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]

@@ -317,6 +317,17 @@ extern "C" int accel_warp(const float* feat, const float* flow, float* out, int 
   return launch_warp(P, (cudaStream_t)stream) == cudaSuccess ? 0 : 5;
 }
 
+extern "C" int accel_warp_split(const float* feat, const float* flow, float* out, void* out_hi, void* out_lo, int channels,
+                                int height, int width, void* stream) {
+  if (!feat || !flow || !out || !out_hi || !out_lo || channels <= 0 || height <= 0 || width <= 0 || feat == out) return 1;
+  if ((channels % 32) || ((uintptr_t)out_hi & 15) || ((uintptr_t)out_lo & 15)) return 1;
+  if (no_device(nullptr, 0)) return 6;
+  WarpParams P{};
+  P.feat = feat; P.flow = flow; P.C = channels; P.H = height; P.W = width; P.out_nchw = out;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.out_ld = channels;
+  return launch_warp(P, (cudaStream_t)stream) == cudaSuccess ? 0 : 5;
+}
+
 extern "C" int accel_fuse_argmax(const float* score_a, const float* score_b, const float* corr_weight,
                                  const float* corr_bias, int num_classes, int h, int w, uint8_t* label,
                                  float* score_full, void* stream) {

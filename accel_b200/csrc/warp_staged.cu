@@ -14,6 +14,8 @@
 // the result is bit-identical.  When the band does not fit (wild flow fields), the CTA gathers from global memory.
 #include <string.h>
 
+#include <algorithm>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -246,9 +248,12 @@ struct alignas(64) WarpFusedParams {
   const float* bias;
   int act, has_split;
   int C, H, W, TH, RMAX;
+  int ring_floats, max_stages;               // ring capacity; the CTA cuts it into min(max_stages, capacity / band) stages
 };
 
-// WF_CONS = consumer threads = pixels per CTA tile (the producer warp comes on top); WF_STAGES = ring depth
+// WF_CONS = consumer threads = pixels per CTA tile (the producer warp comes on top); WF_STAGES = deepest ring (mbarrier pairs):
+// the ring is cut into stages of the band the CTA's flow vectors actually span (R rows, known after the tap set-up), not of
+// the worst case RMAX, so that a smooth field keeps twice the bytes in flight
 template <int WF_CONS, int WF_STAGES>
 __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_constant__ WarpFusedParams P) {
   extern __shared__ __align__(1024) uint8_t wf_smem[];          // [staging hi 16 KB | lo 16 KB][ring]
@@ -316,10 +321,11 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
   ymin = H; ymax = -1;
 #pragma unroll
   for (int i = 0; i < WF_CONS / 32; ++i) { ymin = min(ymin, s_min[i]); ymax = max(ymax, s_max[i]); }
-  const int r0 = ymin, R = ymax - ymin + 1;
+  const int r0 = ymin, R = max(ymax - ymin + 1, 1);
   const bool staged = R <= P.RMAX;
   const int ngroups = C / WF_G;
-  const int slot = P.RMAX * W;                                  // floats per channel slot of the ring
+  const int slot = R * W;                                       // floats per channel slot of the ring
+  const int nst = staged ? min(min(WF_STAGES, P.max_stages), P.ring_floats / (WF_CB * slot)) : 1;
   const uint32_t band_bytes = (uint32_t)(R * W) * 4u;
 
   if (producer) {
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
 #pragma unroll
           for (int c = 0; c < WF_CB; ++c)
             bulk_load(ring0 + (uint32_t)((s * WF_CB + c) * slot) * 4u, P.feat + (size_t)(c0 + c) * npix + (size_t)r0 * W, band_bytes, fb);
-          if (++s == WF_STAGES) { s = 0; ph ^= 1; }
+          if (++s == nst) { s = 0; ph ^= 1; }
         }
     }
     return;
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * s);
-        if (++s == WF_STAGES) { s = 0; ph ^= 1; }
+        if (++s == nst) { s = 0; ph ^= 1; }
       } else {
         const float* sp0 = P.feat + (size_t)c0 * npix + t.o00;
 #pragma unroll
@@ -447,9 +453,13 @@ static cudaError_t launch_fused_variant(const WarpParams& P, int once_slot, cuda
   F.TH = CONS / P.W;
   if (F.TH > P.H) F.TH = P.H;
   F.has_split = P.out_hi ? 1 : 0;
-  // two CTAs per SM: staging (CONS x 64 B x 2 planes) + ring STAGES x WF_CB x RMAX x W floats
-  const int budget = max_smem / 2 - 4096 - 2 * CONS * 64;
-  int rmax = budget / (STAGES * WF_CB * P.W * 4);
+  // `per_sm` CTAs per SM: staging (CONS x 64 B x 2 planes) + the ring; a band may take up to half the ring (two stages)
+  const int per_sm = std::min(std::max(env_int("ACCEL_WARP_FUSED_PER_SM", 2), 1), 4);
+  const int budget = max_smem / per_sm - 4096 - 2 * CONS * 64;
+  if (budget < 2 * WF_CB * P.W * 4 * (F.TH + 2)) return cudaErrorNotSupported;
+  F.ring_floats = budget / 4;
+  F.max_stages = std::min(std::max(env_int("ACCEL_WARP_FUSED_NST", STAGES), 2), STAGES);
+  int rmax = F.ring_floats / (2 * WF_CB * P.W);
   const int cap = env_int("ACCEL_WARP_RMAX", 0);
   if (cap > 0 && rmax > cap) rmax = cap;
   if (rmax > P.H) rmax = P.H;
@@ -465,10 +475,10 @@ static cudaError_t launch_fused_variant(const WarpParams& P, int once_slot, cuda
         !encode(&F.o_lo, P.out_lo, 3, dims, str, box, err, sizeof(err), CU_TENSOR_MAP_SWIZZLE_64B))
       return cudaErrorInvalidValue;
   }
-  const size_t smem = 1024 + 2 * (size_t)CONS * 64 + (size_t)STAGES * WF_CB * rmax * P.W * 4;
+  const size_t smem = 1024 + 2 * (size_t)CONS * 64 + (size_t)F.ring_floats * 4;
   const int bx = (P.H + F.TH - 1) / F.TH;
   const int ngroups = P.C / WF_G;
-  int by = (sms * 2) / bx;
+  int by = (sms * per_sm) / bx;
   if (by < 1) by = 1;
   if (by > ngroups) by = ngroups;
   const int per = (ngroups + by - 1) / by;                       // equal number of groups per CTA: no straggler wave
@@ -477,8 +487,8 @@ static cudaError_t launch_fused_variant(const WarpParams& P, int once_slot, cuda
 }
 
 cudaError_t launch_warp_fused(const WarpParams& P, cudaStream_t stream) {
-  if (wf_cons() == 512) return launch_fused_variant<512, 3>(P, ONCE_WARP_FUSED_1, stream);
-  return launch_fused_variant<256, 4>(P, ONCE_WARP_FUSED, stream);
+  if (wf_cons() == 512) return launch_fused_variant<512, 16>(P, ONCE_WARP_FUSED_1, stream);
+  return launch_fused_variant<256, 16>(P, ONCE_WARP_FUSED, stream);
 }
 
 template <int THREADS, int PPT, int CB>

@@ -302,6 +302,27 @@ def warp(feat, flow, out=None):
     return out
 
 
+def warp_split(feat, flow, out=None, out_hi=None, out_lo=None):
+    """The warp plus the split-fp16 NHWC operand of the head's first conv (accel_18.py:174-183), one pass over `feat`:
+    returns (out fp32 (1,C,H,W), hi fp16 (H,W,C), lo fp16 (H,W,C)) with hi + lo == out to fp32 precision."""
+    lib = _lib.load()
+    n, c, h, w = feat.shape
+    assert n == 1 and tuple(flow.shape) == (1, 2, h, w) and c % 32 == 0
+    if out is None:
+        out = torch.empty_like(feat)
+    if out_hi is None:
+        out_hi = torch.empty(h, w, c, dtype=torch.float16, device=feat.device)
+    if out_lo is None:
+        out_lo = torch.empty(h, w, c, dtype=torch.float16, device=feat.device)
+    st = C.c_void_p(torch.cuda.current_stream(feat.device).cuda_stream)
+    with torch.cuda.device(feat.device):
+        rc = lib.accel_warp_split(_ptr(feat.contiguous()), _ptr(flow.contiguous()), _ptr(out), _ptr(out_hi), _ptr(out_lo),
+                                  c, h, w, st)
+    if rc != 0:
+        raise RuntimeError("accel_warp_split failed (%d)" % rc)
+    return out, out_hi, out_lo
+
+
 def fuse_argmax(score_a, score_b=None, corr_weight=None, corr_bias=None, want_scores=False):
     """x16 upsampling + Crop(8,8) of the low-res score map(s), 1x1 `correction` fusion, argmax."""
     lib = _lib.load()

@@ -138,6 +138,13 @@ int accel_flownet(AccelHandle* h, const float* data, const float* data_key, floa
 int accel_warp(const float* feat, const float* flow, float* out, int channels, int height, int width,
                void* stream);
 
+/* The same warp, also emitting the operand the first conv of the fusion head reads (accel_18.py:176-183: the warped
+ * feature goes straight into `fc6`): the split-fp16 NHWC copy, out_hi[y][x][c] = fp16(v), out_lo[y][x][c] =
+ * fp16(v - out_hi), both (H,W,C) __half, 16-byte aligned, C a multiple of 32.  One pass over `feat`
+ * (warp_kernel_fused) where the shape allows, else the warp followed by a layout pass.  `out` (fp32 NCHW) is required. */
+int accel_warp_split(const float* feat, const float* flow, float* out, void* out_hi, void* out_lo, int channels,
+                     int height, int width, void* stream);
+
 /* Concat(dim=1) -> correction 1x1 (2K -> K, +bias) on the x16-upsampled, cropped score maps, then
  * argmax (accel_18.py:193-197,223-235; demo.py:245).  score_a/score_b: low-res (1,K,h,w) outputs of
  * the `score` / `<v>_score` convs; corr_weight (K,2K) and corr_bias (K) are DEVICE pointers, NULL

@@ -52,6 +52,42 @@ def test_warp_mixed_band_heights():
     assert torch.equal(out, ref)
 
 
+def _split_ref(ref):
+    """hi = rn16(v), lo = rn16(v - hi) of an fp32 NCHW tensor, as (H,W,C) planes (split_pair, common.cuh)."""
+    hi = ref[0].permute(1, 2, 0).contiguous().to(torch.float16)
+    lo = (ref[0].permute(1, 2, 0) - hi.float()).to(torch.float16)
+    return hi, lo
+
+
+@pytest.mark.parametrize("c,h,w,kind", [(2048, 64, 128, "smooth"), (64, 64, 128, "wild"), (96, 32, 64, "mixed"), (32, 8, 16, "smooth"),
+                                        (64, 13, 36, "smooth"), (2048, 64, 128, "noisy")])
+@pytest.mark.parametrize("per_sm", ["2", "3"])
+def test_warp_split_both_outputs_bit_exact(c, h, w, kind, per_sm, monkeypatch):
+    """accel_warp_split: the fp32 NCHW warp equals the oracle bit for bit and the split-fp16 NHWC head operand equals the
+    split of that result, for fields the ring holds (smooth), fields it does not (wild: gather CTAs), both in one launch,
+    and a shape the fused kernel declines (13x36: warp + layout pass)."""
+    monkeypatch.setenv("ACCEL_WARP_FUSED_PER_SM", per_sm)
+    feat = _rand(1, c, h, w, seed=11)
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    smooth = torch.stack([3.0 * torch.sin(yy / 9.0) + 0.01 * xx - 2.0, 2.0 * torch.cos(xx / 13.0 + yy / 7.0)])[None]
+    if kind == "smooth":
+        flow = smooth + _rand(1, 2, h, w, seed=12, scale=0.05)
+    elif kind == "noisy":
+        flow = smooth + _rand(1, 2, h, w, seed=12, scale=0.6)
+    elif kind == "wild":
+        flow = _rand(1, 2, h, w, seed=12, scale=25.0)
+    else:
+        flow = smooth.clone()
+        flow[:, :, h // 2:] = _rand(1, 2, h - h // 2, w, seed=13, scale=25.0)
+    flow = flow.contiguous()
+    ref = ops.bilinear_sampler(feat, ops.grid_generator_warp(flow))
+    out, hi, lo = E.warp_split(feat.to(DEV), flow.to(DEV))
+    assert torch.equal(out.cpu(), ref)
+    rhi, rlo = _split_ref(ref)
+    assert torch.equal(hi.cpu(), rhi)
+    assert torch.equal(lo.cpu(), rlo)
+
+
 @pytest.mark.parametrize("gather", ["0", "1"])
 def test_warp_out_of_range_taps_are_skipped_by_value(gather, monkeypatch):
     """MXNet's BilinearSampler skips out-of-range taps; a zero WEIGHT on a clamped neighbour is not the same thing when
