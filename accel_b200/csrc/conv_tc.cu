@@ -58,7 +58,8 @@ struct alignas(64) TcParams {
   int pair;        // 1: conv_tc2_kernel (cta_group::2 pairs)
   int ncat;        // 1: hi*hi and hi*lo issued as ONE MMA over [B_hi ; B_lo] (N = 2*BN, two accumulator halves summed in the epilogue)
   int tma_out;     // 1: the main output leaves through shared memory + TMA tensor stores (3-D map), 2: 5-D map (transposed-conv phase)
-  int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = no TMA stores
+  int res_prefetch;  // TMA epilogue: the residual tile of the NEXT item is prefetched into L2 while this item is processed
+  int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = direct epilogue; TMA epilogue: 16 = no residual loads, 32 = no tensor stores, 64 = no tcgen05.ld, 128 = no MMAs, 256 / 512 / 1024 = no operand / A / B loads
   int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
   // A-slab reuse (stride-1 multi-tap layers whose tile is one full 128-pixel row segment): the taps of one filter row
   // (same dy, dx = dxmin .. dxmax) read the SAME source pixels shifted by whole pixels, so ONE TMA box of
@@ -196,10 +197,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int t = it / P.chunks, kc = it - t * P.chunks;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t fb = full0 + 8 * s;
-          mbar_arrive_expect_tx(fb, stage_bytes);
+          const bool ldA = !(P.debug & (256 | 512)), ldB = !(P.debug & (256 | 1024));   // timing decomposition only
+          mbar_arrive_expect_tx(fb, (ldA ? 2 * a_bytes : 0u) + (ldB ? 2 * b_bytes : 0u));
           const uint32_t sa = smem0 + s * stage_bytes;
           const int dy = P.dy[t], dx = P.dx[t];
-          if (P.stride2) {
+          if (!ldA) {
+          } else if (P.stride2) {
             tma_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
             tma_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
           } else {
@@ -207,8 +210,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_load_4d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, yl + dy, fr);
           }
           const int kcol = t * P.Cin_pad + kc * BK;
-          tma_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nt * P.BN);
-          tma_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nt * P.BN);
+          if (ldB) {
+            tma_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nt * P.BN);
+            tma_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nt * P.BN);
+          }
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             // magnitude per accumulator); the epilogue adds the buffers in fp32
             const uint32_t d = tmem_base + (uint32_t)((two ? (q & 1) : acc) * acc_cols);
             const uint32_t first = (q >= (two ? 2 : 1)) ? 1u : 0u;
+            if (P.debug & 128) continue;
             if (NCAT) {
               // B_hi and B_lo are adjacent in the stage with one row pitch: a single N = 2*BN operand.  Columns
               // [0, BN) collect hi*hi, columns [BN, 2BN) collect hi*lo and -- issued into the upper half alone --
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int by = r / P.BW, bx = r - by * P.BW;
       const int et = threadIdx.x - 64;
       const Epilogue& E = P.epi;
-      const bool has_res = E.res_hi != nullptr;
+      const bool has_res = E.res_hi != nullptr && !(P.debug & 16);
       const bool leader = quarter == 0 && lane == 0;
       const uint32_t sb0 = stg0 + (uint32_t)cset * 2u * 16384u;
       const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]);
@@ -325,8 +331,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
       int acc = 0, sci = 0, n = 0;                          // sci: scale/shift staging slot, alternates per item
       uint32_t accph = 0;
+      // The staging buffers keep ONE residual chunk in flight per chunk set: fetched from HBM, every chunk would cost a full
+      // DRAM round trip (res4 expand: 3.4 us per chunk against a 3.5 us mainloop per tile).  The leader therefore pulls the
+      // residual boxes of the next item into L2 a whole tile ahead; the staging loads then pay an L2 hit.
+      auto prefetch_res = [&](int item2) {
+        const int tile2 = item2 / P.splits, nt2 = tile2 % P.n_tiles, mt2 = tile2 / P.n_tiles;
+        const int x02 = (mt2 % P.tiles_x) * P.BW, y02 = (mt2 / P.tiles_x) * P.BH;
+        for (int cc2 = cset * 32; cc2 < P.BN; cc2 += 64) {
+          tma_prefetch_3d(&P.r_hi, nt2 * P.BN + cc2, x02, y02);
+          tma_prefetch_3d(&P.r_lo, nt2 * P.BN + cc2, x02, y02);
+        }
+      };
+      const bool pf = leader && has_res && P.res_prefetch;
+      if (pf && (int)blockIdx.x < items) prefetch_res(blockIdx.x);
       if (leader && has_res && (int)blockIdx.x < items) issue_res(blockIdx.x, cset * 32, 0);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        if (pf && item + (int)gridDim.x < items) prefetch_res(item + gridDim.x);
         const int tile = item / P.splits;
         const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
         const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
@@ -360,6 +380,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
           }
           float v[32];
+          if (P.debug & 64) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          } else {
           tmem_ld32(taddr + cc, v);
           if (two) {                                         // second chain's big half first: big + big, then the small halves
             float v2[32];
@@ -378,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          }
           }
           ResChunk rc{};
           if (has_res) {
@@ -399,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           stage_row64(sb + 8192u, r, wl);
           fence_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(2 + cset) : "memory");
-          if (leader) {
+          if (leader && !(P.debug & 32)) {
             if (P.tma_out == 2) {
               tma_store_5d(&P.o_hi, sb, nbase + cc, E.oox, x0, E.ooy, y0);
               tma_store_5d(&P.o_lo, sb + 8192u, nbase + cc, E.oox, x0, E.ooy, y0);
@@ -1036,6 +1061,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     P.vec32 = v ? 1 : 0;
     P.krot = P.aslab ? 0 : env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
     P.debug = env_int("ACCEL_TC_DEBUG", 0);
+    P.res_prefetch = env_int("ACCEL_TC_RES_PREFETCH", 0);
   }
 
   // tensor maps ------------------------------------------------------------------------------------

@@ -248,6 +248,7 @@ struct alignas(64) WarpFusedParams {
   const float* bias;
   int act, has_split;
   int C, H, W, TH, RMAX;
+  int debug;                                 // ACCEL_WARP_FUSED_DEBUG (timing decomposition only): 1 no NCHW stores, 2 no TMA stores
   int ring_floats, max_stages;               // ring capacity; the CTA cuts it into min(max_stages, capacity / band) stages
 };
 
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
           v[ch] = __fadd_rn(x, __fmul_rn(d, t.w11));
         }
       }
-      if (live && P.out_nchw) {
+      if (live && P.out_nchw && !(P.debug & 1)) {
         float* po = P.out_nchw + (size_t)c0 * npix + (size_t)y0 * W + tid;
 #pragma unroll
         for (int ch = 0; ch < WF_CB; ++ch) po[(size_t)ch * npix] = v[ch];
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
       stage_row64(stg_lo, tid, wl);
       fence_async_smem();
       asm volatile("bar.sync 1, %0;" ::"n"(WF_CONS) : "memory");
-      if (tid == 0) {
+      if (tid == 0 && !(P.debug & 2)) {
         tma_store_3d(&P.o_hi, stg_hi, g * WF_G, 0, y0);       // rows past the last image row are clipped by the map
         tma_store_3d(&P.o_lo, stg_lo, g * WF_G, 0, y0);
         bulk_commit();
@@ -458,6 +459,7 @@ static cudaError_t launch_fused_variant(const WarpParams& P, int once_slot, cuda
   const int budget = max_smem / per_sm - 4096 - 2 * CONS * 64;
   if (budget < 2 * WF_CB * P.W * 4 * (F.TH + 2)) return cudaErrorNotSupported;
   F.ring_floats = budget / 4;
+  F.debug = env_int("ACCEL_WARP_FUSED_DEBUG", 0);
   F.max_stages = std::min(std::max(env_int("ACCEL_WARP_FUSED_NST", STAGES), 2), STAGES);
   int rmax = F.ring_floats / (2 * WF_CB * P.W);
   const int cap = env_int("ACCEL_WARP_RMAX", 0);

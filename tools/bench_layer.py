@@ -43,6 +43,7 @@ LAYERS = {
     "res4_2a_x5": (1024, 256, 320, 128, 1, 1, 0, 1, False),
     "res4_2b_x5": (256, 256, 320, 128, 3, 1, 1, 1, False),
     "res4_2c_x5": (256, 1024, 320, 128, 1, 1, 0, 1, True),
+    "res5_br1_x5": (1024, 2048, 320, 128, 1, 1, 0, 1, False),
     "res5_2a_x5": (2048, 512, 320, 128, 1, 1, 0, 1, False),
     "res5_2c_x5": (512, 2048, 320, 128, 1, 1, 0, 1, True),
     "fc6_x5": (2048, 1024, 320, 128, 1, 1, 0, 1, False),
@@ -100,6 +101,14 @@ DEBUG_SWEEP = [
     {"ACCEL_TC_BN": "128", "ACCEL_TC_DEBUG": "7"},
 ]
 
+PF_SWEEP = [{"ACCEL_TC_RES_PREFETCH": "0"}, {"ACCEL_TC_RES_PREFETCH": "1"}]
+MMA_SWEEP = [{"ACCEL_TC_DEBUG": "256"}, {"ACCEL_TC_DEBUG": "256", "ACCEL_TC_NCAT": "0"},
+             {"ACCEL_TC_DEBUG": "256", "ACCEL_TC_BN": "256", "ACCEL_TC_WIDE_KMAX": "100000"},
+             {"ACCEL_TC_DEBUG": "256", "ACCEL_TC_BN": "64"}, {"ACCEL_TC_DEBUG": "256", "ACCEL_TC_BN": "64", "ACCEL_TC_NCAT": "0"},
+             {}, {"ACCEL_TC_NCAT": "0"}, {"ACCEL_TC_BN": "256", "ACCEL_TC_WIDE_KMAX": "100000"}, {"ACCEL_TC_BN": "64"}]
+LD_SWEEP = [{}] + [{"ACCEL_TC_DEBUG": str(b)} for b in (128, 240, 240 + 256, 240 + 512, 240 + 1024, 256, 512, 1024)]
+EPI2_SWEEP = [{}] + [{"ACCEL_TC_DEBUG": str(b)} for b in (16, 32, 64, 128, 48, 112, 240, 128 + 16, 128 + 32, 128 + 64)]
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -118,9 +127,9 @@ def main():
         ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
         wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
         r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
-        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP}.get(a.sweep, SWEEP):
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP}.get(a.sweep, SWEEP):
             for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR", "ACCEL_TC_ASLAB",
-                       "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO"):
+                       "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO", "ACCEL_TC_RES_PREFETCH", "ACCEL_TC_NCAT", "ACCEL_TC_WIDE_KMAX"):
                 os.environ.pop(kk, None)
             os.environ.update(knobs)
             sys.stderr.write("%-14s %-44s " % (name, knobs))

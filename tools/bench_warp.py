@@ -50,14 +50,15 @@ def main():
     hi = [torch.empty(h, w, C, dtype=torch.float16, device=dev) for _ in range(3)]
     lo = [torch.empty(h, w, C, dtype=torch.float16, device=dev) for _ in range(3)]
     fbytes = 3 * C * h * w * 4 + 2 * h * w * 4
-    variants = [v for v in os.environ.get("BENCH_WARP_VARIANTS", "2:16,2:4,3:16,3:4,1:16").split(",") if v]
+    variants = [v for v in os.environ.get("BENCH_WARP_VARIANTS", "2:16").split(",") if v]
     for v in variants:
         per_sm, nst = v.split(":")[:2]
         os.environ["ACCEL_WARP_FUSED_PER_SM"], os.environ["ACCEL_WARP_FUSED_NST"] = per_sm, nst
+        os.environ["ACCEL_WARP_FUSED_DEBUG"] = dbg = (v.split(":") + ["0"])[2]
         for name in ("smooth", "smooth+noise", "random(2px)"):
             fl = flows[name].contiguous().to(dev)
             us = timeit(lambda k: E.warp_split(src[k % 3], fl, dst[k % 3], hi[k % 3], lo[k % 3]))
-            print("warp_split per_sm=%s nst=%-2s %-14s %7.2f us  %7.1f GB/s" % (per_sm, nst, name, us, fbytes / us / 1e3))
+            print("warp_split per_sm=%s nst=%-2s dbg=%s %-14s %7.2f us  %7.1f GB/s" % (per_sm, nst, dbg, name, us, fbytes / us / 1e3))
 
 
 if __name__ == "__main__":

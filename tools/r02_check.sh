@@ -1,3 +1,2 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_ops.py -x -q -k "warp" 2>&1 | tail -5
-timeout 600 python tools/bench_warp.py 2>&1 | tee gpurun_out/r02_bench_warp_fused.txt
+timeout 600 python tools/bench_layer.py --sweep mma --set res5_2a_x5,res4_2b_x5 2>&1 | tee gpurun_out/r02_layer_mma_only.txt
