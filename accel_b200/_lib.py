@@ -36,10 +36,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("ACCEL_B200_LIB", LIB_PATH)          # A/B aid: another build of the same ABI
+    if not os.path.exists(path):
         raise RuntimeError("accel_b200: %s is missing -- build it with `python accel_b200/build.py` "
-                           "(there is no CPU or PyTorch fallback)" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+                           "(there is no CPU or PyTorch fallback)" % path)
+    lib = C.CDLL(path)
     vp, cp, ip, fp, u8p = C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_void_p
     lib.accel_create.argtypes = [C.POINTER(AccelConfig), C.POINTER(vp)]
     lib.accel_destroy.argtypes = [vp]

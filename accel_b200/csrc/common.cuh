@@ -83,6 +83,19 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // of values in [0, 1]).  Out-of-range taps are skipped by VALUE, as MXNet's BilinearSampler skips them -- the clamped
 // neighbour they point at may hold Inf -- while an in-range tap whose weight happens to be +0 still multiplies, as it does
 // there (0 * Inf = NaN in both).
+// The same activation over a register array with the switch taken ONCE (apply_act per element compiles to a branch per
+// element when `act` is a run-time value: 32 taken branches per 32-channel chunk in the conv epilogues).
+template <int N>
+__device__ __forceinline__ void apply_act_n(float (&v)[N], int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * 0.1f;
+  }
+}
+
 constexpr float kSkipTap = -0.0f;
 __device__ __forceinline__ bool keep_tap(float w) { return __float_as_uint(w) != 0x80000000u; }
 

@@ -345,6 +345,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool pf = leader && has_res && P.res_prefetch;
       if (pf && (int)blockIdx.x < items) prefetch_res(blockIdx.x);
       if (leader && has_res && (int)blockIdx.x < items) issue_res(blockIdx.x, cset * 32, 0);
+      // this thread's scale / shift of the NEXT item travel in registers while the current item is processed: with one or
+      // two K steps per tile the epilogue is the critical path and a load issued at the top of an item would be waited for
+      float sc_next = 1.f, sh_next = 0.f;
+      auto fetch_sc = [&](int item2) {
+        const int c = ((item2 / P.splits) % P.n_tiles) * P.BN + et;
+        const bool in = et < P.BN && c < E.Cout;
+        sc_next = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
+        sh_next = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
+      };
+      if ((int)blockIdx.x < items) fetch_sc(blockIdx.x);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         if (pf && item + (int)gridDim.x < items) prefetch_res(item + gridDim.x);
         const int tile = item / P.splits;
@@ -355,11 +365,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int pix = (y * E.osy + E.ooy) * E.OWf + x * E.osx + E.oox;
         const int nbase = nt * P.BN;
         if (et < P.BN) {
-          const int c = nbase + et;
-          const bool in = c < E.Cout;
-          epi_sc[sci][0][et] = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
-          epi_sc[sci][1][et] = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
+          epi_sc[sci][0][et] = sc_next;
+          epi_sc[sci][1][et] = sh_next;
         }
+        if (item + (int)gridDim.x < items) fetch_sc(item + gridDim.x);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (two) {
           mbar_wait(tfull0, accph);
@@ -404,8 +413,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
           }
           }
-          ResChunk rc{};
-          if (has_res) {
+          ResChunk rc;
+          if (!has_res) {
+            rc = ResChunk{};
+          } else {
             mbar_wait(rbar0 + 8u * b, (uint32_t)((n >> 1) & 1));
             const uint32_t row = sb + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
 #pragma unroll
@@ -743,6 +754,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
           const uint32_t fb = mapa_u32(full0 + 8 * s, 0);                // the LEADER's full barrier
           const uint32_t sa = smem0 + s * stage_bytes;
           const int dy = P.dy[t], dx = P.dx[t];
+          if (P.debug & 256) {                                           // timing decomposition: no operand loads
+            if (leader) mbar_arrive(full0 + 8 * s);
+            else mbar_arrive_cluster(fb);
+            if (++s == P.stages) { s = 0; ph ^= 1; }
+            continue;
+          }
           if (P.stride2) {
             tma2_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
             tma2_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
@@ -782,6 +799,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_cons
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);
+            if (P.debug & 128) continue;
             umma2_f16(d, ah + adv, bh + adv, idesc, (it > kb || k > 0) ? 1u : 0u);
             umma2_f16(d, ah + adv, bl + adv, idesc, 1u);
             umma2_f16(d, al + adv, bh + adv, idesc, 1u);

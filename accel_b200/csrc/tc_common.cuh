@@ -27,6 +27,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  // not unrolled: ptxas otherwise replicates the try_wait 64 times at every call site (2 KB of code each; the conv kernel
+  // grew to 15 K instructions and stalled on instruction fetch -- `no_instructions` 28 % of its samples)
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     asm volatile(
         "{\n\t"
@@ -39,8 +42,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (done) return;
   }
-  printf("accel_b200: conv_tc mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-         bar, parity);
+  // (no printf here by default: the call's ABI frame made ptxas spill registers that are live across every wait of the
+  // conv kernels' hot loops -- 340 bytes of spill loads per thread; build with -DACCEL_MBAR_DIAG to get the message back)
+#ifdef ACCEL_MBAR_DIAG
+  printf("accel_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
   __trap();
 }
 
@@ -206,30 +212,41 @@ __device__ __forceinline__ void store_split32(__half* hi, __half* lo, const floa
 // (they replace e.scale / e.shift).
 // store_main = false: the caller writes the main split output itself (TMA store from shared memory); `v`
 // holds the activated values on return either way.
-__device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int c0, float v[32], const ResChunk& rc,
+__device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int c0, float (&v)[32], const ResChunk& rc,
                                                  const float* sc32 = nullptr, const float* sh32 = nullptr,
                                                  bool store_main = true) {
+  if (e.raw_nchw) {                         // the linear part alone (key frame `fc6`: W*F for the commuted L head)
+    size_t base, plane;
+    if (nchw_base(e, pix, base, plane)) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float4 s, b;
-    if (sc32) {
-      s = *(reinterpret_cast<const float4*>(sc32) + q);
-      b = *(reinterpret_cast<const float4*>(sh32) + q);
-    } else {
-      s = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-      b = e.shift ? __ldg(reinterpret_cast<const float4*>(e.shift + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (e.raw_nchw) {                       // the linear part alone (key frame `fc6`: W*F for the commuted L head)
-      size_t base, plane;
-      if (nchw_base(e, pix, base, plane)) {
+      for (int q = 0; q < 8; ++q) {
+        const float4 s = sc32 ? *(reinterpret_cast<const float4*>(sc32) + q)
+                              : (e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f));
         float* rp = e.raw_nchw + base + (size_t)(c0 + 4 * q) * plane;
         rp[0] = v[4 * q + 0] * s.x; rp[plane] = v[4 * q + 1] * s.y; rp[2 * plane] = v[4 * q + 2] * s.z; rp[3 * plane] = v[4 * q + 3] * s.w;
       }
     }
-    v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, b.x);
-    v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, b.y);
-    v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, b.z);
-    v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, b.w);
+  }
+  if (sc32) {                               // (no run-time test inside the loops: each one costs a branch per four channels)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 s = *(reinterpret_cast<const float4*>(sc32) + q);
+      const float4 b = *(reinterpret_cast<const float4*>(sh32) + q);
+      v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, b.x);
+      v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, b.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, b.z);
+      v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, b.w);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 s = e.scale ? __ldg(reinterpret_cast<const float4*>(e.scale + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 b = e.shift ? __ldg(reinterpret_cast<const float4*>(e.shift + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, b.x);
+      v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, b.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, b.z);
+      v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, b.w);
+    }
   }
   if (e.res_hi) {
 #pragma unroll
@@ -240,8 +257,7 @@ __device__ __forceinline__ void epilogue_chunk32(const Epilogue& e, int pix, int
       v[2 * i + 1] += h.y + l.y;
     }
   }
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
+  apply_act_n(v, e.act);
   if (e.out_hi && store_main) store_split32(e.out_hi + (size_t)pix * e.out_ld + c0, e.out_lo + (size_t)pix * e.out_ld + c0, v);
   if (e.out_nchw) {
     size_t base, plane;
@@ -283,14 +299,15 @@ inline EncodeTiledFn encode_fn() {
 }
 
 inline bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-            const cuuint32_t* box, char* err, int errlen, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+            const cuuint32_t* box, char* err, int errlen, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+            CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled is unavailable");
     return false;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -239,9 +239,11 @@ __global__ void __launch_bounds__(WS_THREADS) warp_kernel_staged(const float* __
 // border cannot turn into NaN.
 // ================================================================================================
 constexpr int WF_CB = 4, WF_G = 32;           // channels per ring stage / per staged NHWC group
+constexpr int WF_NMAP = 12;                   // source tensor maps: box {W, R, WF_CB} for band heights R = 1 .. WF_NMAP
 
 struct alignas(64) WarpFusedParams {
   CUtensorMap o_hi, o_lo;                    // split NHWC view {C, W, H}, box {32, W, TH}, SWIZZLE_64B
+  CUtensorMap src[WF_NMAP];                  // fp32 NCHW source {W, H, C}: src[R-1] has box {W, R, WF_CB} -- a whole stage in ONE request
   const float* feat;
   const float* flow;
   float* out_nchw;
@@ -249,6 +251,7 @@ struct alignas(64) WarpFusedParams {
   int act, has_split;
   int C, H, W, TH, RMAX;
   int debug;                                 // ACCEL_WARP_FUSED_DEBUG (timing decomposition only): 1 no NCHW stores, 2 no TMA stores
+  int nmap;                                  // bands up to this height use src[]; taller ones one cp.async.bulk per channel
   int ring_floats, max_stages;               // ring capacity; the CTA cuts it into min(max_stages, capacity / band) stages
 };
 
@@ -339,9 +342,13 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t fb = full0 + 8 * s;
           mbar_arrive_expect_tx(fb, band_bytes * WF_CB);
+          if (R <= P.nmap) {                                    // one tensor request per stage: {W, R rows, WF_CB channels}
+            tma_load_3d(ring0 + (uint32_t)(s * WF_CB * slot) * 4u, &P.src[R - 1], fb, 0, r0, c0);
+          } else {
 #pragma unroll
-          for (int c = 0; c < WF_CB; ++c)
-            bulk_load(ring0 + (uint32_t)((s * WF_CB + c) * slot) * 4u, P.feat + (size_t)(c0 + c) * npix + (size_t)r0 * W, band_bytes, fb);
+            for (int c = 0; c < WF_CB; ++c)
+              bulk_load(ring0 + (uint32_t)((s * WF_CB + c) * slot) * 4u, P.feat + (size_t)(c0 + c) * npix + (size_t)r0 * W, band_bytes, fb);
+          }
           if (++s == nst) { s = 0; ph ^= 1; }
         }
     }
@@ -476,6 +483,19 @@ static cudaError_t launch_fused_variant(const WarpParams& P, int once_slot, cuda
     if (!encode(&F.o_hi, P.out_hi, 3, dims, str, box, err, sizeof(err), CU_TENSOR_MAP_SWIZZLE_64B) ||
         !encode(&F.o_lo, P.out_lo, 3, dims, str, box, err, sizeof(err), CU_TENSOR_MAP_SWIZZLE_64B))
       return cudaErrorInvalidValue;
+  }
+  F.nmap = 0;
+  if (env_int("ACCEL_WARP_FUSED_TMAP", 1) != 0 && P.W <= 256) {
+    char err[256];
+    const cuuint64_t dims[3] = {(cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)P.C};
+    const cuuint64_t str[2] = {(cuuint64_t)P.W * 4, (cuuint64_t)P.W * P.H * 4};
+    const int nmap = std::min(std::min(WF_NMAP, rmax), P.H);
+    int ok = 1;
+    for (int r = 1; r <= nmap && ok; ++r) {
+      const cuuint32_t box[3] = {(cuuint32_t)P.W, (cuuint32_t)r, (cuuint32_t)WF_CB};
+      ok = encode(&F.src[r - 1], P.feat, 3, dims, str, box, err, sizeof(err), CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    }
+    if (ok) F.nmap = nmap;
   }
   const size_t smem = 1024 + 2 * (size_t)CONS * 64 + (size_t)F.ring_floats * 4;
   const int bx = (P.H + F.TH - 1) / F.TH;

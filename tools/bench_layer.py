@@ -106,6 +106,12 @@ MMA_SWEEP = [{"ACCEL_TC_DEBUG": "256"}, {"ACCEL_TC_DEBUG": "256", "ACCEL_TC_NCAT
              {"ACCEL_TC_DEBUG": "256", "ACCEL_TC_BN": "256", "ACCEL_TC_WIDE_KMAX": "100000"},
              {"ACCEL_TC_DEBUG": "256", "ACCEL_TC_BN": "64"}, {"ACCEL_TC_DEBUG": "256", "ACCEL_TC_BN": "64", "ACCEL_TC_NCAT": "0"},
              {}, {"ACCEL_TC_NCAT": "0"}, {"ACCEL_TC_BN": "256", "ACCEL_TC_WIDE_KMAX": "100000"}, {"ACCEL_TC_BN": "64"}]
+_PW = {"ACCEL_TC_PAIR": "1", "ACCEL_TC_BN": "256", "ACCEL_TC_WIDE_KMAX": "100000"}
+_SW = {"ACCEL_TC_BN": "256", "ACCEL_TC_WIDE_KMAX": "100000", "ACCEL_TC_NCAT": "0"}
+PAIR2_SWEEP = [{}, dict(_SW), dict(_SW, ACCEL_TC_DEBUG="256"), dict(_SW, ACCEL_TC_DEBUG="128"),
+               dict(_PW), dict(_PW, ACCEL_TC_DEBUG="256"), dict(_PW, ACCEL_TC_DEBUG="128"), dict(_PW, ACCEL_TC_DEBUG="384")]
+SHORTK_SWEEP = [{}, {"ACCEL_TC_DEBUG": "496"}, {"ACCEL_TC_DEBUG": "240"}, {"ACCEL_TC_DEBUG": "256"}, {"ACCEL_TC_BN": "256"}, {"ACCEL_TC_BN": "256", "ACCEL_TC_DEBUG": "496"},
+                {"ACCEL_TC_BN": "64"}, {"ACCEL_TC_TMA_OUT": "0"}, {"ACCEL_TC_BN": "256", "ACCEL_TC_TMA_OUT": "0"}, {"ACCEL_TC_NCAT": "0"}]
 LD_SWEEP = [{}] + [{"ACCEL_TC_DEBUG": str(b)} for b in (128, 240, 240 + 256, 240 + 512, 240 + 1024, 256, 512, 1024)]
 EPI2_SWEEP = [{}] + [{"ACCEL_TC_DEBUG": str(b)} for b in (16, 32, 64, 128, 48, 112, 240, 128 + 16, 128 + 32, 128 + 64)]
 
@@ -127,7 +133,7 @@ def main():
         ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
         wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
         r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
-        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP}.get(a.sweep, SWEEP):
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP, "pair2": PAIR2_SWEEP, "shortk": SHORTK_SWEEP}.get(a.sweep, SWEEP):
             for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR", "ACCEL_TC_ASLAB",
                        "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO", "ACCEL_TC_RES_PREFETCH", "ACCEL_TC_NCAT", "ACCEL_TC_WIDE_KMAX"):
                 os.environ.pop(kk, None)

@@ -54,11 +54,12 @@ def main():
     for v in variants:
         per_sm, nst = v.split(":")[:2]
         os.environ["ACCEL_WARP_FUSED_PER_SM"], os.environ["ACCEL_WARP_FUSED_NST"] = per_sm, nst
-        os.environ["ACCEL_WARP_FUSED_DEBUG"] = dbg = (v.split(":") + ["0"])[2]
+        os.environ["ACCEL_WARP_FUSED_DEBUG"] = dbg = (v.split(":") + ["0", "1"])[2]
+        os.environ["ACCEL_WARP_FUSED_TMAP"] = tmap = (v.split(":") + ["0", "1"])[3]
         for name in ("smooth", "smooth+noise", "random(2px)"):
             fl = flows[name].contiguous().to(dev)
             us = timeit(lambda k: E.warp_split(src[k % 3], fl, dst[k % 3], hi[k % 3], lo[k % 3]))
-            print("warp_split per_sm=%s nst=%-2s dbg=%s %-14s %7.2f us  %7.1f GB/s" % (per_sm, nst, dbg, name, us, fbytes / us / 1e3))
+            print("warp_split per_sm=%s nst=%-2s dbg=%s tmap=%s %-14s %7.2f us  %7.1f GB/s" % (per_sm, nst, dbg, tmap, name, us, fbytes / us / 1e3))
 
 
 if __name__ == "__main__":
