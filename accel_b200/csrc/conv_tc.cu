@@ -36,7 +36,9 @@ using namespace tc;
 constexpr int BM = 128;          // pixels per tile (UMMA M)
 constexpr int BK = 64;           // channels per stage: 128 bytes of fp16 = one SWIZZLE_128B row
 constexpr int kEpiWarps = 8;      // two warps per TMEM lane quarter; they interleave the 32-column chunks of a tile
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kDmaWarps = 2;      // TMA epilogue: one thread per chunk set issues the tensor stores / residual loads (warps 10, 11)
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * kDmaWarps;
+constexpr int kThreadsPair = 64 + 32 * kEpiWarps;           // conv_tc2_kernel has no DMA warps
 constexpr int kMaxStages = 6;
 constexpr int kSmemMaxDynamic = 227 * 1024 - 6 * 1024;   // 227 KB per CTA minus the static barriers/slots/scale-shift stage
 // epilogue staging for TMA stores: per chunk set (2) x double buffer (2) x [hi | lo] x 128 pixel rows x 64 bytes
@@ -58,7 +60,6 @@ struct alignas(64) TcParams {
   int pair;        // 1: conv_tc2_kernel (cta_group::2 pairs)
   int ncat;        // 1: hi*hi and hi*lo issued as ONE MMA over [B_hi ; B_lo] (N = 2*BN, two accumulator halves summed in the epilogue)
   int tma_out;     // 1: the main output leaves through shared memory + TMA tensor stores (3-D map), 2: 5-D map (transposed-conv phase)
-  int res_prefetch;  // TMA epilogue: the residual tile of the NEXT item is prefetched into L2 while this item is processed
   int debug;       // tuning aid (ACCEL_TC_DEBUG): 1 = no epilogue stores, 2 = no residual loads, 4 = no tcgen05.ld, 8 = direct epilogue; TMA epilogue: 16 = no residual loads, 32 = no tensor stores, 64 = no tcgen05.ld, 128 = no MMAs, 256 / 512 / 1024 = no operand / A / B loads
   int vec32;       // every split-NHWC operand of the epilogue is 32-byte aligned with 32-byte row pitch
   // A-slab reuse (stride-1 multi-tap layers whose tile is one full 128-pixel row segment): the taps of one filter row
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float epi_sc[2][2][256];          // [accumulator][scale | shift][channel of the tile]
-  __shared__ __align__(8) uint64_t res_bars[4];              // TMA epilogue: residual landed in staging buffer [chunk set][buffer]
+  __shared__ __align__(8) uint64_t res_bars[4];              // TMA epilogue: staging buffer [chunk set][buffer] is free / holds its residual
+  __shared__ __align__(8) uint64_t stg_bars[4];              // TMA epilogue: all 128 threads of the chunk set wrote their result rows
   __shared__ int s_last;                                     // fused split-K: this CTA delivered the tile's last slab
 
   // operand ring: [stage][A_hi | A_lo | B_hi | B_lo]
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(tempty0 + 8 * a, kEpiWarps);
     }
     for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&res_bars[a]), 1);
+    for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&stg_bars[a]), 128);
     for (int a = 0; a < 8; ++a) mbar_init(smem_u32(&abars[a]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -301,50 +304,87 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     }
+  } else if (warp >= 2 + kEpiWarps) {
+    // ===================================== epilogue DMA (TMA epilogue only) ===================
+    // One thread per chunk set owns every bulk operation of that set's two staging buffers, so that no epilogue thread ever
+    // waits for a store: chunk k (buffer k & 1) is stored when its 128 threads have arrived on stg_bars, and once the
+    // store has read the buffer it is handed to chunk k + 2 -- with that chunk's residual tile on the way (res_bars carries
+    // the bytes) or, without a residual, by a plain arrival.
+    const int cset = warp - (2 + kEpiWarps);
+    if (P.tma_out && P.splits == 1 && lane == 0 && cset < 2) {
+      const Epilogue& E = P.epi;
+      const bool has_res = E.res_hi != nullptr && !(P.debug & 16);
+      const uint32_t sb0 = stg0 + (uint32_t)cset * 2u * 16384u;
+      const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]), sbar0 = smem_u32(&stg_bars[cset * 2]);
+      const int cpi = P.BN > cset * 32 ? (P.BN - cset * 32 + 63) / 64 : 0;       // chunks of one item that belong to this set
+      const int mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const int total = mine * cpi;
+      auto coords = [&](int k, int& c0, int& x0, int& y0) {
+        const int item = (int)blockIdx.x + (k / cpi) * (int)gridDim.x;
+        const int tile = item / P.splits, nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        c0 = nt * P.BN + cset * 32 + (k % cpi) * 64;
+        x0 = (mt % P.tiles_x) * P.BW;
+        y0 = (mt / P.tiles_x) * P.BH;
+      };
+      auto fill = [&](int k) {                               // buffer k & 1 becomes chunk k's
+        const uint32_t bar = rbar0 + 8u * (uint32_t)(k & 1);
+        if (has_res) {
+          int c0, x0, y0;
+          coords(k, c0, x0, y0);
+          const uint32_t dst = sb0 + (uint32_t)(k & 1) * 16384u;
+          mbar_arrive_expect_tx(bar, 16384u);
+          tma_load_3d(dst, &P.r_hi, bar, c0, x0, y0);
+          tma_load_3d(dst + 8192u, &P.r_lo, bar, c0, x0, y0);
+        } else {
+          mbar_arrive(bar);
+        }
+      };
+      if (total > 0) fill(0);
+      if (total > 1) fill(1);
+      for (int k = 0; k < total; ++k) {
+        const uint32_t sb = sb0 + (uint32_t)(k & 1) * 16384u;
+        mbar_wait(sbar0 + 8u * (uint32_t)(k & 1), (uint32_t)((k >> 1) & 1));
+        if (!(P.debug & 32)) {
+          int c0, x0, y0;
+          coords(k, c0, x0, y0);
+          if (P.tma_out == 2) {
+            tma_store_5d(&P.o_hi, sb, c0, E.oox, x0, E.ooy, y0);
+            tma_store_5d(&P.o_lo, sb + 8192u, c0, E.oox, x0, E.ooy, y0);
+          } else {
+            tma_store_3d(&P.o_hi, sb, c0, x0, y0);
+            tma_store_3d(&P.o_lo, sb + 8192u, c0, x0, y0);
+          }
+          bulk_commit();
+        }
+        if (k + 2 < total) {
+          bulk_wait_read0();                                 // the stores of chunk k have read the buffer
+          fill(k + 2);
+        }
+      }
+      bulk_wait0();
+    }
   } else {
     if (P.tma_out && P.splits == 1) {
       // ===================================== epilogue, TMA both ways ===========================
       // The lane-per-pixel global accesses of the direct epilogue are 32 separate lines per warp instruction and
       // saturate the L1TEX pipe (profiles/r01_ncu_dcn_col.txt shows the same pattern).  Here global memory is only
       // touched by the TMA unit: per chunk set (4 warps = the tile's 128 pixel rows) and 32-channel chunk, the
-      // residual tile lands in a SWIZZLE_64B staging buffer (hi | lo, 16 KB) one chunk ahead, every thread folds
-      // its own 64+64 bytes into its accumulator row and writes the result back IN PLACE, and the leader hands
-      // the buffer to two tensor stores.  Two buffers per chunk set; one named barrier per chunk.
+      // residual tile lands in a SWIZZLE_64B staging buffer (hi | lo, 16 KB), every thread folds its own 64+64 bytes
+      // into its accumulator row and writes the result back IN PLACE, and the set's DMA thread (above) hands the
+      // buffer to two tensor stores.  Two buffers per chunk set; the threads of a set synchronise through the
+      // buffers' mbarriers only -- no named barrier, nobody waits for a store.
       const int quarter = warp & 3, cset = (warp - 2) >> 2;
       const int r = quarter * 32 + lane;
       const int by = r / P.BW, bx = r - by * P.BW;
       const int et = threadIdx.x - 64;
       const Epilogue& E = P.epi;
       const bool has_res = E.res_hi != nullptr && !(P.debug & 16);
-      const bool leader = quarter == 0 && lane == 0;
       const uint32_t sb0 = stg0 + (uint32_t)cset * 2u * 16384u;
-      const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]);
-      auto issue_res = [&](int item2, int cc2, int b2) {     // leader: residual of chunk (item2, cc2) -> buffer b2
-        const int tile2 = item2 / P.splits, nt2 = tile2 % P.n_tiles, mt2 = tile2 / P.n_tiles;
-        const int x02 = (mt2 % P.tiles_x) * P.BW, y02 = (mt2 / P.tiles_x) * P.BH;
-        const uint32_t dst = sb0 + (uint32_t)b2 * 16384u, bar = rbar0 + 8u * b2;
-        mbar_arrive_expect_tx(bar, 16384u);
-        tma_load_3d(dst, &P.r_hi, bar, nt2 * P.BN + cc2, x02, y02);
-        tma_load_3d(dst + 8192u, &P.r_lo, bar, nt2 * P.BN + cc2, x02, y02);
-      };
+      const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]), sbar0 = smem_u32(&stg_bars[cset * 2]);
       const bool two = P.kchains == 2;
       const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
       int acc = 0, sci = 0, n = 0;                          // sci: scale/shift staging slot, alternates per item
       uint32_t accph = 0;
-      // The staging buffers keep ONE residual chunk in flight per chunk set: fetched from HBM, every chunk would cost a full
-      // DRAM round trip (res4 expand: 3.4 us per chunk against a 3.5 us mainloop per tile).  The leader therefore pulls the
-      // residual boxes of the next item into L2 a whole tile ahead; the staging loads then pay an L2 hit.
-      auto prefetch_res = [&](int item2) {
-        const int tile2 = item2 / P.splits, nt2 = tile2 % P.n_tiles, mt2 = tile2 / P.n_tiles;
-        const int x02 = (mt2 % P.tiles_x) * P.BW, y02 = (mt2 / P.tiles_x) * P.BH;
-        for (int cc2 = cset * 32; cc2 < P.BN; cc2 += 64) {
-          tma_prefetch_3d(&P.r_hi, nt2 * P.BN + cc2, x02, y02);
-          tma_prefetch_3d(&P.r_lo, nt2 * P.BN + cc2, x02, y02);
-        }
-      };
-      const bool pf = leader && has_res && P.res_prefetch;
-      if (pf && (int)blockIdx.x < items) prefetch_res(blockIdx.x);
-      if (leader && has_res && (int)blockIdx.x < items) issue_res(blockIdx.x, cset * 32, 0);
       // this thread's scale / shift of the NEXT item travel in registers while the current item is processed: with one or
       // two K steps per tile the epilogue is the critical path and a load issued at the top of an item would be waited for
       float sc_next = 1.f, sh_next = 0.f;
@@ -356,7 +396,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       };
       if ((int)blockIdx.x < items) fetch_sc(blockIdx.x);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        if (pf && item + (int)gridDim.x < items) prefetch_res(item + gridDim.x);
         const int tile = item / P.splits;
         const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
         const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
@@ -381,13 +420,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int cc = cset * 32; cc < P.BN; cc += 64, ++n) {
           const int b = n & 1;
           const uint32_t sb = sb0 + (uint32_t)b * 16384u;
-          if (leader) {
-            bulk_wait_read0();                               // the stores that read buffer b^1 (chunk n-1) are done with it
-            if (has_res) {
-              if (cc + 64 < P.BN) issue_res(item, cc + 64, b ^ 1);
-              else if (item + (int)gridDim.x < items) issue_res(item + gridDim.x, cset * 32, b ^ 1);
-            }
-          }
           float v[32];
           if (P.debug & 64) {
 #pragma unroll
@@ -413,11 +445,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
           }
           }
+          mbar_wait(rbar0 + 8u * b, (uint32_t)((n >> 1) & 1));          // buffer b is ours (and holds the residual rows)
           ResChunk rc;
           if (!has_res) {
             rc = ResChunk{};
           } else {
-            mbar_wait(rbar0 + 8u * b, (uint32_t)((n >> 1) & 1));
             const uint32_t row = sb + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -434,17 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           stage_row64(sb, r, wh);
           stage_row64(sb + 8192u, r, wl);
           fence_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + cset) : "memory");
-          if (leader && !(P.debug & 32)) {
-            if (P.tma_out == 2) {
-              tma_store_5d(&P.o_hi, sb, nbase + cc, E.oox, x0, E.ooy, y0);
-              tma_store_5d(&P.o_lo, sb + 8192u, nbase + cc, E.oox, x0, E.ooy, y0);
-            } else {
-              tma_store_3d(&P.o_hi, sb, nbase + cc, x0, y0);
-              tma_store_3d(&P.o_lo, sb + 8192u, nbase + cc, x0, y0);
-            }
-            bulk_commit();
-          }
+          mbar_arrive(sbar0 + 8u * b);                       // -> the set's DMA thread stores the buffer
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -457,7 +479,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (++acc == 2) { acc = 0; accph ^= 1; }
         }
       }
-      if (leader) bulk_wait0();
     } else {
     // ===================================== epilogue ==========================================
     // Lane = pixel (TMEM lane), 32 consecutive output channels per chunk: 64 contiguous bytes per
@@ -687,7 +708,7 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {      // arrives on 
                : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_tc2_kernel(const __grid_constant__ TcParams P) {
+__global__ void __launch_bounds__(kThreadsPair, 1) conv_tc2_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -1079,7 +1100,6 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     P.vec32 = v ? 1 : 0;
     P.krot = P.aslab ? 0 : env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
     P.debug = env_int("ACCEL_TC_DEBUG", 0);
-    P.res_prefetch = env_int("ACCEL_TC_RES_PREFETCH", 0);
   }
 
   // tensor maps ------------------------------------------------------------------------------------
@@ -1180,7 +1200,7 @@ cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_r
   TcParams P = plan->p;
   if (ext_nchw) P.epi.out_nchw = ext_nchw;
   P.epi.raw_nchw = ext_raw;
-  cudaError_t e = P.pair ? launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreads), plan->smem, stream, 2u, P)
+  cudaError_t e = P.pair ? launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P)
                   : P.fused ? (P.ncat ? launch_k(conv_tc_kernel<true, true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
                                       : launch_k(conv_tc_kernel<false, true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P))
                   : P.ncat ? launch_k(conv_tc_kernel<true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
