@@ -183,9 +183,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       }
-    } else if (lane == 0) {
+    } else if (!P.aslab) {
+      // convergent warp, elect.sync around the TMA instructions (see the MMA issuer)
       int s = 0;
       uint32_t ph = 0;
+      const bool ldA = !(P.debug & (256 | 512)), ldB = !(P.debug & (256 | 1024));   // timing decomposition only
+      const uint32_t tx = (ldA ? 2 * a_bytes : 0u) + (ldB ? 2 * b_bytes : 0u);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int split = item % P.splits, tile = item / P.splits;
         const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
@@ -194,40 +197,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
         const int fr = y0 / P.Hof, yl = y0 - fr * P.Hof;         // frame of the tile and its first row inside that frame
         const int rot = P.krot ? (int)(((unsigned)item * 5u) % (unsigned)(ke - kb)) : 0;
+        int it = kb + rot;                                // each CTA walks K from its own offset: neighbours do not
+        int t = it / P.chunks, kc = it - t * P.chunks;    // stream the same weight lines at the same moment
         for (int i = kb; i < ke; ++i) {
-          int it = i + rot;                               // each CTA walks K from its own offset: neighbours do not
-          if (it >= ke) it -= ke - kb;                    // stream the same weight lines at the same moment
-          const int t = it / P.chunks, kc = it - t * P.chunks;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t fb = full0 + 8 * s;
-          const bool ldA = !(P.debug & (256 | 512)), ldB = !(P.debug & (256 | 1024));   // timing decomposition only
-          mbar_arrive_expect_tx(fb, (ldA ? 2 * a_bytes : 0u) + (ldB ? 2 * b_bytes : 0u));
           const uint32_t sa = smem0 + s * stage_bytes;
           const int dy = P.dy[t], dx = P.dx[t];
-          if (!ldA) {
-          } else if (P.stride2) {
-            tma_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
-            tma_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
-          } else {
-            tma_load_4d(sa, &P.a_hi, fb, kc * BK, x0 + dx, yl + dy, fr);
-            tma_load_4d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, yl + dy, fr);
-          }
           const int kcol = t * P.Cin_pad + kc * BK;
-          if (ldB) {
-            tma_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nt * P.BN);
-            tma_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nt * P.BN);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(fb, tx);
+            if (!ldA) {
+            } else if (P.stride2) {
+              tma_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+              tma_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+            } else {
+              tma_load_4d(sa, &P.a_hi, fb, kc * BK, x0 + dx, yl + dy, fr);
+              tma_load_4d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, yl + dy, fr);
+            }
+            if (ldB) {
+              tma_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nt * P.BN);
+              tma_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nt * P.BN);
+            }
           }
+          __syncwarp();
           if (++s == P.stages) { s = 0; ph ^= 1; }
+          if (++kc == P.chunks) { kc = 0; ++t; }          // next K stage: channel chunks fastest, then taps ...
+          if (++it == ke) { it = kb; t = it / P.chunks; kc = it - t * P.chunks; }   // ... wrapping around at the rotation
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // The WHOLE warp walks this loop convergently and only the tcgen05 instructions are predicated on elect.sync: every
+    // descriptor, TMEM address and barrier address then lives in uniform registers.  Under `if (lane == 0)` the compiler
+    // cannot prove them warp-uniform and wraps each UTCHMMA in an ELECT / R2UR.BROADCAST waterfall; measured
+    // (tools/mma_probe.cu, profiles/r02_mma_probe.txt) that issue path cost ~180 cycles per MMA in this kernel against the
+    // tensor core's 64 (N = 128) / 128 (N = 256) cycles -- the mainloop was ISSUE-bound.
+    {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * P.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const int acc_cols = NCAT ? 2 * P.BN : P.BN;
+      const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
       const bool two = P.kchains == 2;
+      const bool no_mma = (P.debug & 128) != 0;
+      const uint32_t bn = (uint32_t)P.BN;
       int s = 0, acc = 0;
       uint32_t ph = 0, accph = 0;
       int nas = 0, cur = 0;                               // A-slab ring: next slot to consume, slot in use
@@ -243,9 +256,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_wait(tempty0 + 8 * acc, accph ^ 1);
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        int q = 0;                                        // K slice counter of this item
+        // two chains: even slices accumulate in buffer 0, odd slices in buffer 1 (half the steps and half the magnitude
+        // per accumulator); the epilogue adds the buffers in fp32
+        const uint32_t d0 = tmem_base + (two ? 0u : (uint32_t)acc * acc_cols);
+        const uint32_t d1 = two ? tmem_base + acc_cols : d0;
         for (int it = kb; it < ke; ++it) {
-          uint64_t ah, al, bh, bl;
+          uint32_t a_hi, a_lo, b_hi, b_lo;
+          int slab_mode = 0;
           bool slab_done = false;
           if (P.aslab) {
             const int outer = it / P.ndx, i = it - outer * P.ndx;
@@ -256,51 +273,64 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               if (++nas == P.sa_stages) { nas = 0; aphc ^= 1; }
             }
             slab_done = i == P.ndx - 1 || it == ke - 1;
-            mbar_wait(full0 + 8 * s, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = smem0 + (uint32_t)cur * 2u * (uint32_t)P.slab_pl + (uint32_t)(P.dx[t] - P.dxmin) * 128u;
-            const uint32_t sb = bring0 + (uint32_t)s * 2u * b_bytes;
-            ah = umma_desc_rows(a0, P.slab_bo); al = umma_desc_rows(a0 + (uint32_t)P.slab_pl, P.slab_bo);
-            bh = umma_desc(sb); bl = umma_desc(sb + b_bytes);
+            a_hi = smem0 + (uint32_t)cur * 2u * (uint32_t)P.slab_pl + (uint32_t)(P.dx[t] - P.dxmin) * 128u;
+            a_lo = a_hi + (uint32_t)P.slab_pl;
+            b_hi = bring0 + (uint32_t)s * 2u * b_bytes;
+            b_lo = b_hi + b_bytes;
+            slab_mode = 1;
           } else {
-            mbar_wait(full0 + 8 * s, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem0 + s * stage_bytes;
-            ah = umma_desc(sa); al = umma_desc(sa + a_bytes);
-            bh = umma_desc(sa + 2 * a_bytes); bl = umma_desc(sa + 2 * a_bytes + b_bytes);
+            a_hi = smem0 + s * stage_bytes;
+            a_lo = a_hi + a_bytes;
+            b_hi = a_hi + 2 * a_bytes;
+            b_lo = b_hi + b_bytes;
           }
+          mbar_wait(full0 + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t ah = slab_mode ? umma_desc_rows(a_hi, P.slab_bo) : umma_desc(a_hi);
+          const uint64_t al = slab_mode ? umma_desc_rows(a_lo, P.slab_bo) : umma_desc(a_lo);
+          const uint64_t bh = umma_desc(b_hi), bl = umma_desc(b_lo);
+          const uint32_t first0 = it > kb ? 1u : 0u;        // slice 0 (chain 0) / slice 1 (chain 1, or chain 0 again) of this stage
+          if (elect_one()) {
+            if (!no_mma) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k, ++q) {
-            const uint64_t adv = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes along K inside the swizzle atom
-            // two chains: even slices accumulate in buffer 0, odd slices in buffer 1 (half the steps and half the
-            // magnitude per accumulator); the epilogue adds the buffers in fp32
-            const uint32_t d = tmem_base + (uint32_t)((two ? (q & 1) : acc) * acc_cols);
-            const uint32_t first = (q >= (two ? 2 : 1)) ? 1u : 0u;
-            if (P.debug & 128) continue;
-            if (NCAT) {
-              // B_hi and B_lo are adjacent in the stage with one row pitch: a single N = 2*BN operand.  Columns
-              // [0, BN) collect hi*hi, columns [BN, 2BN) collect hi*lo and -- issued into the upper half alone --
-              // lo*hi: the small cross terms never touch the big accumulator, whose truncating additions are the
-              // dominant rounding error.  The tensor core reads the A_hi slice once and issues two instructions.
-              umma_f16(d, ah + adv, bh + adv, idesc2, first);
-              umma_f16(d + (uint32_t)P.BN, al + adv, bh + adv, idesc, 1u);
-            } else {
-              umma_f16(d, ah + adv, bh + adv, idesc, first);
-              umma_f16(d, ah + adv, bl + adv, idesc, 1u);
-              umma_f16(d, al + adv, bh + adv, idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes along K inside the swizzle atom
+                const uint32_t d = (k & 1) ? d1 : d0;         // BK / 16 is even: a stage's slices alternate d0, d1, d0, d1
+                const uint32_t first = two ? (k >= 2 ? 1u : first0) : (k >= 1 ? 1u : first0);
+                if (NCAT) {
+                  // B_hi and B_lo are adjacent in the stage with one row pitch: a single N = 2*BN operand.  Columns
+                  // [0, BN) collect hi*hi, columns [BN, 2BN) collect hi*lo and -- issued into the upper half alone --
+                  // lo*hi: the small cross terms never touch the big accumulator, whose truncating additions are the
+                  // dominant rounding error.  The tensor core reads the A_hi slice once and issues two instructions.
+                  umma_f16(d, ah + adv, bh + adv, idesc2, first);
+                  umma_f16(d + bn, al + adv, bh + adv, idesc, 1u);
+                } else {
+                  umma_f16(d, ah + adv, bh + adv, idesc, first);
+                  umma_f16(d, ah + adv, bl + adv, idesc, 1u);
+                  umma_f16(d, al + adv, bh + adv, idesc, 1u);
+                }
+              }
             }
+            umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
+            if (slab_done) umma_commit(aempty0 + 8 * cur);  // ... and the A slab after the last tap that reads it
           }
-          umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
-          if (slab_done) umma_commit(aempty0 + 8 * cur);  // ... and the A slab after the last tap that reads it
+          __syncwarp();
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
+        if (elect_one()) {
+          if (two) {
+            umma_commit(tfull0);                            // both accumulators complete -> epilogue
+            umma_commit(tfull0 + 8);
+          } else {
+            umma_commit(tfull0 + 8 * acc);                  // accumulator complete -> epilogue
+          }
+        }
+        __syncwarp();
         if (two) {
-          umma_commit(tfull0);                            // both accumulators complete -> epilogue
-          umma_commit(tfull0 + 8);
           accph ^= 1;
-        } else {
-          umma_commit(tfull0 + 8 * acc);                  // accumulator complete -> epilogue
-          if (++acc == 2) { acc = 0; accph ^= 1; }
+        } else if (++acc == 2) {
+          acc = 0;
+          accph ^= 1;
         }
       }
     }

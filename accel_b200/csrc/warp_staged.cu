@@ -358,6 +358,8 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
   // ---------------------------------------------------------------- consumers
   if (staged) t.o00 -= r0 * W;
   const bool n00 = keep_tap(t.w00), n01 = keep_tap(t.w01), n10 = keep_tap(t.w10), n11 = keep_tap(t.w11);
+  const int o01 = t.o00 + t.dx1, o10 = t.o00 + t.dyw, o11 = t.o00 + t.dyw + t.dx1;
+  const bool fast = staged && __all_sync(0xffffffffu, live && n00 && n01 && n10 && n11);
   int s = 0;
   uint32_t ph = 0;
   for (int g = blockIdx.y; g < ngroups; g += gridDim.y) {
@@ -368,15 +370,27 @@ __global__ void __launch_bounds__(WF_CONS + 32) warp_kernel_fused(const __grid_c
       float v[WF_CB];
       if (staged) {
         mbar_wait(full0 + 8 * s, ph);
-        const float* st = ring + (size_t)s * WF_CB * slot + t.o00;
+        if (fast) {                                             // every tap of every lane is in range: no predicates, no zero fills
+          const float* st = ring + (size_t)s * WF_CB * slot;    // warp-uniform: the four tap offsets stay in registers
 #pragma unroll
-        for (int ch = 0; ch < WF_CB; ++ch) {
-          const float* sp = st + ch * slot;
-          const float a = n00 ? sp[0] : 0.f, bq = n01 ? sp[t.dx1] : 0.f, cq = n10 ? sp[t.dyw] : 0.f, d = n11 ? sp[t.dyw + t.dx1] : 0.f;
-          float x = __fmul_rn(a, t.w00);
-          x = __fadd_rn(x, __fmul_rn(bq, t.w01));
-          x = __fadd_rn(x, __fmul_rn(cq, t.w10));
-          v[ch] = __fadd_rn(x, __fmul_rn(d, t.w11));
+          for (int ch = 0; ch < WF_CB; ++ch) {
+            const float* sp = st + ch * slot;
+            float x = __fmul_rn(sp[t.o00], t.w00);
+            x = __fadd_rn(x, __fmul_rn(sp[o01], t.w01));
+            x = __fadd_rn(x, __fmul_rn(sp[o10], t.w10));
+            v[ch] = __fadd_rn(x, __fmul_rn(sp[o11], t.w11));
+          }
+        } else {
+          const float* st = ring + (size_t)s * WF_CB * slot + t.o00;
+#pragma unroll
+          for (int ch = 0; ch < WF_CB; ++ch) {
+            const float* sp = st + ch * slot;
+            const float a = n00 ? sp[0] : 0.f, bq = n01 ? sp[t.dx1] : 0.f, cq = n10 ? sp[t.dyw] : 0.f, d = n11 ? sp[t.dyw + t.dx1] : 0.f;
+            float x = __fmul_rn(a, t.w00);
+            x = __fadd_rn(x, __fmul_rn(bq, t.w01));
+            x = __fadd_rn(x, __fmul_rn(cq, t.w10));
+            v[ch] = __fadd_rn(x, __fmul_rn(d, t.w11));
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * s);

@@ -374,6 +374,7 @@ def run_native(a):
     # comes from HBM, as in the real loop where >1 GB of other traffic separates two warps of a stream),
     # driven by the stream's own FlowNet flow field.
     warp_evs = []
+    warp_fused_ms = None
     if I > 1:
         h, w = H // 16, W // 16
         g = torch.Generator(device="cpu").manual_seed(7)
@@ -394,7 +395,20 @@ def run_native(a):
         w1.record()
         torch.cuda.synchronize()
         warp_evs = [w0.elapsed_time(w1) / n_warp]
-        del bufs, pairs
+        # the kernel the plans launch: accel_warp_split = warp_kernel_fused, which in the same pass also writes the
+        # split-fp16 NHWC operand the head's first conv loads (3 x 64 MiB algorithmic); same rotation, same flow field
+        his = [torch.empty(h, w, warp_c, dtype=torch.float16, device=dev) for _ in range(3)]
+        los = [torch.empty(h, w, warp_c, dtype=torch.float16, device=dev) for _ in range(3)]
+        for k in range(6):
+            E.warp_split(pairs[k % 3][0], flow_t, pairs[k % 3][1], his[k % 3], los[k % 3])
+        torch.cuda.synchronize()
+        w0.record()
+        for k in range(n_warp):
+            E.warp_split(pairs[k % 3][0], flow_t, pairs[k % 3][1], his[k % 3], los[k % 3])
+        w1.record()
+        torch.cuda.synchronize()
+        warp_fused_ms = w0.elapsed_time(w1) / n_warp
+        del bufs, pairs, his, los
         barrier()
 
     # e2e: HOST buffers in, HOST label maps out, through the public pipeline (scheduler.VideoPipeline): every
@@ -589,19 +603,31 @@ def run_native(a):
         # (the un-chained schedule has no consumer for `warping_feat_output`, but this kernel still writes the fp32
         # NCHW feature -- to the handle's scratch -- so the same bytes are counted)
         warp_avg_ms = sum(warp_evs) / len(warp_evs) if warp_evs else None
-        roofline = None
-        traffic = traffic_src = None
-        try:                                            # dram__bytes_read+write per launch from this round's ncu capture
+        roofline = roofline_op = None
+        traffic = traffic_src = f_traffic = f_src = None
+        try:                                            # dram__bytes_read+write per launch from this round's ncu captures
             tj = json.load(open(os.path.join(ROOT, "profiles", "r02_warp_traffic.json")))
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj.get("source")
+            f_traffic, f_src = tj["fused_kernel"]["traffic_bytes_per_launch"], tj["fused_kernel"].get("source")
         except Exception:
             pass
         if warp_avg_ms:
             ach = wb / (warp_avg_ms * 1e-3) / 1e9
-            roofline = {"kernel": "warp_kernel_staged", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
-                        "algorithmic_bytes_per_launch": wb, "avg_launch_ms": warp_avg_ms,
-                        "frac_of_8TBps_nominal": ach / 8000.0}
+            roofline_op = {"kernel": "warp_kernel_staged", "what": "operator accel_warp (fp32 NCHW in, fp32 NCHW out): SURVEY 8(d) bytes",
+                           "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                           "algorithmic_bytes_per_launch": wb, "avg_launch_ms": warp_avg_ms,
+                           "frac_of_8TBps_nominal": ach / 8000.0}
+        if warp_fused_ms:
+            fb = wb + (wb - 2 * (H // 16) * (W // 16) * 4) // 2       # + the split-fp16 NHWC head operand (hi + lo = 4 B / element)
+            ach = fb / (warp_fused_ms * 1e-3) / 1e9
+            roofline = {"kernel": "warp_kernel_fused", "what": "the warp launch of the timed plans (accel_warp_split): one pass writes the "
+                        "fp32 NCHW warped feature AND the split-fp16 NHWC operand of the head's first conv",
+                        "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": f_traffic, "traffic_source": f_src, "peak_kind": peak_kind,
+                        "algorithmic_bytes_per_launch": fb, "avg_launch_ms": warp_fused_ms, "frac_of_8TBps_nominal": ach / 8000.0}
+        elif roofline_op:
+            roofline = roofline_op
         scale = (H * W) / float(1024 * 2048)
         gflop_step = (GFLOP_KEY + (I - 1) * GFLOP_CUR[a.version]) * scale
         # a timed region under ~1 s runs at burst clocks: the burst cuBLAS figure is the apt denominator
@@ -635,7 +661,7 @@ def run_native(a):
                            "linear_head": bool(lin_main), "l2": "working set per step exceeds the 126 MB L2 (frames 24 MiB each, "
                            "features 64 MiB, activations > 1 GiB); no explicit flush"},
                 "gpu_launches": launches_main * a.steps, "launches_per_step": launches_main,
-                "roofline": roofline, "roofline_conv": conv,
+                "roofline": roofline, "roofline_warp_operator": roofline_op, "roofline_conv": conv,
                 "stage_ms_per_interval": {k: round(v, 4) for k, v in sorted(stage_ms.items())},
                 "stage_ms_note": "one untimed interval run eagerly, frame by frame, with CUDA events between ops: kernels that "
                                  "the graphs run concurrently (branches / lanes / lookahead / the interval plan's per-frame "

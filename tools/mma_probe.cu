@@ -1,0 +1,294 @@
+// tcgen05.mma issue-rate probe (sm_100a): what does ONE K=16 slice of the fp16x3 mainloop cost when nothing but the tensor
+// core (and, optionally, a TMA-like stream of bulk copies into the same shared memory) is running?
+//
+// Every SM runs one CTA (cta_group::1) or every TPC one CTA pair (cta_group::2).  One elected thread issues `iters` K
+// stages; a stage is 4 K=16 slices over a SWIZZLE_128B operand stage (like conv_tc_kernel's ring) and a slice is a fixed
+// PATTERN of up to 4 MMAs {A offset, B offset, N, D column}.  Operands are random fp16 values (power draw matters: the
+// clocks under load are part of the answer).  With `tma_kb` > 0 a second thread keeps `cp.async.bulk` copies of that many
+// KB per MMA stage flowing from an L2-resident buffer into a scratch ring, paced by the MMA thread's stage counter.
+// Output: cycles per slice (clock64 around the issue loop + final commit wait), averaged / min / max over CTAs.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_build/mma_probe tools/mma_probe.cu && tools/_build/mma_probe
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+struct Mma { int a_off, b_off, n, dcol; };
+struct Pattern {
+  const char* name;
+  int cg;            // cta_group
+  int nmma;
+  Mma m[4];
+  int stage_bytes;   // operand bytes per stage per CTA (ring stride)
+  int stages;
+  int tma_kb;        // KB of bulk copies per stage per CTA (0: none)
+};
+struct Params {
+  int nmma, stage_bytes, stages, iters, tma_bytes, scratch_off;
+  Mma m[4];
+  const uint8_t* src;
+};
+
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t a) {
+  return (uint64_t)((a & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+template <int CG>
+__device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (CG == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void commit(uint32_t bar) {
+  if (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// STYLE 0: `if (lane == 0)` around the whole issue loop (conv_tc_kernel as of round 2: every operand of every MMA goes
+//          through an ELECT / R2UR.BROADCAST waterfall because the compiler cannot prove it warp-uniform)
+// STYLE 1: the whole warp walks the loop convergently, descriptors live in uniform registers, only the tcgen05
+//          instructions are predicated on elect.sync
+template <int CG, int NM, int STYLE>
+__global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ Params P, long long* out, long long* out_tma) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[8];      // 0: done, 1..2: tma ring, 3..6: stage commits (sink)
+  __shared__ uint32_t tmem_slot;
+  __shared__ volatile int progress;              // MMA stages issued so far
+  const uint32_t smem0 = (saddr(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base = smem_raw + (smem0 - saddr(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // random small fp16 operands
+  {
+    const int total = P.stage_bytes * P.stages / 2;
+    __half* h = reinterpret_cast<__half*>(base);
+    uint32_t x = 1234567u + blockIdx.x * 7919u + threadIdx.x;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      x = x * 1664525u + 1013904223u;
+      h[i] = __float2half(((int)(x >> 9) % 2001 - 1000) * 1e-3f);
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(saddr(&bars[i]), i >= 3 ? (1u << 20) - 1u : 1u);
+    progress = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) {
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (CG == 2) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  else __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  const bool leader = CG == 1 || ctarank() == 0;
+  const uint32_t done = saddr(&bars[0]);
+
+  if (warp == 1 && leader && (STYLE == 1 || lane == 0)) {
+    const int M = CG == 1 ? 128 : 256;
+    uint32_t idesc[NM];
+#pragma unroll
+    for (int j = 0; j < NM; ++j) idesc[j] = (1u << 4) | ((uint32_t)(P.m[j].n >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const long long t0 = clock64();
+    int s = 0;
+    for (int it = 0; it < P.iters; ++it) {
+      const uint32_t sb = smem0 + (uint32_t)s * (uint32_t)P.stage_bytes;
+      const bool go = STYLE == 0 || elect_one();
+      if (go) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int j = 0; j < NM; ++j)
+            umma<CG>(tmem + (uint32_t)P.m[j].dcol, umma_desc(sb + P.m[j].a_off) + (uint64_t)(2 * k),
+                     umma_desc(sb + P.m[j].b_off) + (uint64_t)(2 * k), idesc[j], (it > 0 || k > 0) ? 1u : 0u);
+        }
+        commit<CG>(saddr(&bars[3 + (s & 3)]));        // like the ring's `empty` commit (nobody waits on it)
+        progress = it + 1;
+      }
+      if (STYLE == 1) __syncwarp();
+      if (++s == P.stages) s = 0;
+    }
+    const long long t_issue = clock64();
+    if (STYLE == 0 || elect_one()) commit<CG>(done);
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    if (lane == 0) {
+      out[2 * blockIdx.x] = t1 - t0;
+      out[2 * blockIdx.x + 1] = t_issue - t0;
+    }
+  } else if (warp == 2 && lane == 0 && P.tma_bytes > 0) {
+    // bulk-copy stream: tma_bytes per MMA stage, at most 2 stages ahead of the MMA thread's progress counter
+    const uint32_t scr = smem0 + (uint32_t)P.scratch_off;
+    long long moved = 0;
+    const long long tw0 = clock64();
+    uint32_t ph[2] = {0, 0};
+    int inflight = 0;
+    const uint8_t* src = P.src + (size_t)(blockIdx.x % 64) * (512 * 1024);
+    for (int it = 0; it < P.iters; ++it) {
+      if (leader) while (progress + 3 < it) {}
+      const int b = it & 1;
+      if (inflight == 2) { mbar_wait(saddr(&bars[1 + b]), ph[b]); ph[b] ^= 1; --inflight; }
+      mbar_expect(saddr(&bars[1 + b]), (uint32_t)P.tma_bytes);
+      for (int off = 0; off < P.tma_bytes; off += 16384) {
+        const int n = P.tma_bytes - off < 16384 ? P.tma_bytes - off : 16384;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         scr + (uint32_t)off),
+                     "l"(src + ((size_t)it * 65536 + off) % (448 * 1024)), "r"(n), "r"(saddr(&bars[1 + b]))
+                     : "memory");
+      }
+      ++inflight;
+      moved += P.tma_bytes;
+    }
+    while (inflight > 0) { const int b = (P.iters - inflight) & 1; mbar_wait(saddr(&bars[1 + b]), ph[b]); ph[b] ^= 1; --inflight; }
+    out_tma[blockIdx.x] = moved > 0 ? clock64() - tw0 : 0;
+  } else if (CG == 2 && warp == 1 && lane == 0 && !leader) {
+    mbar_wait(done, 0);                            // multicast commit: the peer sees completion too
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (CG == 2) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  else __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+int main() {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  const int sms = prop.multiProcessorCount;
+  const int K = 1024;
+  const int A = 16 * K;                       // one 128-row x 64-channel fp16 plane
+  // single CTA, BN = 128: stage = [A_hi | A_lo | B_hi | B_lo] = 64 KB
+  // pair,      BN = 128: stage = [A_hi | A_lo | B_hi half | B_lo half | dup] per CTA
+  const Pattern pats[] = {
+      {"cg1 N=256 alone", 1, 1, {{0, 2 * A, 256, 0}}, 4 * A, 2, 0},
+      {"cg1 N=128 alone", 1, 1, {{0, 2 * A, 128, 0}}, 4 * A, 2, 0},
+      {"cg1 N=64 alone", 1, 1, {{0, 2 * A, 64, 0}}, 4 * A, 2, 0},
+      {"cg1 N=32 alone", 1, 1, {{0, 2 * A, 32, 0}}, 4 * A, 2, 0},
+      {"cg1 NCAT BN=128 (N=256 hi x [hi;lo], N=128 lo x hi)", 1, 2, {{0, 2 * A, 256, 0}, {A, 2 * A, 128, 128}}, 4 * A, 3, 0},
+      {"cg1 NCAT BN=128 + 64 KB/stage bulk copies", 1, 2, {{0, 2 * A, 256, 0}, {A, 2 * A, 128, 128}}, 4 * A, 1, 64},
+      {"cg1 3 x N=128 (hh, hl, lh)", 1, 3, {{0, 2 * A, 128, 0}, {0, 3 * A, 128, 128}, {A, 2 * A, 128, 128}}, 4 * A, 3, 0},
+      {"cg1 3 x N=256 (BN=256)", 1, 3, {{0, 2 * A, 256, 0}, {0, 4 * A, 256, 0}, {A, 2 * A, 256, 0}}, 6 * A, 2, 0},
+      {"cg1 3 x N=256 + 96 KB/stage bulk copies", 1, 3, {{0, 2 * A, 256, 0}, {0, 4 * A, 256, 0}, {A, 2 * A, 256, 0}}, 6 * A, 1, 96},
+      {"cg1 NCAT BN=64 (N=128, N=64)", 1, 2, {{0, 2 * A, 128, 0}, {A, 2 * A, 64, 64}}, 3 * A, 3, 0},
+      {"cg2 M=256 N=256 alone", 2, 1, {{0, 2 * A, 256, 0}}, 3 * A, 2, 0},
+      {"cg2 M=256 N=128 alone", 2, 1, {{0, 2 * A, 128, 0}}, 3 * A, 2, 0},
+      {"cg2 M=256 N=64 alone", 2, 1, {{0, 2 * A, 64, 0}}, 3 * A, 2, 0},
+      {"cg2 3 x N=128, pair tile 256 x 128 (hh | hl+lh apart)", 2, 3,
+       {{0, 2 * A, 128, 0}, {0, 2 * A + A / 2, 128, 128}, {A, 2 * A, 128, 128}}, 3 * A, 3, 0},
+      {"cg2 3 x N=128 + 48 KB/stage bulk copies", 2, 3,
+       {{0, 2 * A, 128, 0}, {0, 2 * A + A / 2, 128, 128}, {A, 2 * A, 128, 128}}, 3 * A, 1, 48},
+      {"cg2 NCAT pair 256 x 128 (N=256 + N=128 on a duplicate half)", 2, 2, {{0, 2 * A, 256, 0}, {A, 3 * A, 128, 64}}, 3 * A + A / 2, 3, 0},
+      {"cg2 NCAT pair + 56 KB/stage bulk copies", 2, 2, {{0, 2 * A, 256, 0}, {A, 3 * A, 128, 64}}, 3 * A + A / 2, 1, 56},
+      {"cg2 3 x N=256, pair tile 256 x 256", 2, 3, {{0, 2 * A, 256, 0}, {0, 3 * A, 256, 0}, {A, 2 * A, 256, 0}}, 4 * A, 3, 0},
+      {"cg2 3 x N=256 + 64 KB/stage bulk copies", 2, 3, {{0, 2 * A, 256, 0}, {0, 3 * A, 256, 0}, {A, 2 * A, 256, 0}}, 4 * A, 1, 64},
+      {"cg2 2 x N=256 (256 x 256: hh | hl+lh apart needs 512 cols)", 2, 3,
+       {{0, 2 * A, 256, 0}, {0, 3 * A, 256, 256}, {A, 2 * A, 256, 256}}, 4 * A, 3, 0},
+  };
+  const int npat = sizeof(pats) / sizeof(pats[0]);
+  const int iters = 400;
+  long long *d_out, *d_tma;
+  uint8_t* d_src;
+  CK(cudaMalloc(&d_out, sizeof(long long) * 2 * sms));
+  CK(cudaMalloc(&d_tma, sizeof(long long) * sms));
+  CK(cudaMalloc(&d_src, 64 * 512 * 1024));
+  CK(cudaMemset(d_src, 0x11, 64 * 512 * 1024));
+  const int smem = 220 * 1024;
+  long long* h = (long long*)malloc(sizeof(long long) * 2 * sms);
+  long long* ht = (long long*)malloc(sizeof(long long) * sms);
+  printf("%d SMs, %d stages of 4 K=16 slices per CTA; cycles are per slice\n", sms, iters);
+  printf("%-62s %8s %8s %8s %8s %9s %8s\n", "pattern", "avg", "min", "max", "issue", "wall_us", "MHz");
+  for (int pi = 0; pi < 2 * npat; ++pi) {
+    const Pattern& pt = pats[pi % npat];
+    const int style = pi / npat;
+    if (pi == npat) printf("---- STYLE 1: convergent warp, elect.sync around the tcgen05 instructions ----\n");
+    void (*kern)(const Params, long long*, long long*) = nullptr;
+#define PICK(CGv, NMv) if (pt.cg == CGv && pt.nmma == NMv) kern = style ? probe<CGv, NMv, 1> : probe<CGv, NMv, 0>;
+    PICK(1, 1) PICK(1, 2) PICK(1, 3) PICK(2, 1) PICK(2, 2) PICK(2, 3)
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    Params P;
+    memset(&P, 0, sizeof(P));
+    P.nmma = pt.nmma; P.stage_bytes = pt.stage_bytes; P.stages = pt.stages; P.iters = iters;
+    P.tma_bytes = pt.tma_kb * 1024;
+    P.scratch_off = ((pt.stage_bytes * pt.stages + 1023) / 1024) * 1024;
+    if (P.tma_bytes > 0 && P.scratch_off + P.tma_bytes > smem - 1024) { printf("%s: no room for the scratch slot\n", pt.name); continue; }
+    memcpy(P.m, pt.m, sizeof(P.m));
+    P.src = d_src;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaMemset(d_tma, 0, sizeof(long long) * sms));
+      CK(cudaEventRecord(e0));
+      if (pt.cg == 1) {
+        kern<<<sms, 128, smem>>>(P, d_out, d_tma);
+      } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sms / 2 * 2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, kern, P, d_out, d_tma));
+      }
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms < best) best = ms;
+    }
+    CK(cudaMemcpy(h, d_out, sizeof(long long) * 2 * sms, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ht, d_tma, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    double sum = 0, isum = 0; long long mn = 1ll << 60, mx = 0; int n = 0;
+    for (int b = 0; b < sms / pt.cg * pt.cg; b += pt.cg) { sum += h[2 * b]; isum += h[2 * b + 1]; if (h[2 * b] < mn) mn = h[2 * b]; if (h[2 * b] > mx) mx = h[2 * b]; ++n; }
+    const double slices = iters * 4.0;
+    const double avg = sum / n / slices;
+    printf("%-62s %8.1f %8.1f %8.1f %8.1f %9.1f %8.0f", pt.name, avg, mn / slices, mx / slices, isum / n / slices, best * 1e3,
+           (sum / n) / (best * 1e3));
+    if (pt.tma_kb) printf("   bulk stream: %.1f cycles per stage = %.1f B/cycle", ht[0] / (double)iters, pt.tma_kb * 1024.0 * iters / ht[0]);
+    printf("\n");
+  }
+  return 0;
+}
