@@ -21,11 +21,15 @@ def _stale(obj, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, trace=False):
+    """trace=True: a second library, libaccel_b200_trace.so, with conv_tc_kernel's in-kernel timeline compiled in
+    (tools/tc_trace.py selects it through ACCEL_B200_LIB)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "accel_b200.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_trace" if trace else "build")
+    lib = LIB.replace(".so", "_trace.so") if trace else LIB
+    flags = NVCC_FLAGS + (["-DACCEL_TC_TRACE_BUILD"] if trace else [])
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []
     for src in SOURCES:
@@ -33,7 +37,7 @@ def build(verbose=False, force=False):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [path] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -43,11 +47,11 @@ def build(verbose=False, force=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if procs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart"]
+    if procs or not os.path.exists(lib):
+        cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", lib] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, trace="--trace" in sys.argv))

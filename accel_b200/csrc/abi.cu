@@ -490,6 +490,12 @@ extern "C" int accel_conv_layer(int kind, const float* in, int cin, int hin, int
       double ms = 0.0, fl = 0.0;
       for (auto& o : best)
         if (o.flops > 0) { ms += o.ms; fl += o.flops; }
+      if (getenv("ACCEL_TC_TRACE")) {                       // one more run with a clean trace buffer, then the timeline of CTA 0
+        tc_trace_reset();
+        if (!g.run("layer", ext, 0, &msg)) return fail(msg, 1);
+        cudaDeviceSynchronize();
+        tc_trace_dump(stderr);
+      }
       fprintf(stderr, "ACCEL_LAYER kind=%d cin=%d cout=%d hw=%dx%d k=%d s=%d: %.2f us, %.2f GF, %.1f TF16/s\n", kind, cin, cout, hin,
               win, ksize, stride, ms * 1e3, fl / 1e9, ms > 0 ? 3.0 * fl / (ms * 1e-3) / 1e12 : 0.0);
     }

@@ -88,10 +88,32 @@ __device__ __forceinline__ uint64_t umma_desc_rows(uint32_t saddr, int mode) {
   return tc::umma_desc(saddr) | ((uint64_t)((saddr >> 7) & 7u) << 49);
 }
 
+// In-kernel timeline of CTA 0 (ACCEL_TC_DEBUG bit 2048, tools/bench_layer.py --trace): (tag, item, clock64) records.
+//   0 start | 1 producer: first TMA of the item  2 last TMA | 3 MMA warp: accumulators free  4 first stage landed
+//   5 last MMA + commit issued | 6 epilogue warp 2: item prologue done, waiting for the accumulator  7 accumulator
+//   complete  8 chunk loop done, accumulator released | 9 end
+// Compiled in only with -DACCEL_TC_TRACE_BUILD (`python accel_b200/build.py --trace` -> libaccel_b200_trace.so): the extra
+// code in the role loops costs a few percent on short-K layers.
+__device__ long long g_tc_trace[3 * 2048];
+__device__ unsigned g_tc_trace_n;
+#ifndef ACCEL_TC_TRACE_BUILD
+#define TC_TRACE(tag, item) do { } while (0)
+#else
+#define TC_TRACE(tag, item)                                                              \
+  do {                                                                                   \
+    if ((P.debug & 2048) && blockIdx.x == 0 && lane == 0) {                              \
+      const unsigned ti_ = atomicAdd(&g_tc_trace_n, 1u);                                 \
+      if (ti_ < 2048u) { g_tc_trace[3 * ti_] = (tag); g_tc_trace[3 * ti_ + 1] = (item); g_tc_trace[3 * ti_ + 2] = clock64(); } \
+    }                                                                                    \
+  } while (0)
+#endif
+
 // NCAT: hi*hi and hi*lo issued as ONE MMA over [B_hi ; B_lo] (N = 2*BN <= 256), see the MMA issuer.
 // FUSED: in-kernel split-K tail (TcParams::fused); a template parameter so that the default instantiations keep their
 // register allocation.
-template <bool NCAT, bool FUSED = false>
+// TWO: two accumulation chains (TcParams::kchains == 2): a template parameter so that the ordinary instantiations do not
+// carry the registers of the folded first half, and the two-chain ones do not carry the residual prefetch registers.
+template <bool NCAT, bool FUSED = false, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
@@ -145,6 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int tiles = P.tiles_x * P.tiles_y * P.n_tiles;
   const int items = tiles * P.splits;
+  if (warp == 0) TC_TRACE(0, 0);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -205,6 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t sa = smem0 + s * stage_bytes;
           const int dy = P.dy[t], dx = P.dx[t];
           const int kcol = t * P.Cin_pad + kc * BK;
+          if (i == kb) TC_TRACE(1, item);
+          if (i == ke - 1) TC_TRACE(2, item);
           if (elect_one()) {
             mbar_arrive_expect_tx(fb, tx);
             if (!ldA) {
@@ -238,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * P.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
-      const bool two = P.kchains == 2;
+      constexpr bool two = TWO;
       const bool no_mma = (P.debug & 128) != 0;
       const uint32_t bn = (uint32_t)P.BN;
       int s = 0, acc = 0;
@@ -249,89 +274,78 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int split = item % P.splits;
         const int kb = (int)(((long long)P.kiters * split) / P.splits);
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
-        if (two) {
-          mbar_wait(tempty0, accph ^ 1);
-          mbar_wait(tempty0 + 8, accph ^ 1);
-        } else {
+        // two chains (TcParams::kchains): the first half of the item's K stages accumulates in TMEM buffer 0, the second half in
+        // buffer 1 -- each with the ordinary double-buffer protocol, so the epilogue warps fold buffer 0 into registers while
+        // the second half still runs, and the next item's first half starts as soon as its MMAs are issued.
+        const int kmid = two ? kb + (ke - kb + 1) / 2 : ke;
+        for (int half = 0; half < (two ? 2 : 1); ++half) {
+          const int hb = half ? kmid : kb, he = half ? ke : kmid;
           mbar_wait(tempty0 + 8 * acc, accph ^ 1);
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // two chains: even slices accumulate in buffer 0, odd slices in buffer 1 (half the steps and half the magnitude
-        // per accumulator); the epilogue adds the buffers in fp32
-        const uint32_t d0 = tmem_base + (two ? 0u : (uint32_t)acc * acc_cols);
-        const uint32_t d1 = two ? tmem_base + acc_cols : d0;
-        for (int it = kb; it < ke; ++it) {
-          uint32_t a_hi, a_lo, b_hi, b_lo;
-          int slab_mode = 0;
-          bool slab_done = false;
-          if (P.aslab) {
-            const int outer = it / P.ndx, i = it - outer * P.ndx;
-            const int t = (outer / P.chunks) * P.ndx + i;
-            if (i == 0 || it == kb) {
-              cur = nas;
-              mbar_wait(afull0 + 8 * cur, aphc);
-              if (++nas == P.sa_stages) { nas = 0; aphc ^= 1; }
-            }
-            slab_done = i == P.ndx - 1 || it == ke - 1;
-            a_hi = smem0 + (uint32_t)cur * 2u * (uint32_t)P.slab_pl + (uint32_t)(P.dx[t] - P.dxmin) * 128u;
-            a_lo = a_hi + (uint32_t)P.slab_pl;
-            b_hi = bring0 + (uint32_t)s * 2u * b_bytes;
-            b_lo = b_hi + b_bytes;
-            slab_mode = 1;
-          } else {
-            a_hi = smem0 + s * stage_bytes;
-            a_lo = a_hi + a_bytes;
-            b_hi = a_hi + 2 * a_bytes;
-            b_lo = b_hi + b_bytes;
-          }
-          mbar_wait(full0 + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t ah = slab_mode ? umma_desc_rows(a_hi, P.slab_bo) : umma_desc(a_hi);
-          const uint64_t al = slab_mode ? umma_desc_rows(a_lo, P.slab_bo) : umma_desc(a_lo);
-          const uint64_t bh = umma_desc(b_hi), bl = umma_desc(b_lo);
-          const uint32_t first0 = it > kb ? 1u : 0u;        // slice 0 (chain 0) / slice 1 (chain 1, or chain 0 again) of this stage
-          if (elect_one()) {
-            if (!no_mma) {
+          if (half == 0) TC_TRACE(3, item);
+          const uint32_t d = tmem_base + (uint32_t)acc * acc_cols;
+          for (int it = hb; it < he; ++it) {
+            uint32_t a_hi, a_lo, b_hi, b_lo;
+            int slab_mode = 0;
+            bool slab_done = false;
+            if (P.aslab) {
+              const int outer = it / P.ndx, i = it - outer * P.ndx;
+              const int t = (outer / P.chunks) * P.ndx + i;
+              if (i == 0 || it == kb) {
+                cur = nas;
+                mbar_wait(afull0 + 8 * cur, aphc);
+                if (++nas == P.sa_stages) { nas = 0; aphc ^= 1; }
+              }
+              slab_done = i == P.ndx - 1 || it == ke - 1;
+              a_hi = smem0 + (uint32_t)cur * 2u * (uint32_t)P.slab_pl + (uint32_t)(P.dx[t] - P.dxmin) * 128u;
+              a_lo = a_hi + (uint32_t)P.slab_pl;
+              b_hi = bring0 + (uint32_t)s * 2u * b_bytes;
+              b_lo = b_hi + b_bytes;
+              slab_mode = 1;
+            } else {
+              a_hi = smem0 + s * stage_bytes;
+              a_lo = a_hi + a_bytes;
+              b_hi = a_hi + 2 * a_bytes;
+              b_lo = b_hi + b_bytes;
+            }
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (it == kb) TC_TRACE(4, item);
+            const uint64_t ah = slab_mode ? umma_desc_rows(a_hi, P.slab_bo) : umma_desc(a_hi);
+            const uint64_t al = slab_mode ? umma_desc_rows(a_lo, P.slab_bo) : umma_desc(a_lo);
+            const uint64_t bh = umma_desc(b_hi), bl = umma_desc(b_lo);
+            const uint32_t first0 = it > hb ? 1u : 0u;
+            if (elect_one()) {
+              if (!no_mma) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint64_t adv = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes along K inside the swizzle atom
-                const uint32_t d = (k & 1) ? d1 : d0;         // BK / 16 is even: a stage's slices alternate d0, d1, d0, d1
-                const uint32_t first = two ? (k >= 2 ? 1u : first0) : (k >= 1 ? 1u : first0);
-                if (NCAT) {
-                  // B_hi and B_lo are adjacent in the stage with one row pitch: a single N = 2*BN operand.  Columns
-                  // [0, BN) collect hi*hi, columns [BN, 2BN) collect hi*lo and -- issued into the upper half alone --
-                  // lo*hi: the small cross terms never touch the big accumulator, whose truncating additions are the
-                  // dominant rounding error.  The tensor core reads the A_hi slice once and issues two instructions.
-                  umma_f16(d, ah + adv, bh + adv, idesc2, first);
-                  umma_f16(d + bn, al + adv, bh + adv, idesc, 1u);
-                } else {
-                  umma_f16(d, ah + adv, bh + adv, idesc, first);
-                  umma_f16(d, ah + adv, bl + adv, idesc, 1u);
-                  umma_f16(d, al + adv, bh + adv, idesc, 1u);
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint64_t adv = (uint64_t)(k * 2);       // 16 fp16 = 32 bytes along K inside the swizzle atom
+                  const uint32_t first = k >= 1 ? 1u : first0;
+                  if (NCAT) {
+                    // B_hi and B_lo are adjacent in the stage with one row pitch: a single N = 2*BN operand.  Columns
+                    // [0, BN) collect hi*hi, columns [BN, 2BN) collect hi*lo and -- issued into the upper half alone --
+                    // lo*hi: the small cross terms never touch the big accumulator, whose truncating additions are the
+                    // dominant rounding error.  The tensor core reads the A_hi slice once and issues two instructions.
+                    umma_f16(d, ah + adv, bh + adv, idesc2, first);
+                    umma_f16(d + bn, al + adv, bh + adv, idesc, 1u);
+                  } else {
+                    umma_f16(d, ah + adv, bh + adv, idesc, first);
+                    umma_f16(d, ah + adv, bl + adv, idesc, 1u);
+                    umma_f16(d, al + adv, bh + adv, idesc, 1u);
+                  }
                 }
               }
+              umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
+              if (slab_done) umma_commit(aempty0 + 8 * cur);  // ... and the A slab after the last tap that reads it
             }
-            umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
-            if (slab_done) umma_commit(aempty0 + 8 * cur);  // ... and the A slab after the last tap that reads it
+            __syncwarp();
+            if (++s == P.stages) { s = 0; ph ^= 1; }
           }
+          if (elect_one()) umma_commit(tfull0 + 8 * acc);     // accumulator complete -> epilogue
           __syncwarp();
-          if (++s == P.stages) { s = 0; ph ^= 1; }
+          if (++acc == 2) { acc = 0; accph ^= 1; }
         }
-        if (elect_one()) {
-          if (two) {
-            umma_commit(tfull0);                            // both accumulators complete -> epilogue
-            umma_commit(tfull0 + 8);
-          } else {
-            umma_commit(tfull0 + 8 * acc);                  // accumulator complete -> epilogue
-          }
-        }
-        __syncwarp();
-        if (two) {
-          accph ^= 1;
-        } else if (++acc == 2) {
-          acc = 0;
-          accph ^= 1;
-        }
+        TC_TRACE(5, item);
       }
     }
   } else if (warp >= 2 + kEpiWarps) {
@@ -411,7 +425,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool has_res = E.res_hi != nullptr && !(P.debug & 16);
       const uint32_t sb0 = stg0 + (uint32_t)cset * 2u * 16384u;
       const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]), sbar0 = smem_u32(&stg_bars[cset * 2]);
-      const bool two = P.kchains == 2;
       const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
       int acc = 0, sci = 0, n = 0;                          // sci: scale/shift staging slot, alternates per item
       uint32_t accph = 0;
@@ -439,14 +452,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         if (item + (int)gridDim.x < items) fetch_sc(item + gridDim.x);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (two) {
-          mbar_wait(tfull0, accph);
-          mbar_wait(tfull0 + 8, accph);
-        } else {
-          mbar_wait(tfull0 + 8 * acc, accph);
-        }
+        if (warp == 2) TC_TRACE(6, item);
+        mbar_wait(tfull0 + 8 * acc, accph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (two ? 0u : (uint32_t)acc * acc_cols);
+        if (warp == 2) TC_TRACE(7, item);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols;
         for (int cc = cset * 32; cc < P.BN; cc += 64, ++n) {
           const int b = n & 1;
           const uint32_t sb = sb0 + (uint32_t)b * 16384u;
@@ -456,21 +466,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           } else {
           tmem_ld32(taddr + cc, v);
-          if (two) {                                         // second chain's big half first: big + big, then the small halves
-            float v2[32];
-            tmem_ld32(taddr + acc_cols + cc, v2);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += v2[i];
-          }
           if (NCAT) {
             float v2[32];
             tmem_ld32(taddr + P.BN + cc, v2);
-            if (two) {
-              float v3[32];
-              tmem_ld32(taddr + acc_cols + P.BN + cc, v3);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v2[i] += v3[i];
-            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
           }
@@ -500,14 +498,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
+        if (warp == 2) TC_TRACE(8, item);
         sci ^= 1;
-        if (two) {
-          if (lane == 0) { mbar_arrive(tempty0); mbar_arrive(tempty0 + 8); }
-          accph ^= 1;
-        } else {
-          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-          if (++acc == 2) { acc = 0; accph ^= 1; }
-        }
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
       }
     } else {
     // ===================================== epilogue ==========================================
@@ -523,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int npix = P.Ho * P.Wo;
     const int et = threadIdx.x - 64;                       // 0 .. 255 among the epilogue threads
     const Epilogue& E = P.epi;
-    const bool two = P.kchains == 2;
+    constexpr bool two = TWO;
     const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
     int acc = 0, sci = 0;                                  // sci: scale/shift staging slot, alternates per item
     uint32_t accph = 0;
@@ -547,14 +541,82 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (cset * 32 + 64 < P.BN && nbase + cset * 32 + 96 <= E.Cout) load_res(E, pix, nbase + cset * 32 + 64, rc1);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");       // scale/shift visible to all epilogue warps
-      if (two) {
+      if (warp == 2) TC_TRACE(6, item);
+      if constexpr (two) {
+        // Two chains = two K halves in TMEM buffers 0 and 1 (see the MMA issuer).  Buffer 0 is folded into registers and
+        // released while the second half is still being accumulated; buffer 1 is added on top when it completes.  At most
+        // two 32-channel chunks per thread (BN <= 128, guaranteed by the plan).
+        const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float part[2][32];
         mbar_wait(tfull0, accph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == 2) TC_TRACE(7, item);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int cc = cset * 32 + j * 64;
+          if (cc < P.BN && nbase + cc < P.Cout_pad) {
+            tmem_ld32(tq + cc, part[j]);
+            if (NCAT) {
+              float xt[32];
+              tmem_ld32(tq + P.BN + cc, xt);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) part[j][i] += xt[i];
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0);
         mbar_wait(tfull0 + 8, accph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int cc = cset * 32 + j * 64;
+          const int n0 = nbase + cc;
+          if (cc < P.BN && n0 < P.Cout_pad) {
+            float v[32];
+            tmem_ld32(tq + acc_cols + cc, v);
+            if (NCAT) {
+              float xt[32];
+              tmem_ld32(tq + acc_cols + P.BN + cc, xt);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += xt[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += part[j][i];
+            if (valid && !(P.debug & 1)) {
+              if (P.splits > 1) {
+                float4* dst = reinterpret_cast<float4*>(P.partial + ((size_t)split * npix + (size_t)y * P.Wo + x) * P.Cout_pad + n0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              } else if (P.vec32 && n0 + 32 <= E.Cout) {
+                ResChunk rc{};
+                if (use_res) load_res(E, pix, n0, rc);
+                epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[sci][0][cc], &epi_sc[sci][1][cc]);
+              } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if (n0 + g * 8 < E.Cout) epilogue_store<8>(E, pix, n0 + g * 8, v + g * 8);
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (warp == 2) TC_TRACE(8, item);
+        sci ^= 1;
+        if (lane == 0) mbar_arrive(tempty0 + 8);
+        accph ^= 1;
       } else {
-        mbar_wait(tfull0 + 8 * acc, accph);
+      ResChunk rc{}, rc1{};
+      if (use_res && valid) {
+        if (nbase + cset * 32 + 32 <= E.Cout) load_res(E, pix, nbase + cset * 32, rc);
+        if (cset * 32 + 64 < P.BN && nbase + cset * 32 + 96 <= E.Cout) load_res(E, pix, nbase + cset * 32 + 64, rc1);
       }
+      mbar_wait(tfull0 + 8 * acc, accph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (two ? 0u : (uint32_t)acc * acc_cols);
+      if (warp == 2) TC_TRACE(7, item);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols;
       for (int cc = cset * 32; cc < P.BN; cc += 64) {
         const int n0 = nbase + cc;
         if (n0 >= P.Cout_pad) break;
@@ -564,21 +626,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int i = 0; i < 32; ++i) v[i] = 1.f;
         } else {
           tmem_ld32(taddr + cc, v);
-          if (two) {
-            float v2[32];
-            tmem_ld32(taddr + acc_cols + cc, v2);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += v2[i];
-          }
           if (NCAT) {
             float v2[32];
             tmem_ld32(taddr + P.BN + cc, v2);
-            if (two) {
-              float v3[32];
-              tmem_ld32(taddr + acc_cols + P.BN + cc, v3);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v2[i] += v3[i];
-            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
           }
@@ -604,13 +654,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
+      if (warp == 2) TC_TRACE(8, item);
       sci ^= 1;
-      if (two) {
-        if (lane == 0) { mbar_arrive(tempty0); mbar_arrive(tempty0 + 8); }
-        accph ^= 1;
-      } else {
-        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-        if (++acc == 2) { acc = 0; accph ^= 1; }
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; accph ^= 1; }
       }
       if (FUSED) {
         // Deterministic in-kernel split-K tail (the threadFenceReduction pattern): every epilogue thread fences its
@@ -658,6 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (warp == 0) TC_TRACE(9, 0);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
@@ -1118,7 +1166,9 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     const bool want = mode == 2 || (mode < 0 && kps >= env_int("ACCEL_TC_CHAINS_MIN", 6) &&
                                     (single_wave || kps >= env_int("ACCEL_TC_CHAINS_MULTI_MIN", 16) ||
                                      env_int("ACCEL_TC_CHAINS_MULTI", 0) != 0));
-    P.kchains = (want && !P.pair && mode != 0 && mode != 1) ? 2 : 1;
+    // (the epilogue folds the first half into registers: at most two 32-channel chunks per thread, i.e. BN <= 128, and
+    // at least one K stage per half; the TMA epilogue -- short-K layers -- never combines with it, see below)
+    P.kchains = (want && !P.pair && mode != 0 && mode != 1 && bn <= 128 && kps >= 2 && P.kiters / splits >= 2) ? 2 : 1;
   }
   {
     auto al32 = [](const void* p) { return ((uintptr_t)p & 31) == 0; };
@@ -1194,15 +1244,19 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
       P.tma_out = 2;
     }
   }
+  if (P.tma_out) P.kchains = 1;
   if (!ok) {
     delete plan;
     return nullptr;
   }
   if (first_time_on_device(ONCE_CONV_TC)) {
-    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    cudaError_t ce = cudaSuccess;
+    const void* fns[8] = {(const void*)conv_tc_kernel<false, false, false>, (const void*)conv_tc_kernel<true, false, false>,
+                          (const void*)conv_tc_kernel<false, true, false>,  (const void*)conv_tc_kernel<true, true, false>,
+                          (const void*)conv_tc_kernel<false, false, true>,  (const void*)conv_tc_kernel<true, false, true>,
+                          (const void*)conv_tc_kernel<false, true, true>,   (const void*)conv_tc_kernel<true, true, true>};
+    for (int i = 0; i < 8 && ce == cudaSuccess; ++i)
+      ce = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -1211,6 +1265,26 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     }
   }
   return plan;
+}
+
+// Prints the timeline CTA 0 recorded during the LAST launch with ACCEL_TC_DEBUG bit 2048 (cycles relative to the start tag)
+// and clears it.  Tuning aid, called by accel_conv_layer when ACCEL_TC_TRACE is set.
+void tc_trace_dump(FILE* f) {
+  unsigned n = 0;
+  if (cudaMemcpyFromSymbol(&n, g_tc_trace_n, sizeof(n)) != cudaSuccess) return;
+  if (n > 2048u) n = 2048u;
+  static long long host[3 * 2048];
+  if (n && cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(long long) * 3 * n) != cudaSuccess) return;
+  long long t0 = 0;
+  for (unsigned i = 0; i < n; ++i)
+    if (host[3 * i] == 0) t0 = host[3 * i + 2];
+  for (unsigned i = 0; i < n; ++i) fprintf(f, "TC_TRACE tag %lld item %lld t %lld\n", host[3 * i], host[3 * i + 1], host[3 * i + 2] - t0);
+  n = 0;
+  cudaMemcpyToSymbol(g_tc_trace_n, &n, sizeof(n));
+}
+void tc_trace_reset() {
+  unsigned n = 0;
+  cudaMemcpyToSymbol(g_tc_trace_n, &n, sizeof(n));
 }
 
 void tc_plan_destroy(TcPlan* plan) { delete plan; }
@@ -1230,11 +1304,16 @@ cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_r
   TcParams P = plan->p;
   if (ext_nchw) P.epi.out_nchw = ext_nchw;
   P.epi.raw_nchw = ext_raw;
-  cudaError_t e = P.pair ? launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P)
-                  : P.fused ? (P.ncat ? launch_k(conv_tc_kernel<true, true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
-                                      : launch_k(conv_tc_kernel<false, true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P))
-                  : P.ncat ? launch_k(conv_tc_kernel<true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P)
-                           : launch_k(conv_tc_kernel<false>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, P);
+  cudaError_t e;
+  const dim3 grid(plan->grid), block(kThreads);
+#define ACCEL_TC_LAUNCH(N_, F_, T_) launch_k(conv_tc_kernel<N_, F_, T_>, grid, block, plan->smem, stream, P)
+  const bool two = P.kchains == 2;
+  if (P.pair) e = launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P);
+  else if (P.fused) e = P.ncat ? (two ? ACCEL_TC_LAUNCH(true, true, true) : ACCEL_TC_LAUNCH(true, true, false))
+                               : (two ? ACCEL_TC_LAUNCH(false, true, true) : ACCEL_TC_LAUNCH(false, true, false));
+  else e = P.ncat ? (two ? ACCEL_TC_LAUNCH(true, false, true) : ACCEL_TC_LAUNCH(true, false, false))
+                  : (two ? ACCEL_TC_LAUNCH(false, false, true) : ACCEL_TC_LAUNCH(false, false, false));
+#undef ACCEL_TC_LAUNCH
   if (e != cudaSuccess) return e;
   if (P.splits > 1 && !P.fused) return launch_splitk_epilogue(P.partial, P.splits, P.Ho * P.Wo, P.Cout_pad, P.Wo, P.epi, stream);
   return cudaSuccess;

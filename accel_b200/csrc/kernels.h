@@ -1,6 +1,7 @@
 // Host-callable launchers for the hot-path kernels.  Internal to the library (the public surface is
 // include/accel_b200.h).
 #pragma once
+#include <stdio.h>
 #include <vector>
 
 #include "common.cuh"
@@ -19,6 +20,8 @@ bool tc_supported(const ConvParams& P);
 bool tc_batchable(const ConvParams& P);   // P.nb frames in one launch (frames stacked along H)?
 TcPlan* tc_plan_create(const ConvParams& P, int num_sms, char* err, int errlen);
 void tc_plan_destroy(TcPlan* plan);
+void tc_trace_dump(FILE* f);      // tuning aid: timeline of CTA 0 (ACCEL_TC_DEBUG bit 2048)
+void tc_trace_reset();
 size_t tc_plan_partial_bytes(const TcPlan* plan);
 void tc_plan_set_partial(TcPlan* plan, float* partial);
 // ext_nchw: optional fp32 NCHW destination that replaces the plan's epilogue out_nchw for this launch

@@ -40,6 +40,7 @@ LAYERS = {
     "res3_2a_x5": (512, 128, 640, 256, 1, 1, 0, 1, False),
     "res3_2a": (512, 128, 128, 256, 1, 1, 0, 1, False),
     "res3_2b_x5": (128, 128, 640, 256, 3, 1, 1, 1, False),
+    "res2_2b_x5": (64, 64, 1280, 512, 3, 1, 1, 1, False),
     "res4_2a_x5": (1024, 256, 320, 128, 1, 1, 0, 1, False),
     "res4_2b_x5": (256, 256, 320, 128, 3, 1, 1, 1, False),
     "res4_2c_x5": (256, 1024, 320, 128, 1, 1, 0, 1, True),
@@ -116,6 +117,12 @@ LD_SWEEP = [{}] + [{"ACCEL_TC_DEBUG": str(b)} for b in (128, 240, 240 + 256, 240
 EPI2_SWEEP = [{}] + [{"ACCEL_TC_DEBUG": str(b)} for b in (16, 32, 64, 128, 48, 112, 240, 128 + 16, 128 + 32, 128 + 64)]
 
 
+S2_SWEEP = [{}, {"ACCEL_TC_CHAINS": "0"}, {"ACCEL_TC_TMA_OUT": "1"}, {"ACCEL_TC_TMA_OUT": "1", "ACCEL_TC_CHAINS": "0"},
+            {"ACCEL_TC_ASLAB": "1"}, {"ACCEL_TC_ASLAB": "1", "ACCEL_TC_ASLAB_SA": "3"}, {"ACCEL_TC_BN": "64"},
+            {"ACCEL_TC_DEBUG": "128"}, {"ACCEL_TC_DEBUG": "256"}, {"ACCEL_TC_DEBUG": "384"}, {"ACCEL_TC_DEBUG": "391"},
+            {"ACCEL_TC_DEBUG": "391", "ACCEL_TC_CHAINS": "0"}, {"ACCEL_TC_DEBUG": "7"}, {"ACCEL_TC_DEBUG": "1"}]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--set", default="")
@@ -133,7 +140,12 @@ def main():
         ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
         wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
         r = torch.randn(1, cout, ho, wo, generator=g).to(dev) if res else None
-        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP, "pair2": PAIR2_SWEEP, "shortk": SHORTK_SWEEP}.get(a.sweep, SWEEP):
+        if a.sweep == "env":                      # whatever the caller's environment says, untouched (tools/tc_trace.py)
+            sys.stderr.write("%-14s env " % name)
+            sys.stderr.flush()
+            E.conv_layer(x, wt, "conv", s, p, d, act=1, residual=r, engine=2)
+            continue
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP, "pair2": PAIR2_SWEEP, "shortk": SHORTK_SWEEP, "s2": S2_SWEEP, "env": None}.get(a.sweep, SWEEP):
             for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR", "ACCEL_TC_ASLAB",
                        "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO", "ACCEL_TC_RES_PREFETCH", "ACCEL_TC_NCAT", "ACCEL_TC_WIDE_KMAX"):
                 os.environ.pop(kk, None)

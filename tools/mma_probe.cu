@@ -193,6 +193,111 @@ __global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ Params P
   }
 }
 
+
+// ---- ring skeleton: the conv kernel's producer <-> MMA-issuer barrier protocol with nothing loaded ----------------------
+// warp 0 = producer (waits empty[s], arrives full[s] with 0 bytes), warp 1 = MMA issuer (waits full[s], issues the NCAT
+// slice pattern x4 or nothing, commits empty[s]), `pollers` further warps wait on a barrier that only completes at the end
+// (what the epilogue warps do during a tile's mainloop).  poll_mode 0: all 32 lanes spin on try_wait; 1: lane 0 only;
+// 2: lane 0 with a nanosleep back-off.
+struct RingParams { int stages, iters, do_mma, pollers, poll_mode, stage_bytes; };
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(384, 1) ring_probe(const __grid_constant__ RingParams P, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[16];     // 0..5 full, 6..11 empty, 12 done
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem0 = (saddr(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base = smem_raw + (smem0 - saddr(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int total = P.stage_bytes * P.stages / 2;
+    __half* h = reinterpret_cast<__half*>(base);
+    uint32_t x = 1234567u + blockIdx.x * 7919u + threadIdx.x;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      x = x * 1664525u + 1013904223u;
+      h[i] = __float2half(((int)(x >> 9) % 2001 - 1000) * 1e-3f);
+    }
+  }
+  const uint32_t full0 = saddr(&bars[0]), empty0 = saddr(&bars[6]), done = saddr(&bars[12]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 13; ++i) mbar_init(saddr(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  const int A = 16 * 1024;
+  if (warp == 0) {
+    int s = 0; uint32_t ph = 0;
+    for (int it = 0; it < P.iters; ++it) {
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      if (elect_one()) mbar_expect(full0 + 8 * s, 0);
+      __syncwarp();
+      if (++s == P.stages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const long long t0 = clock64();
+    int s = 0; uint32_t ph = 0;
+    for (int it = 0; it < P.iters; ++it) {
+      mbar_wait(full0 + 8 * s, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sb = smem0 + (uint32_t)s * (uint32_t)P.stage_bytes;
+      const uint64_t ah = umma_desc(sb), al = umma_desc(sb + A), bh = umma_desc(sb + 2 * A);
+      if (elect_one()) {
+        if (P.do_mma) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma<1>(tmem + (k & 1) * 256, ah + 2 * k, bh + 2 * k, idesc2, (it > 0 || k > 1) ? 1u : 0u);
+            umma<1>(tmem + (k & 1) * 256 + 128, al + 2 * k, bh + 2 * k, idesc, 1u);
+          }
+        }
+        commit<1>(empty0 + 8 * s);
+      }
+      __syncwarp();
+      if (++s == P.stages) { s = 0; ph ^= 1; }
+    }
+    if (elect_one()) commit<1>(done);
+    __syncwarp();
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    if (lane == 0) out[blockIdx.x] = t1 - t0;
+  } else if (warp < 2 + P.pollers) {
+    if (P.poll_mode == 0) {
+      mbar_wait(done, 0);
+    } else if (P.poll_mode == 1) {
+      if (lane == 0) mbar_wait(done, 0);
+      __syncwarp();
+    } else {
+      if (lane == 0) {
+        uint32_t ok = 0;
+        while (!ok) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                       : "=r"(ok) : "r"(done), "r"(0u) : "memory");
+          if (!ok) __nanosleep(200);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 int main() {
@@ -289,6 +394,21 @@ int main() {
            (sum / n) / (best * 1e3));
     if (pt.tma_kb) printf("   bulk stream: %.1f cycles per stage = %.1f B/cycle", ht[0] / (double)iters, pt.tma_kb * 1024.0 * iters / ht[0]);
     printf("\n");
+  }
+
+  printf("---- ring skeleton (producer <-> issuer ping-pong, no loads): cycles per K stage (4 slices; MMA floor 768) ----\n");
+  CK(cudaFuncSetAttribute(ring_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int rcfg[][5] = {  // stages, do_mma, pollers, poll_mode
+      {3, 0, 0, 0}, {3, 1, 0, 0}, {3, 1, 8, 0}, {3, 1, 8, 1}, {3, 1, 8, 2}, {3, 1, 10, 0}, {2, 1, 0, 0}, {2, 1, 8, 0}, {1, 1, 0, 0}, {3, 0, 8, 0}, {3, 0, 8, 2},
+  };
+  for (unsigned i = 0; i < sizeof(rcfg) / sizeof(rcfg[0]); ++i) {
+    RingParams R = {rcfg[i][0], 400, rcfg[i][1], rcfg[i][2], rcfg[i][3], 64 * 1024};
+    ring_probe<<<sms, 64 + 32 * (R.pollers > 0 ? R.pollers : 0), smem>>>(R, d_out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, d_out, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    double sum = 0;
+    for (int b = 0; b < sms; ++b) sum += h[b];
+    printf("stages %d  mma %d  pollers %2d  poll_mode %d : %8.1f cycles per stage\n", R.stages, R.do_mma, R.pollers, R.poll_mode, sum / sms / R.iters);
   }
   return 0;
 }
