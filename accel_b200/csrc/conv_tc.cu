@@ -69,6 +69,11 @@ struct alignas(64) TcParams {
   // A bytes through L2 -> SM drop by ndx (3 for a 3x3); the weights keep their own ring.
   int aslab, ndx, dxmin, slab_w, slab_pl, sa_stages, slab_bo;
   unsigned ring_bytes;   // operand rings in front of the epilogue staging area
+  int prefetch;    // > 0: the producer asks L2 for the NEXT item's first `prefetch` A stages (and, bit 8, its residual tile) one
+                   // whole tile period ahead (cp.async.bulk.prefetch.tensor): short-K layers keep only 2-3 stages = 128-192 KB
+                   // in flight per SM, less than DRAM latency x the SM's L2 port needs (tools/tc_trace.py: 3.8k cycles from
+                   // the first TMA of a tile to its arrival)
+  int res_ahead;   // TMA epilogue: chunks of L2 prefetch distance for the residual tiles (0: none)
   int kchains;     // 2: the K slices of a tile alternate between the two TMEM accumulator buffers and the epilogue sums
                    // them in fp32 (round-to-nearest): the tensor core's own accumulation truncates, so its error grows
                    // with the number of accumulation steps per accumulator; long-K layers only
@@ -220,6 +225,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
         const int fr = y0 / P.Hof, yl = y0 - fr * P.Hof;         // frame of the tile and its first row inside that frame
         const int rot = P.krot ? (int)(((unsigned)item * 5u) % (unsigned)(ke - kb)) : 0;
+        if (P.prefetch && item + (int)gridDim.x < items) {
+          const int item2 = item + (int)gridDim.x;
+          const int split2 = item2 % P.splits, tile2 = item2 / P.splits;
+          const int nt2 = tile2 % P.n_tiles, mt2 = tile2 / P.n_tiles;
+          const int x2 = (mt2 % P.tiles_x) * P.BW, y2 = (mt2 / P.tiles_x) * P.BH;
+          const int fr2 = y2 / P.Hof, yl2 = y2 - fr2 * P.Hof;
+          const int kb2 = (int)(((long long)P.kiters * split2) / P.splits);
+          const int ke2 = (int)(((long long)P.kiters * (split2 + 1)) / P.splits);
+          const int np = min(ke2 - kb2, P.prefetch & 255);
+          if (elect_one()) {
+            for (int j = 0; j < np; ++j) {
+              const int it2 = kb2 + j;
+              const int t2 = it2 / P.chunks, kc2 = it2 - t2 * P.chunks;
+              const int dy2 = P.dy[t2], dx2 = P.dx[t2];
+              if (P.stride2) {
+                tma_prefetch_5d(&P.a_hi, kc2 * BK, dx2 & 1, x2 + (dx2 >> 1), dy2 & 1, y2 + (dy2 >> 1));
+                tma_prefetch_5d(&P.a_lo, kc2 * BK, dx2 & 1, x2 + (dx2 >> 1), dy2 & 1, y2 + (dy2 >> 1));
+              } else {
+                tma_prefetch_4d(&P.a_hi, kc2 * BK, x2 + dx2, yl2 + dy2, fr2);
+                tma_prefetch_4d(&P.a_lo, kc2 * BK, x2 + dx2, yl2 + dy2, fr2);
+              }
+            }
+            if ((P.prefetch & 256) && P.tma_out == 1 && P.epi.res_hi != nullptr) {
+              for (int c = 0; c < P.BN; c += 32) {
+                tma_prefetch_3d(&P.r_hi, nt2 * P.BN + c, x2, y2);
+                tma_prefetch_3d(&P.r_lo, nt2 * P.BN + c, x2, y2);
+              }
+            }
+          }
+          __syncwarp();
+        }
         int it = kb + rot;                                // each CTA walks K from its own offset: neighbours do not
         int t = it / P.chunks, kc = it - t * P.chunks;    // stream the same weight lines at the same moment
         for (int i = kb; i < ke; ++i) {
@@ -228,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t sa = smem0 + s * stage_bytes;
           const int dy = P.dy[t], dx = P.dx[t];
           const int kcol = t * P.Cin_pad + kc * BK;
+          if (P.debug & 4096) TC_TRACE(11, i);               // per stage: ring slot free, loads issued
           if (i == kb) TC_TRACE(1, item);
           if (i == ke - 1) TC_TRACE(2, item);
           if (elect_one()) {
@@ -311,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(full0 + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (it == kb) TC_TRACE(4, item);
+            if (P.debug & 4096) TC_TRACE(10, it);             // per stage: operands landed
             const uint64_t ah = slab_mode ? umma_desc_rows(a_hi, P.slab_bo) : umma_desc(a_hi);
             const uint64_t al = slab_mode ? umma_desc_rows(a_lo, P.slab_bo) : umma_desc(a_lo);
             const uint64_t bh = umma_desc(b_hi), bl = umma_desc(b_lo);
@@ -383,9 +421,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_arrive(bar);
         }
       };
+      // the residual tile of chunk k + res_ahead is asked into L2 now: a buffer is refilled only one chunk ahead of its
+      // use, less than DRAM latency (ncu: 13 % of the kernel's stall samples sat on the wait for the residual bytes)
+      const int res_ahead = has_res ? P.res_ahead : 0;
+      auto ask = [&](int k) {
+        int c0, x0, y0;
+        coords(k, c0, x0, y0);
+        tma_prefetch_3d(&P.r_hi, c0, x0, y0);
+        tma_prefetch_3d(&P.r_lo, c0, x0, y0);
+      };
+      if (res_ahead > 0)
+        for (int k = 2; k < min(total, 2 + res_ahead); ++k) ask(k);
       if (total > 0) fill(0);
       if (total > 1) fill(1);
       for (int k = 0; k < total; ++k) {
+        if (res_ahead > 0 && k + 2 + res_ahead < total) ask(k + 2 + res_ahead);
         const uint32_t sb = sb0 + (uint32_t)(k & 1) * 16384u;
         mbar_wait(sbar0 + 8u * (uint32_t)(k & 1), (uint32_t)((k >> 1) & 1));
         if (!(P.debug & 32)) {
@@ -1179,6 +1229,8 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     if (E.out2_hi) v = v && al32(E.out2_hi) && al32(E.out2_lo) && E.out2_ld % 16 == 0;
     P.vec32 = v ? 1 : 0;
     P.krot = P.aslab ? 0 : env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
+    P.prefetch = (P.aslab || P.pair) ? 0 : env_int("ACCEL_TC_PREFETCH", 0);
+    P.res_ahead = env_int("ACCEL_TC_RES_AHEAD", 2);   // measured: 2 chunks -9 % on res2 expand, larger distances lose (profiles/r02_layer_res_ahead.txt)
     P.debug = env_int("ACCEL_TC_DEBUG", 0);
   }
 

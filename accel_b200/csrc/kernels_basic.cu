@@ -231,6 +231,66 @@ __global__ void __launch_bounds__(256) dcn_col_warp_kernel(const DcnColParams P)
   }
 }
 
+// Tiled variant (ACCEL_DCN_TILED=1; measured SLOWER, 115 vs 93 us per 64 x 128 x 512 layer, although it halves the L2 -> SM
+// bytes -- profiles/r02_ncu_dcn_col.txt -- so the kernel is not bound by them): a CTA owns an 8 x 8 block of output pixels and 128 channels (of one deformable group), a
+// half-warp one (pixel, tap), a lane eight channels.  The 9 taps x 4 corners of neighbouring pixels overlap heavily (the taps sit
+// `dilate` pixels apart, the learned offsets move them by a few pixels), so with all of them gathered by the same SM the
+// L1 cache serves most of the 128-byte corner reads: the per-thread kernel above spreads one pixel's taps over several
+// SMs and fetches every corner from L2 (ncu: l1tex 90 % busy, 604 MB L2 -> SM per 64 x 128 x 512 layer).  Sampling
+// position, clamping and weights are computed once per (pixel, tap, group); same arithmetic order, same stores.
+constexpr int DCN_TB = 8;
+constexpr int DCN_CB = 128;          // channels per CTA: 16 lanes x 8 channels
+__global__ void __launch_bounds__(256) dcn_col_tile_kernel(const DcnColParams P) {
+  pdl_trigger();
+  pdl_wait();
+  const int tiles_x = (P.W + DCN_TB - 1) / DCN_TB;
+  const int ty0 = (blockIdx.x / tiles_x) * DCN_TB, tx0 = (blockIdx.x % tiles_x) * DCN_TB;
+  const int cb = blockIdx.y * DCN_CB;                              // this CTA's DCN_CB channels (inside one deformable group)
+  const int cpg = P.C / P.dg;
+  const int dgi = cb / cpg;
+  const int half = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  const size_t plane = (size_t)P.H * P.W;
+  const float* offp = P.offset + (size_t)(dgi * 18) * plane;
+  for (int w = half; w < DCN_TB * DCN_TB * 9; w += 16) {
+    const int pl = w / 9, t = w - pl * 9;
+    const int oy = ty0 + pl / DCN_TB, ox = tx0 + pl % DCN_TB;
+    if (oy >= P.H || ox >= P.W) continue;
+    const int p = oy * P.W + ox;
+    const int ti = t / 3, tj = t - ti * 3;
+    float py = (float)(oy - P.pad) + (float)(ti * P.dilate) + __ldg(offp + (size_t)(2 * t) * plane + p);
+    float px = (float)(ox - P.pad) + (float)(tj * P.dilate) + __ldg(offp + (size_t)(2 * t + 1) * plane + p);
+    const bool inside = py >= 0.f && px >= 0.f && py < (float)P.H && px < (float)P.W;
+    size_t o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+    float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+    if (inside) {
+      int y0 = (int)floorf(py), x0 = (int)floorf(px);
+      int y1, x1;
+      if (y0 >= P.H - 1) { y0 = y1 = P.H - 1; py = (float)y0; } else { y1 = y0 + 1; }
+      if (x0 >= P.W - 1) { x0 = x1 = P.W - 1; px = (float)x0; } else { x1 = x0 + 1; }
+      const float ly = py - (float)y0, lx = px - (float)x0;
+      const float hy = 1.f - ly, hx = 1.f - lx;
+      w00 = hy * hx; w01 = hy * lx; w10 = ly * hx; w11 = ly * lx;
+      o00 = ((size_t)y0 * P.W + x0) * P.in_ld; o01 = ((size_t)y0 * P.W + x1) * P.in_ld;
+      o10 = ((size_t)y1 * P.W + x0) * P.in_ld; o11 = ((size_t)y1 * P.W + x1) * P.in_ld;
+    }
+    {
+      const int c0 = cb + hl * 8;
+      float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (inside) {
+        float a[8], b[8], c[8], d[8];
+        load8(P.in_hi + o00 + c0, P.in_lo + o00 + c0, a);
+        load8(P.in_hi + o01 + c0, P.in_lo + o01 + c0, b);
+        load8(P.in_hi + o10 + c0, P.in_lo + o10 + c0, c);
+        load8(P.in_hi + o11 + c0, P.in_lo + o11 + c0, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = ((a[i] * w00 + b[i] * w01) + c[i] * w10) + d[i] * w11;
+      }
+      const size_t oo = (size_t)p * P.col_ld + (size_t)t * P.C + c0;
+      store8(P.col_hi + oo, P.col_lo + oo, out);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Flow-guided warp: GridGenerator(transform_type='warp') + BilinearSampler
 // (dff_deeplab/symbols/accel_18.py:174-175).  The sampling position is computed with the same fp32
@@ -640,6 +700,12 @@ cudaError_t launch_dcn_col(const DcnColParams& P, cudaStream_t stream) {
   if (warp_variant && P.C % 8 == 0 && (P.C / 8) % P.dg == 0) {
     const long long warps = (long long)P.H * P.W * 9;
     return launch_k(dcn_col_warp_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, P);
+  }
+  static int tiled = -1;                         // ACCEL_DCN_TILED=1: the tiled kernel (measured slower: 115 vs 93 us, stays off)
+  if (tiled < 0) { const char* e = getenv("ACCEL_DCN_TILED"); tiled = (e && e[0] == '1') ? 1 : 0; }
+  if (tiled && P.C % P.dg == 0 && (P.C / P.dg) % DCN_CB == 0) {
+    const int tiles = ((P.W + DCN_TB - 1) / DCN_TB) * ((P.H + DCN_TB - 1) / DCN_TB);
+    return launch_k(dcn_col_tile_kernel, dim3((unsigned)tiles, (unsigned)(P.C / DCN_CB)), dim3(256), 0, stream, P);
   }
   const long long work = (long long)P.H * P.W * 9 * (P.C / 8);
   return launch_k(dcn_col_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, stream, P);

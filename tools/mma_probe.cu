@@ -298,6 +298,41 @@ __global__ void __launch_bounds__(384, 1) ring_probe(const __grid_constant__ Rin
   }
 }
 
+// ---- bulk-copy stream alone: bytes per cycle into one SM's shared memory against the bytes kept in flight --------------
+// `depth` slots of `slot_bytes`, each refilled as soon as it lands (nothing consumes the data).  src_mode 0: every CTA
+// streams its own 512 KB window of an L2-resident buffer; 1: a 1 GB buffer (DRAM).
+__global__ void __launch_bounds__(32, 1) stream_probe(const uint8_t* src, size_t window, int depth, int slot_bytes, int iters,
+                                                       long long* out, int chunk) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[8];
+  const uint32_t smem0 = (saddr(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(saddr(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint8_t* base = src + (size_t)blockIdx.x * window;
+    uint32_t phs = 0;                                   // phase bits of the slots
+    size_t off = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters + depth; ++it) {
+      const int b = it % depth;
+      if (it >= depth) { mbar_wait(saddr(&bars[b]), (phs >> b) & 1u); phs ^= 1u << b; }
+      if (it < iters) {
+        mbar_expect(saddr(&bars[b]), (uint32_t)slot_bytes);
+        for (int o = 0; o < slot_bytes; o += chunk) {
+          const int n = slot_bytes - o < chunk ? slot_bytes - o : chunk;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem0 + (uint32_t)(b * slot_bytes + o)),
+                       "l"(base + ((off + o) & (window - 1))), "r"(n), "r"(saddr(&bars[b]))
+                       : "memory");
+        }
+        off += slot_bytes;
+      }
+    }
+    out[blockIdx.x] = clock64() - t0;
+  }
+}
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 int main() {
@@ -410,5 +445,26 @@ int main() {
     for (int b = 0; b < sms; ++b) sum += h[b];
     printf("stages %d  mma %d  pollers %2d  poll_mode %d : %8.1f cycles per stage\n", R.stages, R.do_mma, R.pollers, R.poll_mode, sum / sms / R.iters);
   }
+
+  printf("---- bulk-copy stream alone: B/cycle/SM against bytes in flight (all SMs streaming) ----\n");
+  CK(cudaFuncSetAttribute(stream_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  uint8_t* d_big = nullptr;
+  const size_t big = (size_t)1 << 30;
+  CK(cudaMalloc(&d_big, big));
+  CK(cudaMemset(d_big, 1, big));
+  for (int mode = 0; mode < 2; ++mode)
+    for (int chunk = 16; chunk <= 64; chunk *= 2)
+    for (int slot = 64; slot <= 64; slot *= 2)
+      for (int depth = 1; depth <= 3 && depth * slot <= 208; ++depth) {
+        const int its = 600;
+        const size_t window = mode ? (size_t)4 << 20 : (size_t)256 * 1024;   // powers of two (masked in the kernel)
+        stream_probe<<<sms, 32, smem>>>(mode ? d_big : d_src, window, depth, slot * 1024, its, d_out, chunk * 1024);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h, d_out, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+        double sum = 0;
+        for (int b = 0; b < sms; ++b) sum += h[b];
+        printf("%s  %2d KB copies, slot %2d KB x depth %d = %3d KB in flight: %6.1f B/cycle/SM\n", mode ? "DRAM" : "L2  ", chunk, slot, depth, slot * depth,
+               (double)slot * 1024.0 * its / (sum / sms));
+      }
   return 0;
 }
