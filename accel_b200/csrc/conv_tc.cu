@@ -73,6 +73,9 @@ struct alignas(64) TcParams {
                    // whole tile period ahead (cp.async.bulk.prefetch.tensor): short-K layers keep only 2-3 stages = 128-192 KB
                    // in flight per SM, less than DRAM latency x the SM's L2 port needs (tools/tc_trace.py: 3.8k cycles from
                    // the first TMA of a tile to its arrival)
+  int mcast;       // 1: launched as clusters of two CTAs that work on two M tiles of the SAME N tile in lockstep; each CTA loads one
+                   // plane of the weight tile (B_hi / B_lo) and multicasts it into both CTAs' rings: 48 instead of 64 KB of L2
+                   // reads per CTA and K stage (the L2 output, ~20 TB/s over all SMs, is what bounds the mainloop)
   int res_ahead;   // TMA epilogue: chunks of L2 prefetch distance for the residual tiles (0: none)
   int kchains;     // 2: the K slices of a tile alternate between the two TMEM accumulator buffers and the epilogue sums
                    // them in fp32 (round-to-nearest): the tensor core's own accumulation truncates, so its error grows
@@ -118,6 +121,44 @@ __device__ unsigned g_tc_trace_n;
 // register allocation.
 // TWO: two accumulation chains (TcParams::kchains == 2): a template parameter so that the ordinary instantiations do not
 // carry the registers of the folded first half, and the two-chain ones do not carry the residual prefetch registers.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_idx() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// B-operand multicast (TcParams::mcast): one TMA load lands in BOTH CTAs of the cluster, at the same shared-memory offset, and
+// completes bytes on each CTA's own mbarrier at the same offset.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {   // arrives on `bar` in every CTA of the mask
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 template <bool NCAT, bool FUSED = false, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -145,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, P.mcast ? 2 : 1);         // mcast: the slot is rewritten by both CTAs' loads -> both MMA warps free it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -165,13 +206,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
   pdl_trigger();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (P.mcast) cluster_sync_all();                         // the peer's barriers exist before anything is multicast to them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   pdl_wait();                                              // the prologue above touched no global memory
   const uint32_t tmem_base = tmem_base_slot;
 
+  // mcast (TcParams::mcast): clusters of two CTAs walk pair-items q = (two M tiles, one N tile); rank r takes M tile 2*m2 + r
+  const bool mc = P.mcast != 0;
+  const int rank = mc ? (int)cluster_ctarank() : 0, mstep = mc ? 2 : 1;
+  const int it0 = mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, itstep = mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int tiles = P.tiles_x * P.tiles_y * P.n_tiles;
-  const int items = tiles * P.splits;
+  const int items = mc ? ((P.tiles_x * P.tiles_y + 1) / 2) * P.n_tiles : tiles * P.splits;
   if (warp == 0) TC_TRACE(0, 0);
 
   if (warp == 0) {
@@ -217,18 +263,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t ph = 0;
       const bool ldA = !(P.debug & (256 | 512)), ldB = !(P.debug & (256 | 1024));   // timing decomposition only
       const uint32_t tx = (ldA ? 2 * a_bytes : 0u) + (ldB ? 2 * b_bytes : 0u);
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int item = it0; item < items; item += itstep) {
         const int split = item % P.splits, tile = item / P.splits;
-        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * mstep + rank;
         const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
         const int kb = (int)(((long long)P.kiters * split) / P.splits);
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
         const int fr = y0 / P.Hof, yl = y0 - fr * P.Hof;         // frame of the tile and its first row inside that frame
         const int rot = P.krot ? (int)(((unsigned)item * 5u) % (unsigned)(ke - kb)) : 0;
-        if (P.prefetch && item + (int)gridDim.x < items) {
-          const int item2 = item + (int)gridDim.x;
+        if (P.prefetch && item + itstep < items) {
+          const int item2 = item + itstep;
           const int split2 = item2 % P.splits, tile2 = item2 / P.splits;
-          const int nt2 = tile2 % P.n_tiles, mt2 = tile2 / P.n_tiles;
+          const int nt2 = tile2 % P.n_tiles, mt2 = (tile2 / P.n_tiles) * mstep + rank;
           const int x2 = (mt2 % P.tiles_x) * P.BW, y2 = (mt2 / P.tiles_x) * P.BH;
           const int fr2 = y2 / P.Hof, yl2 = y2 - fr2 * P.Hof;
           const int kb2 = (int)(((long long)P.kiters * split2) / P.splits);
@@ -277,7 +323,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               tma_load_4d(sa, &P.a_hi, fb, kc * BK, x0 + dx, yl + dy, fr);
               tma_load_4d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, yl + dy, fr);
             }
-            if (ldB) {
+            if (ldB && mc) {                               // each CTA fetches one plane of the shared weight tile for both
+              if (rank == 0) tma_load_2d_mc(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nt * P.BN, (uint16_t)3);
+              else tma_load_2d_mc(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nt * P.BN, (uint16_t)3);
+            } else if (ldB) {
               tma_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nt * P.BN);
               tma_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nt * P.BN);
             }
@@ -307,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t ph = 0, accph = 0;
       int nas = 0, cur = 0;                               // A-slab ring: next slot to consume, slot in use
       uint32_t aphc = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int item = it0; item < items; item += itstep) {
         const int split = item % P.splits;
         const int kb = (int)(((long long)P.kiters * split) / P.splits);
         const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
@@ -373,7 +422,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   }
                 }
               }
-              umma_commit(empty0 + 8 * s);                    // frees the smem slot when these MMAs retire
+              if (mc) umma_commit_mc(empty0 + 8 * s, (uint16_t)3);   // ... in both CTAs: either may write the other's slot
+              else umma_commit(empty0 + 8 * s);               // frees the smem slot when these MMAs retire
               if (slab_done) umma_commit(aempty0 + 8 * cur);  // ... and the A slab after the last tap that reads it
             }
             __syncwarp();
@@ -399,11 +449,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t sb0 = stg0 + (uint32_t)cset * 2u * 16384u;
       const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]), sbar0 = smem_u32(&stg_bars[cset * 2]);
       const int cpi = P.BN > cset * 32 ? (P.BN - cset * 32 + 63) / 64 : 0;       // chunks of one item that belong to this set
-      const int mine = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const int mine = it0 < items ? (items - it0 + itstep - 1) / itstep : 0;
       const int total = mine * cpi;
       auto coords = [&](int k, int& c0, int& x0, int& y0) {
-        const int item = (int)blockIdx.x + (k / cpi) * (int)gridDim.x;
-        const int tile = item / P.splits, nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int item = it0 + (k / cpi) * itstep;
+        const int tile = item / P.splits, nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * mstep + rank;
         c0 = nt * P.BN + cset * 32 + (k % cpi) * 64;
         x0 = (mt % P.tiles_x) * P.BW;
         y0 = (mt / P.tiles_x) * P.BH;
@@ -487,10 +537,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         sc_next = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
         sh_next = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
       };
-      if ((int)blockIdx.x < items) fetch_sc(blockIdx.x);
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      if (it0 < items) fetch_sc(it0);
+      for (int item = it0; item < items; item += itstep) {
         const int tile = item / P.splits;
-        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * mstep + rank;
         const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
         const int x = x0 + bx, y = y0 + by;
         const bool valid = x < P.Wo && y < P.Ho;
@@ -500,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           epi_sc[sci][0][et] = sc_next;
           epi_sc[sci][1][et] = sh_next;
         }
-        if (item + (int)gridDim.x < items) fetch_sc(item + gridDim.x);
+        if (item + itstep < items) fetch_sc(item + itstep);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 2) TC_TRACE(6, item);
         mbar_wait(tfull0 + 8 * acc, accph);
@@ -571,9 +621,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
     int acc = 0, sci = 0;                                  // sci: scale/shift staging slot, alternates per item
     uint32_t accph = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    for (int item = it0; item < items; item += itstep) {
       const int split = item % P.splits, tile = item / P.splits;
-      const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+      const int nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * mstep + rank;
       const int x = (mt % P.tiles_x) * P.BW + bx, y = (mt / P.tiles_x) * P.BH + by;
       const bool valid = x < P.Wo && y < P.Ho;
       const int pix = (y * E.osy + E.ooy) * E.OWf + x * E.osx + E.oox;
@@ -754,7 +804,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (P.mcast) cluster_sync_all();                         // nobody leaves while its partner may still write or signal it
+  else __syncthreads();
   if (warp == 0) TC_TRACE(9, 0);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -772,31 +823,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // signal the LEADER's `full` barrier, MMA completion is multicast to both CTAs' `empty` / `tfull`
 // barriers, and the peer's epilogue warps release the accumulator on the leader's `tempty` barrier.
 // ================================================================================================
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_idx() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_count() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire: the arrival comes from the peer CTA (release.cluster)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
 }
 __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -836,11 +882,27 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {      // arrives on 
                : "memory");
 }
 
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// Pair tile = 256 pixels x BN channels (BN <= 128).  Per CTA and stage: A_hi | A_lo of its own 128 pixels (32 KB) and its
+// HALF of the weight rows, B_hi | B_lo (BN/2 rows each) -- 48 KB at BN = 128 against the single-CTA kernel's 64 KB, which is
+// what that kernel is bound by (L2 -> shared memory saturates near 73 B/cycle/SM, tools/mma_probe.cu).  Three MMAs per K
+// slice, M = 256, N = BN: hi*hi into accumulator columns [0, BN), hi*lo and lo*hi into [BN, 2BN) -- the same separation of
+// the small cross terms as the N-concatenated single-CTA issue.  Accumulators are double-buffered
+// (4*BN TMEM columns); TWO = two accumulation chains as K halves through the two buffers, exactly as in conv_tc_kernel.
+template <bool TWO>
 __global__ void __launch_bounds__(kThreadsPair, 1) conv_tc2_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ __align__(8) uint64_t pbars[kMaxStages];           // leader's copy: the PEER's operands of stage s have landed
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float epi_sc[2][2][256];
+  __shared__ __align__(16) float epi_sc[2][2][128];
 
   // operand ring per CTA: [stage][A_hi | A_lo | B_hi half | B_lo half]
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -852,11 +914,16 @@ __global__ void __launch_bounds__(kThreadsPair, 1) conv_tc2_kernel(const __grid_
   const bool leader = rank == 0;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
   const uint32_t tfull0 = smem_u32(&bars[2 * kMaxStages]), tempty0 = smem_u32(&bars[2 * kMaxStages + 2]);
+  const uint32_t pfull0 = smem_u32(&pbars[0]);
 
+  // Every CTA's TMA loads complete on its OWN `full` barrier; the peer's relay warp (its idle MMA warp) forwards each
+  // completion with ONE remote arrival on the leader's `pfull`.  (Signalling the leader's barrier straight from the peer's
+  // TMA loads -- cta_group::2 loads with a remote mbarrier -- measured 1750 cycles per 48 KB stage with nothing else running.)
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(full0 + 8 * s, 2);                  // (leader's copy is the live one) one arrival per CTA's producer
+      mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
+      mbar_init(pfull0 + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -880,85 +947,107 @@ __global__ void __launch_bounds__(kThreadsPair, 1) conv_tc2_kernel(const __grid_
 
   const int tiles_m = P.tiles_x * P.tiles_y;
   const int tiles_m2 = (tiles_m + 1) / 2;
-  const int items = tiles_m2 * P.n_tiles * P.splits;
+  const int items = tiles_m2 * P.n_tiles;           // (the plan never splits K for pair tiles)
   const int cid = (int)cluster_idx(), ncl = (int)cluster_count();
+  const uint32_t acc_cols = 2u * (uint32_t)P.BN;
 
   if (warp == 0) {
-    // ===================================== TMA producer (both CTAs) =====================================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int item = cid; item < items; item += ncl) {
-        const int split = item % P.splits, tile = item / P.splits;
-        const int nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * 2 + (int)rank;     // phantom tile past the end: all OOB
-        const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
-        const int kb = (int)(((long long)P.kiters * split) / P.splits);
-        const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
-        const int rot = P.krot ? (int)(((unsigned)item * 5u) % (unsigned)(ke - kb)) : 0;
-        for (int i = kb; i < ke; ++i) {
-          int it = i + rot;
-          if (it >= ke) it -= ke - kb;
-          const int t = it / P.chunks, kc = it - t * P.chunks;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          const uint32_t fb = mapa_u32(full0 + 8 * s, 0);                // the LEADER's full barrier
-          const uint32_t sa = smem0 + s * stage_bytes;
-          const int dy = P.dy[t], dx = P.dx[t];
+    // ===================================== TMA producer (both CTAs; converged warp, elect.sync) ==========
+    int s = 0;
+    uint32_t ph = 0;
+    for (int item = cid; item < items; item += ncl) {
+      const int nt = item % P.n_tiles, mt = (item / P.n_tiles) * 2 + (int)rank;       // phantom tile past the end: all OOB
+      const int x0 = (mt % P.tiles_x) * P.BW, y0 = (mt / P.tiles_x) * P.BH;
+      const int fr = y0 / P.Hof, yl = y0 - fr * P.Hof;
+      const int nrow = nt * P.BN + (int)rank * (P.BN / 2);
+      int t = 0, kc = 0;
+      for (int it = 0; it < P.kiters; ++it) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t fb = full0 + 8 * s;
+        const uint32_t sa = smem0 + s * stage_bytes;
+        const int dy = P.dy[t], dx = P.dx[t];
+        const int kcol = t * P.Cin_pad + kc * BK;
+        if (elect_one()) {
           if (P.debug & 256) {                                           // timing decomposition: no operand loads
-            if (leader) mbar_arrive(full0 + 8 * s);
-            else mbar_arrive_cluster(fb);
-            if (++s == P.stages) { s = 0; ph ^= 1; }
-            continue;
-          }
-          if (P.stride2) {
-            tma2_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
-            tma2_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+            mbar_arrive(fb);
           } else {
-            tma2_load_3d(sa, &P.a_hi, fb, kc * BK, x0 + dx, y0 + dy);
-            tma2_load_3d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, y0 + dy);
+            const bool ldA = !(P.debug & 512), ldB = !(P.debug & 1024);   // timing decomposition only
+            mbar_arrive_expect_tx(fb, (ldA ? 2 * a_bytes : 0u) + (ldB ? 2 * b_bytes : 0u));
+            if (!ldA) {
+            } else if (P.stride2) {
+              tma_load_5d(sa, &P.a_hi, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+              tma_load_5d(sa + a_bytes, &P.a_lo, fb, kc * BK, dx & 1, x0 + (dx >> 1), dy & 1, y0 + (dy >> 1));
+            } else {
+              tma_load_4d(sa, &P.a_hi, fb, kc * BK, x0 + dx, yl + dy, fr);
+              tma_load_4d(sa + a_bytes, &P.a_lo, fb, kc * BK, x0 + dx, yl + dy, fr);
+            }
+            if (ldB) {
+              tma_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nrow);
+              tma_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nrow);
+            }
           }
-          const int kcol = t * P.Cin_pad + kc * BK;
-          const int nrow = nt * P.BN + (int)rank * (P.BN / 2);
-          tma2_load_2d(sa + 2 * a_bytes, &P.b_hi, fb, kcol, nrow);
-          tma2_load_2d(sa + 2 * a_bytes + b_bytes, &P.b_lo, fb, kcol, nrow);
-          if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * stage_bytes);   // bytes of BOTH CTAs' loads
-          else mbar_arrive_cluster(fb);
-          if (++s == P.stages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == P.stages) { s = 0; ph ^= 1; }
+        if (++kc == P.chunks) { kc = 0; ++t; }
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer (leader CTA only) ==================================
-    if (leader && lane == 0) {
+    // ===================================== MMA issuer (leader CTA only; converged warp) ==================
+    if (leader) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t bn = (uint32_t)P.BN;
+      const bool no_mma = (P.debug & 128) != 0;
       int s = 0, acc = 0;
       uint32_t ph = 0, accph = 0;
       for (int item = cid; item < items; item += ncl) {
-        const int split = item % P.splits;
-        const int kb = (int)(((long long)P.kiters * split) / P.splits);
-        const int ke = (int)(((long long)P.kiters * (split + 1)) / P.splits);
-        mbar_wait(tempty0 + 8 * acc, accph ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(acc * P.BN);
-        for (int it = kb; it < ke; ++it) {
-          mbar_wait(full0 + 8 * s, ph);
+        const int kmid = TWO ? (P.kiters + 1) / 2 : P.kiters;
+        for (int half = 0; half < (TWO ? 2 : 1); ++half) {
+          const int hb = half ? kmid : 0, he = half ? P.kiters : kmid;
+          mbar_wait(tempty0 + 8 * acc, accph ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem0 + s * stage_bytes;
-          const uint64_t ah = umma_desc(sa), al = umma_desc(sa + a_bytes);
-          const uint64_t bh = umma_desc(sa + 2 * a_bytes), bl = umma_desc(sa + 2 * a_bytes + b_bytes);
+          const uint32_t d = tmem_base + (uint32_t)acc * acc_cols;
+          for (int it = hb; it < he; ++it) {
+            mbar_wait(full0 + 8 * s, ph);
+            mbar_wait_cluster(pfull0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem0 + s * stage_bytes;
+            const uint64_t ah = umma_desc(sa), al = umma_desc(sa + a_bytes);
+            const uint64_t bh = umma_desc(sa + 2 * a_bytes), bl = umma_desc(sa + 2 * a_bytes + b_bytes);
+            const uint32_t first0 = it > hb ? 1u : 0u;
+            if (elect_one()) {
+              if (!no_mma) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);
-            if (P.debug & 128) continue;
-            umma2_f16(d, ah + adv, bh + adv, idesc, (it > kb || k > 0) ? 1u : 0u);
-            umma2_f16(d, ah + adv, bl + adv, idesc, 1u);
-            umma2_f16(d, al + adv, bh + adv, idesc, 1u);
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint64_t adv = (uint64_t)(k * 2);
+                  const uint32_t first = k >= 1 ? 1u : first0;
+                  umma2_f16(d, ah + adv, bh + adv, idesc, first);          // hi*hi          -> [0, BN)
+                  umma2_f16(d + bn, ah + adv, bl + adv, idesc, first);     // hi*lo          -> [BN, 2BN)
+                  umma2_f16(d + bn, al + adv, bh + adv, idesc, 1u);        // lo*hi on top
+                }
+              }
+              umma2_commit(empty0 + 8 * s);                   // frees the stage in both CTAs
+            }
+            __syncwarp();
+            if (++s == P.stages) { s = 0; ph ^= 1; }
           }
-          umma2_commit(empty0 + 8 * s);                   // frees the stage in both CTAs
+          if (elect_one()) umma2_commit(tfull0 + 8 * acc);    // accumulator complete -> both CTAs' epilogues
+          __syncwarp();
+          if (++acc == 2) { acc = 0; accph ^= 1; }
+        }
+      }
+    } else {
+      // relay: this CTA's operands of stage s have landed -> one arrival on the leader's pfull[s]
+      const uint32_t pf_leader0 = mapa_u32(pfull0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = cid; item < items; item += ncl)
+        for (int it = 0; it < P.kiters; ++it) {
+          mbar_wait(full0 + 8 * s, ph);
+          if (elect_one()) mbar_arrive_cluster(pf_leader0 + 8 * s);
+          __syncwarp();
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
-        umma2_commit(tfull0 + 8 * acc);                   // accumulator complete -> both CTAs' epilogues
-        if (++acc == 2) { acc = 0; accph ^= 1; }
-      }
     }
   } else {
     // ===================================== epilogue (each CTA: its own 128 pixel rows) =====================
@@ -966,61 +1055,81 @@ __global__ void __launch_bounds__(kThreadsPair, 1) conv_tc2_kernel(const __grid_
     const int cset = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const int by = r / P.BW, bx = r - by * P.BW;
-    const int npix = P.Ho * P.Wo;
     const int et = threadIdx.x - 64;
     const Epilogue& E = P.epi;
     const uint32_t tempty_leader0 = mapa_u32(tempty0, 0);
-    int acc = 0;
+    const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int acc = 0, sci = 0;
     uint32_t accph = 0;
     for (int item = cid; item < items; item += ncl) {
-      const int split = item % P.splits, tile = item / P.splits;
-      const int nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * 2 + (int)rank;
+      const int nt = item % P.n_tiles, mt = (item / P.n_tiles) * 2 + (int)rank;
       const int x = (mt % P.tiles_x) * P.BW + bx, y = (mt / P.tiles_x) * P.BH + by;
       const bool valid = mt < tiles_m && x < P.Wo && y < P.Ho;
       const int pix = (y * E.osy + E.ooy) * E.OWf + x * E.osx + E.oox;
       const int nbase = nt * P.BN;
-      const bool use_res = P.splits == 1 && E.res_hi != nullptr && P.vec32;
-      if (P.splits == 1 && et < P.BN) {
+      const bool use_res = E.res_hi != nullptr && P.vec32 && valid;
+      if (et < P.BN) {
         const int c = nbase + et;
         const bool in = c < E.Cout;
-        epi_sc[acc][0][et] = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
-        epi_sc[acc][1][et] = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
-      }
-      ResChunk rc{}, rc1{};
-      if (use_res && valid) {
-        if (nbase + cset * 32 + 32 <= E.Cout) load_res(E, pix, nbase + cset * 32, rc);
-        if (cset * 32 + 64 < P.BN && nbase + cset * 32 + 96 <= E.Cout) load_res(E, pix, nbase + cset * 32 + 64, rc1);
+        epi_sc[sci][0][et] = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
+        epi_sc[sci][1][et] = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(tfull0 + 8 * acc, accph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN);
-      for (int cc = cset * 32; cc < P.BN; cc += 64) {
-        const int n0 = nbase + cc;
-        if (n0 >= P.Cout_pad) break;
-        float v[32];
-        tmem_ld32(taddr + cc, v);
-        ResChunk rn{};
-        const int nn = n0 + 128;
-        if (use_res && valid && cc + 128 < P.BN && nn + 32 <= E.Cout) load_res(E, pix, nn, rn);
-        if (valid) {
-          if (P.splits > 1) {
-            float4* dst = reinterpret_cast<float4*>(P.partial + ((size_t)split * npix + (size_t)y * P.Wo + x) * P.Cout_pad + n0);
+      float part[2][32];
+      if (TWO) {
+        mbar_wait(tfull0 + 8 * acc, accph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else if (P.vec32 && n0 + 32 <= E.Cout) {
-            epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[acc][0][cc], &epi_sc[acc][1][cc]);
-          } else {
+        for (int j = 0; j < 2; ++j) {
+          const int cc = cset * 32 + j * 64;
+          if (cc < P.BN && nbase + cc < P.Cout_pad) {
+            float xt[32];
+            tmem_ld32(tq + (uint32_t)acc * acc_cols + cc, part[j]);
+            tmem_ld32(tq + (uint32_t)acc * acc_cols + P.BN + cc, xt);
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (n0 + g * 8 < E.Cout) epilogue_store<8>(E, pix, n0 + g * 8, v + g * 8);
+            for (int i = 0; i < 32; ++i) part[j][i] += xt[i];
           }
         }
-        rc = rc1;
-        rc1 = rn;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * acc);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
+      mbar_wait(tfull0 + 8 * acc, accph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cc = cset * 32 + j * 64;
+        const int n0 = nbase + cc;
+        if (cc < P.BN && n0 < P.Cout_pad) {
+          float v[32];
+          {
+            float xt[32];
+            tmem_ld32(tq + (uint32_t)acc * acc_cols + cc, v);
+            tmem_ld32(tq + (uint32_t)acc * acc_cols + P.BN + cc, xt);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += xt[i];
+          }
+          if (TWO) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += part[j][i];
+          }
+          if (valid && !(P.debug & 1)) {
+            if (P.vec32 && n0 + 32 <= E.Cout) {
+              ResChunk rc{};
+              if (use_res) load_res(E, pix, n0, rc);
+              epilogue_chunk32(E, pix, n0, v, rc, &epi_sc[sci][0][cc], &epi_sc[sci][1][cc]);
+            } else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (n0 + g * 8 < E.Cout) epilogue_store<8>(E, pix, n0 + g * 8, v + g * 8);
+            }
+          }
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
+      sci ^= 1;
       if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * acc);     // the leader's MMA thread owns this wait
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
@@ -1057,7 +1166,6 @@ bool tc_supported(const ConvParams& P) {
 bool tc_batchable(const ConvParams& C) {
   if (C.nb <= 1) return true;
   if (!tc_supported(C)) return false;
-  if (env_int("ACCEL_TC_PAIR", 0) != 0) return false;
   int bw = 1;
   while (bw * 2 <= C.Wo && bw * 2 <= BM) bw *= 2;
   const int bh = BM / bw;
@@ -1137,11 +1245,23 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   if (auto_t) best_bn = t_bn;
   int bn = env_int("ACCEL_TC_BN", best_bn);
   if (bn != 64 && bn != 128 && bn != 256) bn = best_bn;
-  P.pair = env_int("ACCEL_TC_PAIR", 0) != 0 ? 1 : 0;
-  if (P.pair && bn > C.Cout_pad && bn != 64) P.pair = 0;
+  // CTA pairs (conv_tc2_kernel): 256-pixel x 128-channel tiles, each SM stages half of the weight rows.  Pays where the
+  // single-CTA mainloop is bound by its 64 KB of operands per K stage, i.e. long-K layers that are not split:
+  // ACCEL_TC_PAIR = 0 never, 1 wherever legal, unset = auto (at least ACCEL_TC_PAIR_KMIN K stages, >= 128 output channels,
+  // enough pair tiles for the SM pairs).
+  {
+    const int mode = env_int("ACCEL_TC_PAIR", 0);       // measured slower than the single-CTA kernel: opt-in
+    const int pbn = C.Cout_pad >= 128 ? 128 : 64;
+    const int pitems = ((tiles_m + 1) / 2) * ((C.Cout_pad + pbn - 1) / pbn);
+    const bool legal = C.Cout_pad >= 64 && (P.stride2 ? nb == 1 : true);
+    const bool want_pair = mode == 1 || (mode < 0 && best_splits == 1 && !auto_t && P.kiters >= env_int("ACCEL_TC_PAIR_KMIN", 12) &&
+                                         C.Cout_pad >= 128 && pitems >= (num_sms / 2) * env_int("ACCEL_TC_PAIR_WAVES", 2));
+    P.pair = (legal && want_pair && mode != 0) ? 1 : 0;
+    if (P.pair) bn = pbn;
+  }
   P.BN = bn;
   P.n_tiles = (C.Cout_pad + bn - 1) / bn;
-  int splits = env_int("ACCEL_TC_SPLITS", bn == best_bn ? best_splits : 1);
+  int splits = P.pair ? 1 : env_int("ACCEL_TC_SPLITS", bn == best_bn ? best_splits : 1);
   if (splits > P.kiters) splits = P.kiters;
   if (splits < 1) splits = 1;
   const size_t stage_bytes = 2 * (size_t)BM * 128 + (P.pair ? 1 : 2) * (size_t)bn * 128;   // pair: half the weight rows per CTA
@@ -1190,7 +1310,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     P.ncat = (!P.pair && bn <= 128 && ncat_mode != 0) ? 1 : 0;
   }
   int cols = 32;
-  while (cols < (P.ncat ? 4 : 2) * bn) cols *= 2;
+  while (cols < ((P.ncat || P.pair) ? 4 : 2) * bn) cols *= 2;   // pair: [hi*hi | cross terms] x two buffers
   P.tmem_cols = cols;
 
   const int tiles = tiles_m * P.n_tiles;
@@ -1205,6 +1325,19 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     const int ncl = items < num_sms / 2 ? items : num_sms / 2;
     plan->grid = 2 * ncl;
   }
+  // B multicast between the two CTAs of a cluster (TcParams::mcast).  ACCEL_TC_MCAST: 0 never, 1 wherever legal,
+  // unset = auto (at least ACCEL_TC_MCAST_KMIN K stages per tile).
+  {
+    const int mode = env_int("ACCEL_TC_MCAST", 0);
+    const bool legal = !P.pair && !P.aslab && splits == 1 && tiles_m >= 2 && num_sms >= 2;
+    const bool want_mc = mode == 1 || (mode < 0 && P.kiters >= env_int("ACCEL_TC_MCAST_KMIN", 8));
+    P.mcast = (legal && want_mc) ? 1 : 0;
+    if (P.mcast) {
+      const int pitems = ((tiles_m + 1) / 2) * P.n_tiles;
+      const int ncl = pitems < num_sms / 2 ? pitems : num_sms / 2;
+      plan->grid = 2 * ncl;
+    }
+  }
   plan->launches = (splits > 1 && !P.fused) ? 2 : 1;
   {
     // Long K chains: split the accumulation over both TMEM buffers (TcParams::kchains).  ACCEL_TC_CHAINS: 0/1 never,
@@ -1218,7 +1351,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
                                      env_int("ACCEL_TC_CHAINS_MULTI", 0) != 0));
     // (the epilogue folds the first half into registers: at most two 32-channel chunks per thread, i.e. BN <= 128, and
     // at least one K stage per half; the TMA epilogue -- short-K layers -- never combines with it, see below)
-    P.kchains = (want && !P.pair && mode != 0 && mode != 1 && bn <= 128 && kps >= 2 && P.kiters / splits >= 2) ? 2 : 1;
+    P.kchains = (want && mode != 0 && mode != 1 && bn <= 128 && kps >= 2 && P.kiters / splits >= 2) ? 2 : 1;
   }
   {
     auto al32 = [](const void* p) { return ((uintptr_t)p & 31) == 0; };
@@ -1228,7 +1361,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     if (E.res_hi) v = v && al32(E.res_hi) && al32(E.res_lo) && E.res_ld % 16 == 0;
     if (E.out2_hi) v = v && al32(E.out2_hi) && al32(E.out2_lo) && E.out2_ld % 16 == 0;
     P.vec32 = v ? 1 : 0;
-    P.krot = P.aslab ? 0 : env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
+    P.krot = (P.aslab || P.mcast) ? 0 : env_int("ACCEL_TC_KROT", P.BN == 256 ? 1 : 0);
     P.prefetch = (P.aslab || P.pair) ? 0 : env_int("ACCEL_TC_PREFETCH", 0);
     P.res_ahead = env_int("ACCEL_TC_RES_AHEAD", 2);   // measured: 2 chunks -9 % on res2 expand, larger distances lose (profiles/r02_layer_res_ahead.txt)
     P.debug = env_int("ACCEL_TC_DEBUG", 0);
@@ -1237,13 +1370,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   // tensor maps ------------------------------------------------------------------------------------
   bool ok = true;
   const cuuint64_t e = sizeof(__half);
-  if (!P.stride2 && P.pair) {
-    cuuint64_t dims[3] = {(cuuint64_t)C.Cin, (cuuint64_t)C.Win, (cuuint64_t)C.Hin};
-    cuuint64_t str[2] = {(cuuint64_t)C.in_ld * e, (cuuint64_t)C.in_ld * C.Win * e};
-    cuuint32_t box[3] = {BK, (cuuint32_t)P.BW, (cuuint32_t)P.BH};
-    ok = ok && encode(&P.a_hi, C.in_hi, 3, dims, str, box, err, errlen);
-    ok = ok && encode(&P.a_lo, C.in_lo, 3, dims, str, box, err, errlen);
-  } else if (!P.stride2) {
+  if (!P.stride2) {
     // (channel, x, y, frame): out-of-image rows / columns are zero-filled per frame, so the conv padding stays right
     // when several frames share one launch
     cuuint64_t dims[4] = {(cuuint64_t)C.Cin, (cuuint64_t)C.Win, (cuuint64_t)C.Hin, (cuuint64_t)nb};
@@ -1309,7 +1436,8 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
                           (const void*)conv_tc_kernel<false, true, true>,   (const void*)conv_tc_kernel<true, true, true>};
     for (int i = 0; i < 8 && ce == cudaSuccess; ++i)
       ce = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
       delete plan;
@@ -1358,9 +1486,12 @@ cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_r
   P.epi.raw_nchw = ext_raw;
   cudaError_t e;
   const dim3 grid(plan->grid), block(kThreads);
-#define ACCEL_TC_LAUNCH(N_, F_, T_) launch_k(conv_tc_kernel<N_, F_, T_>, grid, block, plan->smem, stream, P)
+#define ACCEL_TC_LAUNCH(N_, F_, T_)                                                                             \
+  (P.mcast ? launch_k_cluster(conv_tc_kernel<N_, F_, T_>, grid, block, plan->smem, stream, 2u, P)                \
+           : launch_k(conv_tc_kernel<N_, F_, T_>, grid, block, plan->smem, stream, P))
   const bool two = P.kchains == 2;
-  if (P.pair) e = launch_k_cluster(conv_tc2_kernel, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P);
+  if (P.pair) e = two ? launch_k_cluster(conv_tc2_kernel<true>, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P)
+                      : launch_k_cluster(conv_tc2_kernel<false>, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P);
   else if (P.fused) e = P.ncat ? (two ? ACCEL_TC_LAUNCH(true, true, true) : ACCEL_TC_LAUNCH(true, true, false))
                                : (two ? ACCEL_TC_LAUNCH(false, true, true) : ACCEL_TC_LAUNCH(false, true, false));
   else e = P.ncat ? (two ? ACCEL_TC_LAUNCH(true, false, true) : ACCEL_TC_LAUNCH(true, false, false))

@@ -209,6 +209,43 @@ def test_conv_layer_matches_torch(case, engine):
     assert (out - ref).abs().max().item() < _tol(ref)
 
 
+# CTA-pair kernel (conv_tc2_kernel, cta_group::2: 256-pixel x 128-channel tiles, each SM stages half of the weight rows):
+# forced on for every shape the planner admits -- odd tile counts (a phantom tile in the last pair), partial tiles,
+# stride 2, few / many output channels, long K (two accumulation chains as K halves), a residual.
+PAIR_CASES = CONV_CASES + [(256, 256, 64, 128, 3, 1, 1, 1), (1024, 256, 24, 128, 1, 1, 0, 1), (512, 2048, 5, 128, 1, 1, 0, 1),
+                           (2048, 512, 64, 128, 1, 1, 0, 1)]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_layer_cta_pairs(case, monkeypatch):
+    monkeypatch.setenv("ACCEL_TC_PAIR", "1")
+    cin, cout, h, w, k, s, p, d = case
+    x = _rand(1, cin, h, w, seed=50)
+    wt = _rand(cout, cin, k, k, seed=51, scale=(2.0 / (cin * k * k)) ** 0.5)
+    scale, shift = torch.rand(cout, generator=torch.Generator().manual_seed(52)) + 0.5, _rand(cout, seed=53, scale=0.1)
+    ref = F.conv2d(x, wt, None, s, p, d) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = _rand(*ref.shape, seed=54)
+    ref = F.relu(ref + res)
+    out = E.conv_layer(x.to(DEV), wt, "conv", s, p, d, scale, shift, act=1, residual=res.to(DEV), engine=2).cpu()
+    assert (out - ref).abs().max().item() < _tol(ref)
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_layer_weight_multicast(case, monkeypatch):
+    """ACCEL_TC_MCAST=1: clusters of two CTAs on two M tiles of one N tile, each CTA loads one plane of the weight tile and
+    multicasts it into both rings (TcParams::mcast) -- forced on for every shape the planner admits."""
+    monkeypatch.setenv("ACCEL_TC_MCAST", "1")
+    cin, cout, h, w, k, s, p, d = case
+    x = _rand(1, cin, h, w, seed=60)
+    wt = _rand(cout, cin, k, k, seed=61, scale=(2.0 / (cin * k * k)) ** 0.5)
+    scale, shift = torch.rand(cout, generator=torch.Generator().manual_seed(62)) + 0.5, _rand(cout, seed=63, scale=0.1)
+    ref = F.conv2d(x, wt, None, s, p, d) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = _rand(*ref.shape, seed=64)
+    ref = F.relu(ref + res)
+    out = E.conv_layer(x.to(DEV), wt, "conv", s, p, d, scale, shift, act=1, residual=res.to(DEV), engine=2).cpu()
+    assert (out - ref).abs().max().item() < _tol(ref)
+
+
 # Wide maps (W >= 128): one-row tiles, where the taps of a filter row share one TMA slab (TcParams::aslab, tap-shifted
 # shared-memory descriptors) -- incl. a right border that is not a multiple of the tile, dilation 2 (the offset convs of
 # res5), few and many output channels, a long K (two accumulation chains) and a transposed-conv phase set.

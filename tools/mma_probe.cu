@@ -452,8 +452,16 @@ int main() {
   const size_t big = (size_t)1 << 30;
   CK(cudaMalloc(&d_big, big));
   CK(cudaMemset(d_big, 1, big));
+  for (int nsm = sms / 4; nsm <= sms; nsm *= 2) {     // fewer SMs streaming: is the limit per SM or L2-wide?
+    stream_probe<<<nsm, 32, smem>>>(d_src, (size_t)256 * 1024, 3, 64 * 1024, 600, d_out, 16384);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, d_out, sizeof(long long) * nsm, cudaMemcpyDeviceToHost));
+    double sum = 0;
+    for (int b = 0; b < nsm; ++b) sum += h[b];
+    printf("L2    %3d CTAs streaming, 192 KB in flight each: %6.1f B/cycle/SM\n", nsm, 64.0 * 1024.0 * 600 / (sum / nsm));
+  }
   for (int mode = 0; mode < 2; ++mode)
-    for (int chunk = 16; chunk <= 64; chunk *= 2)
+    for (int chunk = 16; chunk <= 16; chunk *= 2)
     for (int slot = 64; slot <= 64; slot *= 2)
       for (int depth = 1; depth <= 3 && depth * slot <= 208; ++depth) {
         const int its = 600;
