@@ -120,30 +120,28 @@ struct alignas(16) Half8 {
   __half2 v[4];
 };
 
-// 8 consecutive channels of one pixel: hi + lo -> fp32
+// 8 consecutive channels of one pixel: hi + lo -> fp32.  Explicit 128-bit accesses: a copy of the Half8 struct was
+// scalarised by the compiler into four 32-bit loads / stores (cuobjdump: 34 LDG.E.32 in dcn_col_kernel), i.e. four times the
+// L1 data-pipe wavefronts -- which is what that kernel is bound by (ncu: l1tex__data_pipe_lsu_wavefronts 90 % of peak).
 __device__ __forceinline__ void load8(const __half* hi, const __half* lo, float out[8]) {
-  Half8 a = *reinterpret_cast<const Half8*>(hi);
-  Half8 b = *reinterpret_cast<const Half8*>(lo);
+  const uint4 a = *reinterpret_cast<const uint4*>(hi);
+  const uint4 b = *reinterpret_cast<const uint4*>(lo);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 fa = __half22float2(a.v[i]);
-    float2 fb = __half22float2(b.v[i]);
+    const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[i]));
+    const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[i]));
     out[2 * i] = fa.x + fb.x;
     out[2 * i + 1] = fa.y + fb.y;
   }
 }
 
 __device__ __forceinline__ void store8(__half* hi, __half* lo, const float v[8]) {
-  Half8 a, b;
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t h2, l2;
-    split_pair(v[2 * i], v[2 * i + 1], h2, l2);
-    a.v[i] = *reinterpret_cast<__half2*>(&h2);
-    b.v[i] = *reinterpret_cast<__half2*>(&l2);
-  }
-  *reinterpret_cast<Half8*>(hi) = a;
-  *reinterpret_cast<Half8*>(lo) = b;
+  for (int i = 0; i < 4; ++i) split_pair(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 struct alignas(8) Half4 {

@@ -231,62 +231,64 @@ __global__ void __launch_bounds__(256) dcn_col_warp_kernel(const DcnColParams P)
   }
 }
 
-// Tiled variant (ACCEL_DCN_TILED=1; measured SLOWER, 115 vs 93 us per 64 x 128 x 512 layer, although it halves the L2 -> SM
-// bytes -- profiles/r02_ncu_dcn_col.txt -- so the kernel is not bound by them): a CTA owns an 8 x 8 block of output pixels and 128 channels (of one deformable group), a
+// Tiled variant (default since load8 / store8 issue 128-bit accesses; ACCEL_DCN_TILED=0 = the per-thread kernel): a CTA owns an 8 x 4 block of output pixels and 128 channels (of one deformable group), a
 // half-warp one (pixel, tap), a lane eight channels.  The 9 taps x 4 corners of neighbouring pixels overlap heavily (the taps sit
 // `dilate` pixels apart, the learned offsets move them by a few pixels), so with all of them gathered by the same SM the
 // L1 cache serves most of the 128-byte corner reads: the per-thread kernel above spreads one pixel's taps over several
 // SMs and fetches every corner from L2 (ncu: l1tex 90 % busy, 604 MB L2 -> SM per 64 x 128 x 512 layer).  Sampling
 // position, clamping and weights are computed once per (pixel, tap, group); same arithmetic order, same stores.
-constexpr int DCN_TB = 8;
+constexpr int DCN_TBX = 8, DCN_TBY = 4;   // output pixels per CTA (x, y)
 constexpr int DCN_CB = 128;          // channels per CTA: 16 lanes x 8 channels
 __global__ void __launch_bounds__(256) dcn_col_tile_kernel(const DcnColParams P) {
   pdl_trigger();
   pdl_wait();
-  const int tiles_x = (P.W + DCN_TB - 1) / DCN_TB;
-  const int ty0 = (blockIdx.x / tiles_x) * DCN_TB, tx0 = (blockIdx.x % tiles_x) * DCN_TB;
+  const int tiles_x = (P.W + DCN_TBX - 1) / DCN_TBX;
+  const int ty0 = (blockIdx.x / tiles_x) * DCN_TBY, tx0 = (blockIdx.x % tiles_x) * DCN_TBX;
   const int cb = blockIdx.y * DCN_CB;                              // this CTA's DCN_CB channels (inside one deformable group)
   const int cpg = P.C / P.dg;
   const int dgi = cb / cpg;
   const int half = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);            // the 16 lanes of this half-warp
   const size_t plane = (size_t)P.H * P.W;
   const float* offp = P.offset + (size_t)(dgi * 18) * plane;
-  for (int w = half; w < DCN_TB * DCN_TB * 9; w += 16) {
-    const int pl = w / 9, t = w - pl * 9;
-    const int oy = ty0 + pl / DCN_TB, ox = tx0 + pl % DCN_TB;
-    if (oy >= P.H || ox >= P.W) continue;
+  const int c0 = cb + hl * 8;
+  // a half-warp walks whole pixels: the pixel's 18 offsets are fetched once (lane l: offsets l and 16 + (l & 1)) and
+  // handed round by shuffles, so the nine taps are nine independent gather / interpolate / store groups
+  for (int pl = half; pl < DCN_TBX * DCN_TBY; pl += 16) {
+    const int oy = ty0 + pl / DCN_TBX, ox = tx0 + pl % DCN_TBX;
+    if (oy >= P.H || ox >= P.W) continue;                          // (uniform per half-warp)
     const int p = oy * P.W + ox;
-    const int ti = t / 3, tj = t - ti * 3;
-    float py = (float)(oy - P.pad) + (float)(ti * P.dilate) + __ldg(offp + (size_t)(2 * t) * plane + p);
-    float px = (float)(ox - P.pad) + (float)(tj * P.dilate) + __ldg(offp + (size_t)(2 * t + 1) * plane + p);
-    const bool inside = py >= 0.f && px >= 0.f && py < (float)P.H && px < (float)P.W;
-    size_t o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-    float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
-    if (inside) {
-      int y0 = (int)floorf(py), x0 = (int)floorf(px);
-      int y1, x1;
-      if (y0 >= P.H - 1) { y0 = y1 = P.H - 1; py = (float)y0; } else { y1 = y0 + 1; }
-      if (x0 >= P.W - 1) { x0 = x1 = P.W - 1; px = (float)x0; } else { x1 = x0 + 1; }
-      const float ly = py - (float)y0, lx = px - (float)x0;
-      const float hy = 1.f - ly, hx = 1.f - lx;
-      w00 = hy * hx; w01 = hy * lx; w10 = ly * hx; w11 = ly * lx;
-      o00 = ((size_t)y0 * P.W + x0) * P.in_ld; o01 = ((size_t)y0 * P.W + x1) * P.in_ld;
-      o10 = ((size_t)y1 * P.W + x0) * P.in_ld; o11 = ((size_t)y1 * P.W + x1) * P.in_ld;
-    }
-    {
-      const int c0 = cb + hl * 8;
+    const float o_a = __ldg(offp + (size_t)hl * plane + p);
+    const float o_b = __ldg(offp + (size_t)(16 + (hl & 1)) * plane + p);
+    const float by = (float)(oy - P.pad), bx = (float)(ox - P.pad);
+    const size_t orow = (size_t)p * P.col_ld + c0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int ti = t / 3, tj = t - ti * 3;
+      const float offy = t < 8 ? __shfl_sync(hmask, o_a, 2 * t, 16) : __shfl_sync(hmask, o_b, 0, 16);
+      const float offx = t < 8 ? __shfl_sync(hmask, o_a, 2 * t + 1, 16) : __shfl_sync(hmask, o_b, 1, 16);
+      float py = by + (float)(ti * P.dilate) + offy;
+      float px = bx + (float)(tj * P.dilate) + offx;
       float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (inside) {
+      if (py >= 0.f && px >= 0.f && py < (float)P.H && px < (float)P.W) {
+        int y0 = (int)floorf(py), x0 = (int)floorf(px);
+        int y1, x1;
+        if (y0 >= P.H - 1) { y0 = y1 = P.H - 1; py = (float)y0; } else { y1 = y0 + 1; }
+        if (x0 >= P.W - 1) { x0 = x1 = P.W - 1; px = (float)x0; } else { x1 = x0 + 1; }
+        const float ly = py - (float)y0, lx = px - (float)x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
+        const size_t o00 = ((size_t)y0 * P.W + x0) * P.in_ld + c0, o01 = ((size_t)y0 * P.W + x1) * P.in_ld + c0;
+        const size_t o10 = ((size_t)y1 * P.W + x0) * P.in_ld + c0, o11 = ((size_t)y1 * P.W + x1) * P.in_ld + c0;
         float a[8], b[8], c[8], d[8];
-        load8(P.in_hi + o00 + c0, P.in_lo + o00 + c0, a);
-        load8(P.in_hi + o01 + c0, P.in_lo + o01 + c0, b);
-        load8(P.in_hi + o10 + c0, P.in_lo + o10 + c0, c);
-        load8(P.in_hi + o11 + c0, P.in_lo + o11 + c0, d);
+        load8(P.in_hi + o00, P.in_lo + o00, a);
+        load8(P.in_hi + o01, P.in_lo + o01, b);
+        load8(P.in_hi + o10, P.in_lo + o10, c);
+        load8(P.in_hi + o11, P.in_lo + o11, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) out[i] = ((a[i] * w00 + b[i] * w01) + c[i] * w10) + d[i] * w11;
       }
-      const size_t oo = (size_t)p * P.col_ld + (size_t)t * P.C + c0;
-      store8(P.col_hi + oo, P.col_lo + oo, out);
+      store8(P.col_hi + orow + (size_t)t * P.C, P.col_lo + orow + (size_t)t * P.C, out);
     }
   }
 }
@@ -701,10 +703,10 @@ cudaError_t launch_dcn_col(const DcnColParams& P, cudaStream_t stream) {
     const long long warps = (long long)P.H * P.W * 9;
     return launch_k(dcn_col_warp_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, P);
   }
-  static int tiled = -1;                         // ACCEL_DCN_TILED=1: the tiled kernel (measured slower: 115 vs 93 us, stays off)
-  if (tiled < 0) { const char* e = getenv("ACCEL_DCN_TILED"); tiled = (e && e[0] == '1') ? 1 : 0; }
+  static int tiled = -1;                         // ACCEL_DCN_TILED=0: the one-thread-per-(pixel, tap, 8 channels) kernel
+  if (tiled < 0) { const char* e = getenv("ACCEL_DCN_TILED"); tiled = (e && e[0] == '0') ? 0 : 1; }
   if (tiled && P.C % P.dg == 0 && (P.C / P.dg) % DCN_CB == 0) {
-    const int tiles = ((P.W + DCN_TB - 1) / DCN_TB) * ((P.H + DCN_TB - 1) / DCN_TB);
+    const int tiles = ((P.W + DCN_TBX - 1) / DCN_TBX) * ((P.H + DCN_TBY - 1) / DCN_TBY);
     return launch_k(dcn_col_tile_kernel, dim3((unsigned)tiles, (unsigned)(P.C / DCN_CB)), dim3(256), 0, stream, P);
   }
   const long long work = (long long)P.H * P.W * 9 * (P.C / 8);

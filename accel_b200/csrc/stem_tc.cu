@@ -168,12 +168,18 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bfull, b_bytes);
-      for (int b = 0; b < P.nblocks; ++b) {
-        tma_load_2d(smem0 + b * 16384, &P.b_hi, bfull, b * 64, 0);
-        tma_load_2d(smem0 + b * 16384 + 8192, &P.b_lo, bfull, b * 64, 0);
+    // converged warp, elect.sync around the tcgen05 / TMA instructions: operands in uniform registers (under
+    // `if (lane == 0)` every UTCHMMA sat in an ELECT / R2UR waterfall, ~180 cycles per MMA against the N = 64 MMA's 62 --
+    // this loop, not the producers, was the 77 us hand-off floor of profiles/r01_stem_decomposition.txt)
+    {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bfull, b_bytes);
+        for (int b = 0; b < P.nblocks; ++b) {
+          tma_load_2d(smem0 + b * 16384, &P.b_hi, bfull, b * 64, 0);
+          tma_load_2d(smem0 + b * 16384 + 8192, &P.b_lo, bfull, b * 64, 0);
+        }
       }
+      __syncwarp();
       mbar_wait(bfull, 0);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const int kreal = P.nchunks * 8;
@@ -192,15 +198,23 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
           const uint64_t ah = umma_desc(sa), al = umma_desc(sa + 16384);
           const uint64_t bh = umma_desc(smem0 + b * 16384), bl = umma_desc(smem0 + b * 16384 + 8192);
           const int slices = min(4, (kreal - b * 64 + 15) / 16);
-          for (int ks = 0; ks < slices; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);
-            umma_f16(d, ah + adv, bh + adv, idesc, (b > 0 || ks > 0) ? 1u : 0u);
-            umma_f16(d, ah + adv, bl + adv, idesc, 1u);
-            umma_f16(d, al + adv, bh + adv, idesc, 1u);
+          const uint32_t first0 = b > 0 ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < slices) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                umma_f16(d, ah + adv, bh + adv, idesc, ks > 0 ? 1u : first0);
+                umma_f16(d, ah + adv, bl + adv, idesc, 1u);
+                umma_f16(d, al + adv, bh + adv, idesc, 1u);
+              }
+            }
+            umma_commit(empty0 + 8 * s);
           }
-          umma_commit(empty0 + 8 * s);
+          __syncwarp();
         }
-        umma_commit(tfull0 + 8 * acc);
+        if (elect_one()) umma_commit(tfull0 + 8 * acc);
+        __syncwarp();
         if (++acc == 2) { acc = 0; accph ^= 1; }
       }
     }

@@ -519,6 +519,10 @@ static cudaError_t launch_fused_variant(const WarpParams& P, int once_slot, cuda
   if (by > ngroups) by = ngroups;
   const int per = (ngroups + by - 1) / by;                       // equal number of groups per CTA: no straggler wave
   by = (ngroups + per - 1) / per;
+  {
+    const int force = env_int("ACCEL_WARP_FUSED_BY", 0);         // tuning aid: CTAs per row tile, unequal group counts allowed
+    if (force > 0 && force <= ngroups) by = force;
+  }
   return launch_k(warp_kernel_fused<CONS, STAGES>, dim3(bx, by), dim3(CONS + 32), smem, stream, F);
 }
 
