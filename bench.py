@@ -651,6 +651,12 @@ def run_native(a):
         conv["executed_graph_gflop_per_step"] = exec_step
         conv["executed_fp16_mma_tflops"] = 3.0 * exec_step * a.steps / (ms_max / 1e3) / 1e3
         conv["executed_frac"] = conv["executed_fp16_mma_tflops"] / tf_peak
+        # what actually bounds the K-heavy layers' mainloop (profiles/r02_mma_probe.txt, r02_ncu_conv_s2.txt)
+        conv["mainloop_bound"] = {"bound": "shared-memory bandwidth", "bytes_per_k_stage": 147456,
+                                  "what": "per 128x128x64 stage the tensor core reads 80 KB of split-fp16 operands and TMA writes 64 KB",
+                                  "measured_smem_bytes_per_cycle": 134, "roofline_cycles_per_stage": 1100,
+                                  "tensor_issue_floor_cycles_per_stage": 768, "kernel_cycles_per_stage": "1100-1130 (tools/tc_trace.py)",
+                                  "source": "tools/mma_probe.cu on this GPU model, committed under profiles/ (not re-measured by bench.py)"}
         mode = "interval plan (the interval's frames issued as one CUDA graph: per-frame chains run concurrently)" if use_batched \
             else ("key-frame lookahead" if look else "online")
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
