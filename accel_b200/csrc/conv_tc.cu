@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         int it = kb + rot;                                // each CTA walks K from its own offset: neighbours do not
         int t = it / P.chunks, kc = it - t * P.chunks;    // stream the same weight lines at the same moment
         for (int i = kb; i < ke; ++i) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          if (P.debug & 8192) mbar_wait_spin(empty0 + 8 * s, ph ^ 1);
+          else mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t fb = full0 + 8 * s;
           const uint32_t sa = smem0 + s * stage_bytes;
           const int dy = P.dy[t], dx = P.dx[t];
@@ -394,7 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               b_hi = a_hi + 2 * a_bytes;
               b_lo = b_hi + b_bytes;
             }
-            mbar_wait(full0 + 8 * s, ph);
+            if (P.debug & 8192) mbar_wait_spin(full0 + 8 * s, ph);
+            else mbar_wait(full0 + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (it == kb) TC_TRACE(4, item);
             if (P.debug & 4096) TC_TRACE(10, it);             // per stage: operands landed

@@ -31,6 +31,15 @@ LAYERS = {
     "res5_off": (512, 18, 64, 128, 3, 1, 1, 1, False),
     "flow_conv3_1": (256, 256, 128, 256, 3, 1, 1, 1, False),
     "flow_conv3": (128, 256, 128, 256, 5, 2, 2, 1, False),
+    "flow_conv2": (64, 128, 512, 1024, 5, 2, 2, 1, False),
+    "flow_conv4": (256, 512, 128, 256, 3, 2, 1, 1, False),
+    "flow_conv5": (512, 512, 64, 128, 3, 2, 1, 1, False),
+    "flow_conv6": (512, 1024, 32, 64, 3, 2, 1, 1, False),
+    "r18_s1": (64, 64, 256, 512, 3, 1, 1, 1, True),
+    "r18_s1_x4": (64, 64, 1024, 512, 3, 1, 1, 1, True),
+    "r18_s2_x4": (128, 128, 512, 256, 3, 1, 1, 1, True),
+    "r18_s3_x4": (256, 256, 256, 128, 3, 1, 1, 1, True),
+    "r18_s4_x4": (512, 512, 256, 128, 3, 1, 2, 2, True),
     # the same layers over 5 frames stacked along H: what batching an interval's frames through one launch would give
     "res2_2c_x5": (64, 256, 1280, 512, 1, 1, 0, 1, True),
     "res2_br1_x5": (64, 256, 1280, 512, 1, 1, 0, 1, False),
@@ -128,6 +137,7 @@ PAIR3_SWEEP = [{"ACCEL_TC_PAIR": "0"}, {"ACCEL_TC_PAIR": "1"}, {"ACCEL_TC_PAIR":
 PAIR4_SWEEP = [{"ACCEL_TC_PAIR": "1", "ACCEL_TC_DEBUG": str(d)} for d in (128, 384, 128 + 512, 128 + 1024, 391)] + \
               [{"ACCEL_TC_PAIR": "0", "ACCEL_TC_DEBUG": str(d)} for d in (128, 384, 128 + 512, 128 + 1024)]
 MC_SWEEP = [{"ACCEL_TC_MCAST": "0"}, {"ACCEL_TC_MCAST": "1"}, {"ACCEL_TC_MCAST": "1", "ACCEL_TC_DEBUG": "128"}, {"ACCEL_TC_MCAST": "0", "ACCEL_TC_DEBUG": "128"}]
+SPIN_SWEEP = [{}, {"ACCEL_TC_DEBUG": "8192"}, {"ACCEL_TC_DEBUG": "384"}, {"ACCEL_TC_DEBUG": str(384 + 8192)}]
 RA_SWEEP = [{}] + [{"ACCEL_TC_RES_AHEAD": str(d)} for d in (2, 4, 6, 8, 12)]
 PF2_SWEEP = [{}, {"ACCEL_TC_PREFETCH": "4"}, {"ACCEL_TC_PREFETCH": "8"}, {"ACCEL_TC_PREFETCH": "260"}, {"ACCEL_TC_PREFETCH": "264"}, {"ACCEL_TC_PREFETCH": "2"}]
 
@@ -154,7 +164,7 @@ def main():
             sys.stderr.flush()
             E.conv_layer(x, wt, "conv", s, p, d, act=1, residual=r, engine=2)
             continue
-        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP, "pair2": PAIR2_SWEEP, "shortk": SHORTK_SWEEP, "s2": S2_SWEEP, "pf2": PF2_SWEEP, "ra": RA_SWEEP, "mc": MC_SWEEP, "pair4": PAIR4_SWEEP, "pair3": PAIR3_SWEEP, "env": None}.get(a.sweep, SWEEP):
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP, "pair2": PAIR2_SWEEP, "shortk": SHORTK_SWEEP, "s2": S2_SWEEP, "pf2": PF2_SWEEP, "ra": RA_SWEEP, "spin": SPIN_SWEEP, "mc": MC_SWEEP, "pair4": PAIR4_SWEEP, "pair3": PAIR3_SWEEP, "env": None}.get(a.sweep, SWEEP):
             for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR", "ACCEL_TC_ASLAB",
                        "ACCEL_TC_MCAST", "ACCEL_TC_PREFETCH", "ACCEL_TC_RES_AHEAD", "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO", "ACCEL_TC_RES_PREFETCH", "ACCEL_TC_NCAT", "ACCEL_TC_WIDE_KMAX"):
                 os.environ.pop(kk, None)
