@@ -76,6 +76,7 @@ struct alignas(64) TcParams {
   int mcast;       // 1: launched as clusters of two CTAs that work on two M tiles of the SAME N tile in lockstep; each CTA loads one
                    // plane of the weight tile (B_hi / B_lo) and multicasts it into both CTAs' rings: 48 instead of 64 KB of L2
                    // reads per CTA and K stage (the L2 output, ~20 TB/s over all SMs, is what bounds the mainloop)
+  int epiw16;      // TMA epilogue with 16 epilogue warps (conv_tc_kernel<..., 16>) when the launch has a plain main output only
   int res_ahead;   // TMA epilogue: chunks of L2 prefetch distance for the residual tiles (0: none)
   int kchains;     // 2: the K slices of a tile alternate between the two TMEM accumulator buffers and the epilogue sums
                    // them in fp32 (round-to-nearest): the tensor core's own accumulation truncates, so its error grows
@@ -159,8 +160,12 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {   
                : "memory");
 }
 
-template <bool NCAT, bool FUSED = false, bool TWO = false>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
+// EPIW: epilogue warps.  8 = two per TMEM lane quarter (each thread one pixel row x 32 channels of a chunk).  16 (TMA epilogue
+// with a plain main output only, TcParams::epiw): four per quarter -- two chunk sets x two 16-channel halves of a chunk: the
+// TMA epilogue is bound by instruction issue / latency with 8 warps (ncu: issue slots 39 % busy, 11.4k warp instructions per
+// 128 x 128 tile), so the expand convs, whose mainloop is 4 K stages, spent 80 % of their time in it.
+template <bool NCAT, bool FUSED = false, bool TWO = false, int EPIW = 8>
+__global__ void __launch_bounds__(64 + 32 * EPIW + 32 * kDmaWarps, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -190,10 +195,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, kEpiWarps);
+      mbar_init(tempty0 + 8 * a, EPIW);
     }
     for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&res_bars[a]), 1);
-    for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&stg_bars[a]), 128);
+    for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&stg_bars[a]), 16 * EPIW);
     for (int a = 0; a < 8; ++a) mbar_init(smem_u32(&abars[a]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -438,13 +443,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         TC_TRACE(5, item);
       }
     }
-  } else if (warp >= 2 + kEpiWarps) {
+  } else if (warp >= 2 + EPIW) {
     // ===================================== epilogue DMA (TMA epilogue only) ===================
     // One thread per chunk set owns every bulk operation of that set's two staging buffers, so that no epilogue thread ever
     // waits for a store: chunk k (buffer k & 1) is stored when its 128 threads have arrived on stg_bars, and once the
     // store has read the buffer it is handed to chunk k + 2 -- with that chunk's residual tile on the way (res_bars carries
     // the bytes) or, without a residual, by a plain arrival.
-    const int cset = warp - (2 + kEpiWarps);
+    const int cset = warp - (2 + EPIW);
     if (P.tma_out && P.splits == 1 && lane == 0 && cset < 2) {
       const Epilogue& E = P.epi;
       const bool has_res = E.res_hi != nullptr && !(P.debug & 16);
@@ -510,7 +515,101 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       bulk_wait0();
     }
   } else {
-    if (P.tma_out && P.splits == 1) {
+    if constexpr (EPIW == 16) {
+      // ===================================== epilogue, TMA both ways, 16 warps ==================
+      // Same protocol as the 8-warp version below (buffers, mbarriers, DMA threads); a thread owns one pixel row and 16 of
+      // the chunk's 32 channels: warp -> (TMEM lane quarter, chunk set, channel half).  Main split output (+ residual) only.
+      const int e = warp - 2;
+      const int quarter = warp & 3, cset = (e >> 2) & 1, chalf = e >> 3;
+      const int r = quarter * 32 + lane;
+      const int et = threadIdx.x - 64;
+      const Epilogue& E = P.epi;
+      const bool has_res = E.res_hi != nullptr && !(P.debug & 16);
+      const uint32_t sb0 = stg0 + (uint32_t)cset * 2u * 16384u;
+      const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]), sbar0 = smem_u32(&stg_bars[cset * 2]);
+      const uint32_t acc_cols = (uint32_t)(NCAT ? 2 * P.BN : P.BN);
+      const uint32_t row = (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
+      const uint32_t p0 = row + (((uint32_t)(2 * chalf) ^ sw) << 4), p1 = row + (((uint32_t)(2 * chalf + 1) ^ sw) << 4);
+      int acc = 0, sci = 0, n = 0;
+      uint32_t accph = 0;
+      float sc_next = 1.f, sh_next = 0.f;
+      auto fetch_sc = [&](int item2) {
+        const int c = ((item2 / P.splits) % P.n_tiles) * P.BN + et;
+        const bool in = et < P.BN && c < E.Cout;
+        sc_next = (in && E.scale) ? __ldg(E.scale + c) : 1.f;
+        sh_next = (in && E.shift) ? __ldg(E.shift + c) : 0.f;
+      };
+      if (it0 < items) fetch_sc(it0);
+      for (int item = it0; item < items; item += itstep) {
+        if (et < P.BN) {
+          epi_sc[sci][0][et] = sc_next;
+          epi_sc[sci][1][et] = sh_next;
+        }
+        if (item + itstep < items) fetch_sc(item + itstep);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        mbar_wait(tfull0 + 8 * acc, accph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(chalf * 16);
+        for (int cc = cset * 32; cc < P.BN; cc += 64, ++n) {
+          const int b = n & 1;
+          const uint32_t sb = sb0 + (uint32_t)b * 16384u;
+          float v[16];
+          if (P.debug & 64) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          } else {
+            tmem_ld16(taddr + cc, v);
+            if (NCAT) {
+              float v2[16];
+              tmem_ld16(taddr + P.BN + cc, v2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += v2[i];
+            }
+          }
+          const float* sc = &epi_sc[sci][0][cc + chalf * 16];
+          const float* sh = &epi_sc[sci][1][cc + chalf * 16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 s4 = *(reinterpret_cast<const float4*>(sc) + q);
+            const float4 b4 = *(reinterpret_cast<const float4*>(sh) + q);
+            v[4 * q + 0] = fmaf(v[4 * q + 0], s4.x, b4.x);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], s4.y, b4.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], s4.z, b4.z);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], s4.w, b4.w);
+          }
+          mbar_wait(rbar0 + 8u * b, (uint32_t)((n >> 1) & 1));          // buffer b is ours (and holds the residual rows)
+          if (has_res) {
+            uint32_t h[8], l[8];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(sb + p0));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]) : "r"(sb + p1));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(sb + 8192u + p0));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[4]), "=r"(l[5]), "=r"(l[6]), "=r"(l[7]) : "r"(sb + 8192u + p1));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 fh = unpack_h2(h[i]), fl = unpack_h2(l[i]);
+              v[2 * i] += fh.x + fl.x;
+              v[2 * i + 1] += fh.y + fl.y;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], E.act);
+          uint32_t wh[8], wl[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_pair(v[2 * i], v[2 * i + 1], wh[i], wl[i]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + p0), "r"(wh[0]), "r"(wh[1]), "r"(wh[2]), "r"(wh[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + p1), "r"(wh[4]), "r"(wh[5]), "r"(wh[6]), "r"(wh[7]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + 8192u + p0), "r"(wl[0]), "r"(wl[1]), "r"(wl[2]), "r"(wl[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + 8192u + p1), "r"(wl[4]), "r"(wl[5]), "r"(wl[6]), "r"(wl[7]) : "memory");
+          fence_async_smem();
+          mbar_arrive(sbar0 + 8u * b);                       // -> the set's DMA thread stores the buffer
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        sci ^= 1;
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
+    } else if (P.tma_out && P.splits == 1) {
       // ===================================== epilogue, TMA both ways ===========================
       // The lane-per-pixel global accesses of the direct epilogue are 32 separate lines per warp instruction and
       // saturate the L1TEX pipe (profiles/r01_ncu_dcn_col.txt shows the same pattern).  Here global memory is only
@@ -1426,6 +1525,12 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     }
   }
   if (P.tma_out) P.kchains = 1;
+  // measured (profiles/r02_layer_epiw16.txt, five frames batched): res2 shortcut -16 %, res3 expand -9 %, res4 expand -2 %,
+  // res5 expand (8 K stages) +4 % -> only where the tile's mainloop is at most ACCEL_TC_EPIW16_KMAX (4) K stages
+  {
+    const int m = env_int("ACCEL_TC_EPIW16", -1);
+    P.epiw16 = (P.tma_out && !P.mcast && !P.pair && (m == 1 || (m < 0 && P.kiters <= env_int("ACCEL_TC_EPIW16_KMAX", 4)))) ? 1 : 0;
+  }
   if (!ok) {
     delete plan;
     return nullptr;
@@ -1438,6 +1543,8 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
                           (const void*)conv_tc_kernel<false, true, true>,   (const void*)conv_tc_kernel<true, true, true>};
     for (int i = 0; i < 8 && ce == cudaSuccess; ++i)
       ce = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<false, false, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<true, false, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
@@ -1492,7 +1599,12 @@ cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_r
   (P.mcast ? launch_k_cluster(conv_tc_kernel<N_, F_, T_>, grid, block, plan->smem, stream, 2u, P)                \
            : launch_k(conv_tc_kernel<N_, F_, T_>, grid, block, plan->smem, stream, P))
   const bool two = P.kchains == 2;
-  if (P.pair) e = two ? launch_k_cluster(conv_tc2_kernel<true>, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P)
+  const bool w16 = P.epiw16 && P.tma_out && !two && !P.fused && !P.epi.out_nchw && !P.epi.raw_nchw && !P.epi.out2_hi;
+  if (w16) {
+    const dim3 block16(64 + 32 * 16 + 32 * kDmaWarps);
+    e = P.ncat ? launch_k(conv_tc_kernel<true, false, false, 16>, grid, block16, plan->smem, stream, P)
+               : launch_k(conv_tc_kernel<false, false, false, 16>, grid, block16, plan->smem, stream, P);
+  } else if (P.pair) e = two ? launch_k_cluster(conv_tc2_kernel<true>, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P)
                       : launch_k_cluster(conv_tc2_kernel<false>, dim3(plan->grid), dim3(kThreadsPair), plan->smem, stream, 2u, P);
   else if (P.fused) e = P.ncat ? (two ? ACCEL_TC_LAUNCH(true, true, true) : ACCEL_TC_LAUNCH(true, true, false))
                                : (two ? ACCEL_TC_LAUNCH(false, true, true) : ACCEL_TC_LAUNCH(false, true, false));
