@@ -285,6 +285,7 @@ struct ConvParams {
   int nb;              // frames (0/1 = one): input, outputs and residual hold `nb` frames stacked densely along H
   int splits;          // split-K factor (1 = epilogue in-kernel)
   float* partial;      // [splits][Ho*Wo][Cout_pad] fp32 when splits > 1
+  int ext_outputs;     // 1: a launch may add caller-owned fp32 outputs (launch_conv_tc_ext) to `epi`
   Epilogue epi;
 };
 

@@ -44,6 +44,7 @@ constexpr int kSmemMaxDynamic = 227 * 1024 - 6 * 1024;   // 227 KB per CTA minus
 // epilogue staging for TMA stores: per chunk set (2) x double buffer (2) x [hi | lo] x 128 pixel rows x 64 bytes
 constexpr int kStageOut = 2 * 2 * 2 * 8192;
 constexpr int kSmemBudget = kSmemMaxDynamic - 1024;      // minus the 1024-byte alignment slack
+constexpr int kSmemEpi1 = 3 * 65536 + 2 * 2 * 8192;      // conv_tc_kernel<..., 8, 1>: three 64 KB stages + 32 KB of staging
 
 struct alignas(64) TcParams {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -76,6 +77,8 @@ struct alignas(64) TcParams {
   int mcast;       // 1: launched as clusters of two CTAs that work on two M tiles of the SAME N tile in lockstep; each CTA loads one
                    // plane of the weight tile (B_hi / B_lo) and multicasts it into both CTAs' rings: 48 instead of 64 KB of L2
                    // reads per CTA and K stage (the L2 output, ~20 TB/s over all SMs, is what bounds the mainloop)
+  int epi1;        // TMA epilogue, half-chunk variant with ONE chunk set (conv_tc_kernel<..., 8, 1>): 32 KB of staging, one more
+                   // operand stage in the ring
   int epiw16;      // TMA epilogue with 16 epilogue warps (conv_tc_kernel<..., 16>) when the launch has a plain main output only
   int res_ahead;   // TMA epilogue: chunks of L2 prefetch distance for the residual tiles (0: none)
   int kchains;     // 2: the K slices of a tile alternate between the two TMEM accumulator buffers and the epilogue sums
@@ -164,12 +167,16 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {   
 // with a plain main output only, TcParams::epiw): four per quarter -- two chunk sets x two 16-channel halves of a chunk: the
 // TMA epilogue is bound by instruction issue / latency with 8 warps (ncu: issue slots 39 % busy, 11.4k warp instructions per
 // 128 x 128 tile), so the expand convs, whose mainloop is 4 K stages, spent 80 % of their time in it.
-template <bool NCAT, bool FUSED = false, bool TWO = false, int EPIW = 8>
+// CSETS = 1 (with EPIW = 8): the half-chunk epilogue with ONE chunk set -- all eight warps work on the same 32-channel chunk,
+// 32 KB of staging instead of 64, so that a THIRD 64 KB operand stage fits (229,376 dynamic + 3 KB static = the 227 KB limit
+// exactly): the expand convs' 2-stage ring was bound by its commit -> producer -> load -> issuer round trip.
+template <bool NCAT, bool FUSED = false, bool TWO = false, int EPIW = 8, int CSETS = 2>
 __global__ void __launch_bounds__(64 + 32 * EPIW + 32 * kDmaWarps, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
+  constexpr bool kHalf = EPIW == 16 || CSETS == 1;           // half-chunk TMA epilogue (a thread owns 16 channels of a chunk)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float epi_sc[2][2][256];          // [accumulator][scale | shift][channel of the tile]
+  __shared__ __align__(16) float epi_sc[2][2][kHalf ? 128 : 256];   // [accumulator][scale | shift][channel of the tile]
   __shared__ __align__(8) uint64_t res_bars[4];              // TMA epilogue: staging buffer [chunk set][buffer] is free / holds its residual
   __shared__ __align__(8) uint64_t stg_bars[4];              // TMA epilogue: all 128 threads of the chunk set wrote their result rows
   __shared__ int s_last;                                     // fused split-K: this CTA delivered the tile's last slab
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW + 32 * kDmaWarps, 1) conv_tc_ke
       mbar_init(tempty0 + 8 * a, EPIW);
     }
     for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&res_bars[a]), 1);
-    for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&stg_bars[a]), 16 * EPIW);
+    for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&stg_bars[a]), 32 * EPIW / CSETS);   // the threads of one chunk set
     for (int a = 0; a < 8; ++a) mbar_init(smem_u32(&abars[a]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -450,18 +457,19 @@ __global__ void __launch_bounds__(64 + 32 * EPIW + 32 * kDmaWarps, 1) conv_tc_ke
     // store has read the buffer it is handed to chunk k + 2 -- with that chunk's residual tile on the way (res_bars carries
     // the bytes) or, without a residual, by a plain arrival.
     const int cset = warp - (2 + EPIW);
-    if (P.tma_out && P.splits == 1 && lane == 0 && cset < 2) {
+    if (P.tma_out && P.splits == 1 && lane == 0 && cset < CSETS) {
       const Epilogue& E = P.epi;
       const bool has_res = E.res_hi != nullptr && !(P.debug & 16);
       const uint32_t sb0 = stg0 + (uint32_t)cset * 2u * 16384u;
       const uint32_t rbar0 = smem_u32(&res_bars[cset * 2]), sbar0 = smem_u32(&stg_bars[cset * 2]);
-      const int cpi = P.BN > cset * 32 ? (P.BN - cset * 32 + 63) / 64 : 0;       // chunks of one item that belong to this set
+      constexpr int cstep = 32 * CSETS;
+      const int cpi = P.BN > cset * 32 ? (P.BN - cset * 32 + cstep - 1) / cstep : 0;   // chunks of one item that belong to this set
       const int mine = it0 < items ? (items - it0 + itstep - 1) / itstep : 0;
       const int total = mine * cpi;
       auto coords = [&](int k, int& c0, int& x0, int& y0) {
         const int item = it0 + (k / cpi) * itstep;
         const int tile = item / P.splits, nt = tile % P.n_tiles, mt = (tile / P.n_tiles) * mstep + rank;
-        c0 = nt * P.BN + cset * 32 + (k % cpi) * 64;
+        c0 = nt * P.BN + cset * 32 + (k % cpi) * cstep;
         x0 = (mt % P.tiles_x) * P.BW;
         y0 = (mt / P.tiles_x) * P.BH;
       };
@@ -515,12 +523,12 @@ __global__ void __launch_bounds__(64 + 32 * EPIW + 32 * kDmaWarps, 1) conv_tc_ke
       bulk_wait0();
     }
   } else {
-    if constexpr (EPIW == 16) {
+    if constexpr (kHalf) {
       // ===================================== epilogue, TMA both ways, 16 warps ==================
       // Same protocol as the 8-warp version below (buffers, mbarriers, DMA threads); a thread owns one pixel row and 16 of
       // the chunk's 32 channels: warp -> (TMEM lane quarter, chunk set, channel half).  Main split output (+ residual) only.
       const int e = warp - 2;
-      const int quarter = warp & 3, cset = (e >> 2) & 1, chalf = e >> 3;
+      const int quarter = warp & 3, cset = CSETS == 2 ? (e >> 2) & 1 : 0, chalf = CSETS == 2 ? e >> 3 : e >> 2;
       const int r = quarter * 32 + lane;
       const int et = threadIdx.x - 64;
       const Epilogue& E = P.epi;
@@ -546,11 +554,11 @@ __global__ void __launch_bounds__(64 + 32 * EPIW + 32 * kDmaWarps, 1) conv_tc_ke
           epi_sc[sci][1][et] = sh_next;
         }
         if (item + itstep < items) fetch_sc(item + itstep);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPIW) : "memory");
         mbar_wait(tfull0 + 8 * acc, accph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(chalf * 16);
-        for (int cc = cset * 32; cc < P.BN; cc += 64, ++n) {
+        for (int cc = cset * 32; cc < P.BN; cc += 32 * CSETS, ++n) {
           const int b = n & 1;
           const uint32_t sb = sb0 + (uint32_t)b * 16384u;
           float v[16];
@@ -1370,7 +1378,16 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   // ring stages still fit (BN <= 128).
   const bool want_stage = !P.pair && (tma_mode > 0 || (auto_t && bn == best_bn)) && splits == 1 && C.epi.out_hi != nullptr &&
                           (kSmemBudget - kStageOut) / stage_bytes >= 2;
-  int stages = (int)((kSmemBudget - (want_stage ? kStageOut : 0)) / stage_bytes);
+  // Half-size staging (ONE chunk set, TcParams::epi1, ACCEL_TC_EPI1=1) buys a third operand stage: main split output
+  // (+ residual) only.  229,376 bytes of dynamic shared memory + the kernel's 3 KB
+  // of static = exactly the 227 KB a block may have; the ring is 1024-aligned by the array's own alignment (no slack).
+  const Epilogue& E0 = C.epi;
+  const int epi1_mode = env_int("ACCEL_TC_EPI1", -1);
+  const bool epi1 = want_stage && stage_bytes == 65536 && !E0.out2_hi && !E0.out_nchw && !E0.raw_nchw && !C.ext_outputs &&
+                    epi1_mode == 1;      // MEASURED SLOWER (one chunk set halves the epilogue's throughput: res4 expand x5 frames
+                                         // 92 -> 129 us, profiles/r02_layer_epi1.txt): opt-in only
+  P.epi1 = epi1 ? 1 : 0;
+  int stages = epi1 ? 3 : (int)((kSmemBudget - (want_stage ? kStageOut : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   P.stages = stages;
   P.ring_bytes = (unsigned)(stages * stage_bytes);
@@ -1403,7 +1420,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
       P.ring_bytes = (unsigned)(sa * 2 * slab_pl + sb * b_stage);
     }
   }
-  plan->smem = P.ring_bytes + 1024 + (want_stage ? kStageOut : 0);
+  plan->smem = P.epi1 ? P.ring_bytes + kStageOut / 2 : P.ring_bytes + 1024 + (want_stage ? kStageOut : 0);
   // hi*hi and hi*lo as one N = 2*BN MMA (see the MMA issuer): needs 4*BN TMEM columns, i.e. BN <= 128.
   // ACCEL_TC_NCAT: -1 auto (on whenever it fits), 0 off, 1 on.
   {
@@ -1430,7 +1447,7 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
   // unset = auto (at least ACCEL_TC_MCAST_KMIN K stages per tile).
   {
     const int mode = env_int("ACCEL_TC_MCAST", 0);
-    const bool legal = !P.pair && !P.aslab && splits == 1 && tiles_m >= 2 && num_sms >= 2;
+    const bool legal = !P.pair && !P.aslab && !P.epi1 && splits == 1 && tiles_m >= 2 && num_sms >= 2;
     const bool want_mc = mode == 1 || (mode < 0 && P.kiters >= env_int("ACCEL_TC_MCAST_KMIN", 8));
     P.mcast = (legal && want_mc) ? 1 : 0;
     if (P.mcast) {
@@ -1525,11 +1542,15 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
     }
   }
   if (P.tma_out) P.kchains = 1;
+  if (P.epi1 && !P.tma_out) {                                  // the output did not qualify for TMA stores after all: the direct
+    P.epi1 = 0;                                                //  epilogue needs no staging, the three stages stay
+    plan->smem = P.ring_bytes + 1024;
+  }
   // measured (profiles/r02_layer_epiw16.txt, five frames batched): res2 shortcut -16 %, res3 expand -9 %, res4 expand -2 %,
   // res5 expand (8 K stages) +4 % -> only where the tile's mainloop is at most ACCEL_TC_EPIW16_KMAX (4) K stages
   {
     const int m = env_int("ACCEL_TC_EPIW16", -1);
-    P.epiw16 = (P.tma_out && !P.mcast && !P.pair && (m == 1 || (m < 0 && P.kiters <= env_int("ACCEL_TC_EPIW16_KMAX", 4)))) ? 1 : 0;
+    P.epiw16 = (P.tma_out && !P.epi1 && !P.mcast && !P.pair && (m == 1 || (m < 0 && P.kiters <= env_int("ACCEL_TC_EPIW16_KMAX", 4)))) ? 1 : 0;
   }
   if (!ok) {
     delete plan;
@@ -1545,6 +1566,8 @@ TcPlan* tc_plan_create(const ConvParams& C, int num_sms, char* err, int errlen) 
       ce = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<false, false, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<true, false, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<false, false, false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEpi1);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<true, false, false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEpi1);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaxDynamic);
     if (ce != cudaSuccess) {
@@ -1600,7 +1623,11 @@ cudaError_t launch_conv_tc_ext(const TcPlan* plan, float* ext_nchw, float* ext_r
            : launch_k(conv_tc_kernel<N_, F_, T_>, grid, block, plan->smem, stream, P))
   const bool two = P.kchains == 2;
   const bool w16 = P.epiw16 && P.tma_out && !two && !P.fused && !P.epi.out_nchw && !P.epi.raw_nchw && !P.epi.out2_hi;
-  if (w16) {
+  if (P.epi1) {
+    if (two || P.fused || P.epi.out_nchw || P.epi.raw_nchw || P.epi.out2_hi) return cudaErrorInvalidValue;   // planned without them
+    e = P.ncat ? launch_k(conv_tc_kernel<true, false, false, 8, 1>, grid, block, plan->smem, stream, P)
+               : launch_k(conv_tc_kernel<false, false, false, 8, 1>, grid, block, plan->smem, stream, P);
+  } else if (w16) {
     const dim3 block16(64 + 32 * 16 + 32 * kDmaWarps);
     e = P.ncat ? launch_k(conv_tc_kernel<true, false, false, 16>, grid, block16, plan->smem, stream, P)
                : launch_k(conv_tc_kernel<false, false, false, 16>, grid, block16, plan->smem, stream, P);

@@ -629,6 +629,7 @@ bool Graph::resolve_conv(Op& op, std::string* err) {
   }
   E.nchw_hw = E.OHf * E.OWf;
   E.nchw_nb = op.epi.f32_frames;
+  P.ext_outputs = (op.epi.ext_out != X_NONE || op.epi.ext_raw != X_NONE) ? 1 : 0;
 
   // frames of a batched plan: every operand holds the same number of frames, stacked densely
   const int nb = ti.nb;

@@ -246,6 +246,24 @@ def test_conv_layer_weight_multicast(case, monkeypatch):
     assert (out - ref).abs().max().item() < _tol(ref)
 
 
+@pytest.mark.parametrize("knob", ["ACCEL_TC_EPI1", "ACCEL_TC_EPIW16"])
+@pytest.mark.parametrize("case", [(64, 256, 16, 128, 1, 1, 0, 1), (256, 1024, 9, 128, 1, 1, 0, 1), (512, 2048, 4, 128, 1, 1, 0, 1),
+                                  (128, 512, 32, 64, 1, 1, 0, 1), (256, 128, 8, 128, 1, 1, 0, 1)])
+def test_conv_layer_half_chunk_tma_epilogues(case, knob, monkeypatch):
+    """The two half-chunk variants of the TMA epilogue forced on for short-K layers with a residual: 16 epilogue warps
+    (conv_tc_kernel<..., 16>) and one chunk set with a third operand stage (conv_tc_kernel<..., 8, 1>, exactly 227 KB)."""
+    monkeypatch.setenv(knob, "1")
+    cin, cout, h, w, k, s, p, d = case
+    x = _rand(1, cin, h, w, seed=70)
+    wt = _rand(cout, cin, k, k, seed=71, scale=(2.0 / (cin * k * k)) ** 0.5)
+    scale, shift = torch.rand(cout, generator=torch.Generator().manual_seed(72)) + 0.5, _rand(cout, seed=73, scale=0.1)
+    ref = F.conv2d(x, wt, None, s, p, d) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = _rand(*ref.shape, seed=74)
+    ref = F.relu(ref + res)
+    out = E.conv_layer(x.to(DEV), wt, "conv", s, p, d, scale, shift, act=1, residual=res.to(DEV), engine=2).cpu()
+    assert (out - ref).abs().max().item() < _tol(ref)
+
+
 # Wide maps (W >= 128): one-row tiles, where the taps of a filter row share one TMA slab (TcParams::aslab, tap-shifted
 # shared-memory descriptors) -- incl. a right border that is not a multiple of the tile, dilation 2 (the offset convs of
 # res5), few and many output channels, a long K (two accumulation chains) and a transposed-conv phase set.
