@@ -53,13 +53,6 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_constant__ StemTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
-  // ONE ring of 2 * P.stages slots shared by the two producer groups, walked in the global block order q = tile * nblocks + b
-  // (slot q % S): a tile's last block no longer waits for the same tile's first block to be consumed, as it did when each
-  // group owned a private ring of S / 2 < nblocks slots.  A slot is produced by either group, so a producer may wait for
-  // a use of its slot that it has not followed itself; with ONE empty barrier per slot a parity wait could alias two uses
-  // back.  Each slot therefore has TWO empty barriers used alternately (use u = q / S commits to ebars[u & 1][s]): an alias
-  // would need the consumer to be four uses (4 * S blocks) behind, more than the two tiles + ring a group can run ahead.
-  __shared__ __align__(8) uint64_t ebars[2][kMaxStages];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,11 +68,9 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
   const uint32_t bfull = smem_u32(&bars[2 * kMaxStages + 4]);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2 * P.stages; ++s) {
-      mbar_init(full0 + 8 * s, 4);            // the 4 warps of the producer group that builds the block
+    for (int s = 0; s < 2 * P.stages; ++s) {  // ring g uses barriers [g*stages, (g+1)*stages)
+      mbar_init(full0 + 8 * s, 4);            // the 4 warps of the producer group that owns the ring
       mbar_init(empty0 + 8 * s, 1);
-      mbar_init(smem_u32(&ebars[0][s]), 1);
-      mbar_init(smem_u32(&ebars[1][s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -143,10 +134,11 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
       // ---- build the K blocks of this tile ----
       int c = 0, ky = 0;
       for (int b = 0; b < P.nblocks; ++b) {
-        const int S = 2 * P.stages;
-        const int q = k * P.nblocks + b;
-        const int s = q % S, u = q / S;
-        if (u > 0) mbar_wait(smem_u32(&ebars[(u - 1) & 1][s]), (uint32_t)((u - 1) >> 1) & 1u);   // use u - 1 of the slot consumed
+        // Each group is the only producer of its own ring, so the parity protocol never aliases.
+        const int q = (k >> 1) * P.nblocks + b;
+        const int s = grp * P.stages + q % P.stages;
+        const uint32_t ph = (uint32_t)(q / P.stages) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
         uint8_t* a_hi = gen0 + (stage0 - smem0) + (size_t)s * 32768 + (size_t)r * 128;
         uint8_t* a_lo = a_hi + 16384;
 #pragma unroll
@@ -198,10 +190,9 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem_base + (uint32_t)(acc * 64);
         for (int b = 0; b < P.nblocks; ++b) {
-          const int S = 2 * P.stages;
-          const int q = k * P.nblocks + b;
-          const int s = q % S, u = q / S;
-          mbar_wait(full0 + 8 * s, (uint32_t)u & 1u);
+          const int q = (k >> 1) * P.nblocks + b;
+          const int s = (k & 1) * P.stages + q % P.stages;
+          mbar_wait(full0 + 8 * s, (uint32_t)(q / P.stages) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = stage0 + s * 32768;
           const uint64_t ah = umma_desc(sa), al = umma_desc(sa + 16384);
@@ -218,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_tc_kernel(const __grid_const
                 umma_f16(d, al + adv, bh + adv, idesc, 1u);
               }
             }
-            umma_commit(smem_u32(&ebars[u & 1][s]));
+            umma_commit(empty0 + 8 * s);
           }
           __syncwarp();
         }
