@@ -139,6 +139,7 @@ PAIR4_SWEEP = [{"ACCEL_TC_PAIR": "1", "ACCEL_TC_DEBUG": str(d)} for d in (128, 3
 MC_SWEEP = [{"ACCEL_TC_MCAST": "0"}, {"ACCEL_TC_MCAST": "1"}, {"ACCEL_TC_MCAST": "1", "ACCEL_TC_DEBUG": "128"}, {"ACCEL_TC_MCAST": "0", "ACCEL_TC_DEBUG": "128"}]
 SPIN_SWEEP = [{}, {"ACCEL_TC_DEBUG": "8192"}, {"ACCEL_TC_DEBUG": "384"}, {"ACCEL_TC_DEBUG": str(384 + 8192)}]
 E1_SWEEP = [{"ACCEL_TC_EPI1": "0"}, {"ACCEL_TC_EPI1": "1"}, {"ACCEL_TC_EPI1": "0", "ACCEL_TC_EPIW16": "0"}]
+T0_SWEEP = [{}, {"ACCEL_TC_TMA_OUT": "0"}, {"ACCEL_TC_EPIW16": "1"}, {"ACCEL_TC_DEBUG": "128"}, {"ACCEL_TC_DEBUG": "256"}]
 W16_SWEEP = [{"ACCEL_TC_EPIW16": "0"}, {"ACCEL_TC_EPIW16": "1"}]
 RA_SWEEP = [{}] + [{"ACCEL_TC_RES_AHEAD": str(d)} for d in (2, 4, 6, 8, 12)]
 PF2_SWEEP = [{}, {"ACCEL_TC_PREFETCH": "4"}, {"ACCEL_TC_PREFETCH": "8"}, {"ACCEL_TC_PREFETCH": "260"}, {"ACCEL_TC_PREFETCH": "264"}, {"ACCEL_TC_PREFETCH": "2"}]
@@ -166,7 +167,7 @@ def main():
             sys.stderr.flush()
             E.conv_layer(x, wt, "conv", s, p, d, act=1, residual=r, engine=2)
             continue
-        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP, "pair2": PAIR2_SWEEP, "shortk": SHORTK_SWEEP, "s2": S2_SWEEP, "pf2": PF2_SWEEP, "ra": RA_SWEEP, "w16": W16_SWEEP, "e1": E1_SWEEP, "spin": SPIN_SWEEP, "mc": MC_SWEEP, "pair4": PAIR4_SWEEP, "pair3": PAIR3_SWEEP, "env": None}.get(a.sweep, SWEEP):
+        for knobs in {"debug": DEBUG_SWEEP, "pair": PAIR_SWEEP, "r02": R02_SWEEP, "one": ONE, "epi": EPI_SWEEP, "pf": PF_SWEEP, "epi2": EPI2_SWEEP, "ld": LD_SWEEP, "mma": MMA_SWEEP, "pair2": PAIR2_SWEEP, "shortk": SHORTK_SWEEP, "s2": S2_SWEEP, "pf2": PF2_SWEEP, "ra": RA_SWEEP, "w16": W16_SWEEP, "t0": T0_SWEEP, "e1": E1_SWEEP, "spin": SPIN_SWEEP, "mc": MC_SWEEP, "pair4": PAIR4_SWEEP, "pair3": PAIR3_SWEEP, "env": None}.get(a.sweep, SWEEP):
             for kk in ("ACCEL_TC_BN", "ACCEL_TC_SPLITS", "ACCEL_TC_KROT", "ACCEL_TC_STAGES", "ACCEL_TC_DEBUG", "ACCEL_TC_TMA_OUT", "ACCEL_TC_PAIR", "ACCEL_TC_ASLAB",
                        "ACCEL_TC_EPI1", "ACCEL_TC_EPIW16", "ACCEL_TC_MCAST", "ACCEL_TC_PREFETCH", "ACCEL_TC_RES_AHEAD", "ACCEL_TC_CHAINS", "ACCEL_TC_ASLAB_SA", "ACCEL_TC_ASLAB_BO", "ACCEL_TC_RES_PREFETCH", "ACCEL_TC_NCAT", "ACCEL_TC_WIDE_KMAX"):
                 os.environ.pop(kk, None)
