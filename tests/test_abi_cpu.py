@@ -107,3 +107,19 @@ def test_interval_forward_needs_a_plan(lib):
     assert lib.accel_rbranch_forward(h, C.c_void_p(16), None, None, None) != 0
     assert b"correction network" in lib.accel_last_error(h)
     lib.accel_destroy(h)
+
+
+def test_every_environment_switch_is_documented():
+    """Every ACCEL_* variable the library or the host package reads appears in DESIGN.md (section 5.6), README.md or
+    INTEGRATION.md: the switches are the record of what was measured and not adopted."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, "accel_b200", "csrc", "*")) + glob.glob(os.path.join(root, "accel_b200", "*.py")):
+        names |= set(re.findall(r'"(ACCEL_[A-Z0-9_]+)"', open(f).read()))
+    docs = "".join(open(os.path.join(root, d)).read() for d in ("DESIGN.md", "README.md", "INTEGRATION.md"))
+    missing = sorted(n for n in names if n not in docs and not any(n.startswith(p[:-1]) and p.endswith("*") for p in re.findall(r"ACCEL_[A-Z0-9_]+\*", docs)))
+    # `ACCEL_WARP_FUSED_PER_SM`, `_NST`, ... are listed with a shared prefix
+    missing = [n for n in missing if not (n.startswith("ACCEL_WARP_FUSED_") and "ACCEL_WARP_FUSED_PER_SM" in docs and ("`_" + n[len("ACCEL_WARP_FUSED_"):]) in docs)]
+    assert not missing, missing
